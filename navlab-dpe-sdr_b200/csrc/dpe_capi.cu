@@ -1,0 +1,372 @@
+// dpe_capi.cu -- the extern "C" boundary of libdpe_b200.so (include/dpe_b200.h).
+// Context lifetime, parameter upload, stage sequencing.  No torch types, no
+// exceptions across the boundary, no CPU fallback: every stage launches CUDA
+// kernels or returns a negative error code.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "dpe_internal.cuh"
+
+namespace dpe {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace dpe
+
+using namespace dpe;
+
+#define DPE_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) {                          \
+            dpe::set_error(__VA_ARGS__);        \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+template <typename Tp>
+static int dev_alloc(Tp** p, size_t n, bool zero = true) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(Tp));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) -> %s", n * sizeof(Tp), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? DPE_ENOMEM : DPE_ECUDA;
+    }
+    if (zero) {
+        e = cudaMemset(*p, 0, n * sizeof(Tp));
+        if (e != cudaSuccess) { set_error("cudaMemset -> %s", cudaGetErrorString(e)); return DPE_ECUDA; }
+    }
+    return DPE_OK;
+}
+#define DPE_ALLOC(ptr, n)                                 \
+    do {                                                  \
+        int rc__ = dev_alloc(&(ptr), (size_t)(n));        \
+        if (rc__) { dpe_ctx_destroy(c); return rc__; }    \
+    } while (0)
+
+extern "C" {
+
+const char* dpe_last_error(void) { return g_err; }
+int dpe_abi_version(void) { return DPE_ABI_VERSION; }
+
+int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
+    DPE_REQUIRE(out && cfg, DPE_EINVAL, "dpe_ctx_create: null argument");
+    *out = nullptr;
+    DPE_REQUIRE(cfg->abi_version == DPE_ABI_VERSION, DPE_EINVAL, "ABI version %u != %d", cfg->abi_version,
+                DPE_ABI_VERSION);
+    DPE_REQUIRE(cfg->S >= 64 && (cfg->S % 2) == 0 && cfg->S <= (1 << 26), DPE_EINVAL,
+                "S=%lld must be even, 64..2^26", (long long)cfg->S);
+    DPE_REQUIRE(cfg->fs > 0, DPE_EINVAL, "fs must be positive");
+    DPE_REQUIRE(cfg->max_chan >= 1 && cfg->max_chan <= DPE_MAX_CHAN, DPE_EINVAL, "max_chan out of range");
+    DPE_REQUIRE(cfg->G >= 1 && cfg->G < (1ll << 31), DPE_EINVAL, "G out of range");
+    DPE_REQUIRE(cfg->lpower >= 1, DPE_EINVAL, "lpower must be >= 1");
+    DPE_REQUIRE(cfg->lag_halfwidth >= 0 && cfg->lag_halfwidth <= 160, DPE_EINVAL, "lag_halfwidth 0..160");
+    DPE_REQUIRE(cfg->grid_offset >= 0 && cfg->G_total >= cfg->grid_offset + cfg->G, DPE_EINVAL,
+                "grid shard [%lld,+%lld) outside G_total=%lld", (long long)cfg->grid_offset, (long long)cfg->G,
+                (long long)cfg->G_total);
+    int ndev = 0;
+    DPE_CUDA(cudaGetDeviceCount(&ndev));
+    DPE_REQUIRE(cfg->device >= 0 && cfg->device < ndev, DPE_EINVAL, "device %d of %d", cfg->device, ndev);
+    DPE_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    DPE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    DPE_REQUIRE(prop.major == 10, DPE_EINVAL, "libdpe_b200 is built for sm_100a only; device is sm_%d%d",
+                prop.major, prop.minor);
+
+    dpe_ctx* c = new (std::nothrow) dpe_ctx();
+    DPE_REQUIRE(c, DPE_ENOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    c->sm_count = prop.multiProcessorCount;
+    c->S = cfg->S;
+    c->S_pad = ((cfg->S + kBfTile - 1) / kBfTile) * kBfTile;
+    c->G = cfg->G;
+    c->Gv = cfg->Gv;
+    c->W = cfg->lag_halfwidth > 0 ? cfg->lag_halfwidth : 32;
+    DPE_REQUIRE(2 * c->W + 2 < c->S, DPE_EINVAL, "lag window wider than the block");
+    c->NL = 2 * c->W + 2;
+    c->NLp = ((c->NL + kLagTile - 1) / kLagTile) * kLagTile;
+    c->H = ((c->W + 8 + 31) / 32) * 32;
+    c->nchunk = (int)((c->S + kCorrChunk - 1) / kCorrChunk);
+    c->maxC = cfg->max_chan;
+    c->T = cfg->time_dim > 0 ? cfg->time_dim : 1;
+    const size_t C = c->maxC, S = c->S, G = c->G;
+    const bool brute = (cfg->flags & DPE_FLAG_BRUTE_TILES) != 0;
+
+    DPE_ALLOC(c->iq_own, 2 * S + 16);
+    DPE_ALLOC(c->ca, DPE_MAX_CHAN * 1024);
+    DPE_ALLOC(c->ep, 1);
+    DPE_ALLOC(c->sat, C * c->T * 8);
+    DPE_ALLOC(c->xw, C * S);
+    DPE_ALLOC(c->rs, C * S);
+    if (cfg->flags & DPE_FLAG_KEEP_CHIP_IDX) DPE_ALLOC(c->chip_idx, C * S);
+    DPE_ALLOC(c->idx_next, C);
+    DPE_ALLOC(c->no_flip, C);
+    DPE_ALLOC(c->cpart, C * c->nchunk * 2 * c->NLp);
+    DPE_ALLOC(c->cs, C * c->NL);
+    DPE_ALLOC(c->grid, G * 4);
+    DPE_ALLOC(c->scores, G);
+    DPE_ALLOC(c->blk_partial, ((G + kReduceBlock - 1) / kReduceBlock) * 8);
+    DPE_ALLOC(c->partial, kPartialLen);
+    DPE_ALLOC(c->zval, 16);     // the reference's EKF_PassMeas reads 16; keep the slack
+    DPE_ALLOC(c->rval, 64);
+    DPE_ALLOC(c->result, 16);
+    if (brute) {
+        c->bx_stride = skewX(c->S_pad);
+        c->br_stride = skewR(c->S_pad + 2 * c->H);
+        DPE_ALLOC(c->bxr, C * c->bx_stride);
+        DPE_ALLOC(c->bxi, C * c->bx_stride);
+        DPE_ALLOC(c->brr, C * c->br_stride);
+        const size_t NB = 2 * c->W + 1;
+        DPE_REQUIRE(sizeof(int32_t) * (2 * C * NB + 1) <= 48 * 1024, DPE_EINVAL,
+                    "max_chan * (2W+1) too large for the bucket scan");
+        c->max_groups = (int64_t)(C * ((G + kBfNC - 1) / kBfNC + NB) + C * kBfWarps);
+        DPE_ALLOC(c->pair_k, C * G);
+        DPE_ALLOC(c->pair_a, C * G);
+        DPE_ALLOC(c->pair_v, C * G);
+        DPE_ALLOC(c->hist, C * NB);
+        DPE_ALLOC(c->cursor, C * NB);
+        DPE_ALLOC(c->bucket_base, C * NB);
+        DPE_ALLOC(c->hdr, c->max_groups * 4);
+        DPE_ALLOC(c->ent_j, c->max_groups * kBfNC);
+        DPE_ALLOC(c->ent_a, c->max_groups * kBfNC);
+        DPE_ALLOC(c->n_groups, 1);
+    }
+    c->iq = c->iq_own;
+    int rc = launch_gen_ca(c, 0);
+    if (rc) { dpe_ctx_destroy(c); return rc; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error("ctx_create sync -> %s", cudaGetErrorString(e));
+        dpe_ctx_destroy(c);
+        return DPE_ECUDA;
+    }
+    *out = c;
+    return DPE_OK;
+}
+
+int dpe_ctx_destroy(dpe_ctx* c) {
+    if (!c) return DPE_OK;
+    cudaSetDevice(c->cfg.device);
+    void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
+                    c->cpart, c->cs, c->bxr, c->bxi, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
+                    c->zval, c->rval, c->result, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
+                    c->bucket_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
+                    c->vgrid, c->vscores, c->carr};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete c;
+    return DPE_OK;
+}
+
+int dpe_grid_set(dpe_ctx* c, const double* enu_dt, int64_t G, void* stream) {
+    DPE_REQUIRE(c && enu_dt, DPE_EINVAL, "dpe_grid_set: null argument");
+    DPE_REQUIRE(G == c->G, DPE_EINVAL, "dpe_grid_set: G=%lld, context holds %lld", (long long)G, (long long)c->G);
+    DPE_CUDA(cudaMemcpyAsync(c->grid, enu_dt, sizeof(double) * 4 * G, cudaMemcpyDefault, (cudaStream_t)stream));
+    return DPE_OK;
+}
+
+int dpe_vel_grid_set(dpe_ctx* c, const double* venu_ddt, int64_t Gv, void* stream) {
+    (void)venu_ddt; (void)Gv; (void)stream;
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    set_error("velocity manifold not built in this round (SURVEY.md section 8 f-1)");
+    return DPE_ESTATE;
+}
+
+int dpe_block_stage(dpe_ctx* c, const int16_t* iq, int64_t S, void* stream) {
+    DPE_REQUIRE(c && iq, DPE_EINVAL, "dpe_block_stage: null argument");
+    DPE_REQUIRE(S == c->S, DPE_EINVAL, "block of %lld samples, context built for %lld", (long long)S,
+                (long long)c->S);
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, iq);
+    bool on_device = (e == cudaSuccess) && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+    if (e != cudaSuccess) cudaGetLastError();
+    if (on_device && at.device == c->cfg.device && (reinterpret_cast<uintptr_t>(iq) & 15) == 0) {
+        c->iq = iq;                                   // zero copy
+    } else {
+        DPE_CUDA(cudaMemcpyAsync(c->iq_own, iq, sizeof(int16_t) * 2 * S, cudaMemcpyDefault,
+                                 (cudaStream_t)stream));
+        c->iq = c->iq_own;
+    }
+    c->have_block = 1;
+    c->have_prepare = c->have_corr = c->have_scores = 0;
+    return DPE_OK;
+}
+
+int dpe_epoch_set(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, void* stream) {
+    DPE_REQUIRE(c && ep && sat_states, DPE_EINVAL, "dpe_epoch_set: null argument");
+    DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
+    EpochDev& h = c->ep_host;
+    memset(&h, 0, sizeof(h));
+    h.C = ep->C;
+    h.doppler_sign = ep->doppler_sign;
+    h.rx_time = ep->rx_time;
+    memcpy(h.center, ep->center, sizeof(h.center));
+    memcpy(h.R, ep->enu2ecef, sizeof(h.R));
+    for (int i = 0; i < ep->C; ++i) {
+        DPE_REQUIRE(ep->prn[i] >= 1 && ep->prn[i] <= DPE_MAX_CHAN, DPE_EINVAL, "PRN %d out of range", ep->prn[i]);
+        DPE_REQUIRE(ep->fc[i] > 0, DPE_EINVAL, "code frequency of channel %d not positive", i);
+        h.prn[i] = ep->prn[i];
+        h.rc_start[i] = ep->rc_start[i]; h.ri_start[i] = ep->ri_start[i];
+        h.fc[i] = ep->fc[i]; h.fi[i] = ep->fi[i];
+        h.cp_start[i] = ep->cp_start[i]; h.cp_ref[i] = ep->cp_ref[i];
+        h.rc_end[i] = ep->rc_end[i]; h.cp_end[i] = ep->cp_end[i]; h.cp_ref_tow[i] = ep->cp_ref_tow[i];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DPE_CUDA(cudaMemcpyAsync(c->ep, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    DPE_CUDA(cudaMemcpyAsync(c->sat, sat_states, sizeof(double) * 8 * (size_t)ep->C * c->T,
+                             cudaMemcpyDefault, s));
+    c->epoch_C = ep->C;
+    c->have_epoch = 1;
+    c->have_prepare = c->have_corr = c->have_scores = 0;
+    return DPE_OK;
+}
+
+int dpe_replica_prepare(dpe_ctx* c, void* stream) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(c->have_block && c->have_epoch, DPE_ESTATE, "replica_prepare before block_stage/epoch_set");
+    int rc = launch_prepare(c, (cudaStream_t)stream);
+    if (rc) return rc;
+    c->have_prepare = 1;
+    c->have_corr = 0;
+    return DPE_OK;
+}
+
+int dpe_correlogram(dpe_ctx* c, void* stream) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(c->have_prepare, DPE_ESTATE, "correlogram before replica_prepare");
+    int rc = launch_correlogram(c, (cudaStream_t)stream);
+    if (rc) return rc;
+    c->have_corr = 1;
+    return DPE_OK;
+}
+
+int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(c->have_corr, DPE_ESTATE, "score_pos before correlogram");
+    DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
+    int rc;
+    if (score_mode == DPE_SCORE_LOOKUP) {
+        rc = launch_score_lookup(c, sat_mode, (cudaStream_t)stream);
+    } else if (score_mode == DPE_SCORE_BRUTE) {
+        DPE_REQUIRE(c->cfg.flags & DPE_FLAG_BRUTE_TILES, DPE_ESTATE,
+                    "context created without DPE_FLAG_BRUTE_TILES");
+        rc = launch_score_brute(c, sat_mode, (cudaStream_t)stream);
+    } else {
+        set_error("bad score_mode %d", score_mode);
+        return DPE_EINVAL;
+    }
+    if (rc) return rc;
+    c->have_scores = 1;
+    return DPE_OK;
+}
+
+int dpe_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, void* stream) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(c->have_scores, DPE_ESTATE, "estimate before score_pos");
+    DPE_REQUIRE(est_mode == DPE_EST_ARGMAX || est_mode == DPE_EST_WEIGHTED, DPE_EINVAL, "bad est_mode");
+    DPE_REQUIRE(!gathered || nranks >= 1, DPE_EINVAL, "nranks must be >= 1");
+    return launch_estimate(c, est_mode, gathered, nranks, (cudaStream_t)stream);
+}
+
+int dpe_score_vel(dpe_ctx* c, void* stream) {
+    (void)stream;
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    set_error("velocity manifold not built in this round (SURVEY.md section 8 f-1)");
+    return DPE_ESTATE;
+}
+
+int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
+    DPE_REQUIRE(c && out, DPE_EINVAL, "null argument");
+    double r[16];
+    DPE_CUDA(cudaMemcpyAsync(r, c->result, sizeof(r), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DPE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < 8; ++i) out->z[i] = r[i];
+    out->max_score = r[8];
+    out->sum_score = r[9];
+    out->argmax = (int64_t)r[10];
+    out->out_of_window = (int64_t)r[11];
+    out->vel_max_score = r[12];
+    out->vel_argmax = (int64_t)r[13];
+    return DPE_OK;
+}
+
+int dpe_epoch_run(dpe_ctx* c, const int16_t* iq_host, const dpe_epoch* ep, const double* sat_states,
+                  int score_mode, int est_mode, int with_vel, dpe_result* out, void* stream) {
+    int rc;
+    if ((rc = dpe_block_stage(c, iq_host, c ? c->S : 0, stream))) return rc;
+    if ((rc = dpe_epoch_set(c, ep, sat_states, stream))) return rc;
+    if ((rc = dpe_replica_prepare(c, stream))) return rc;
+    if ((rc = dpe_correlogram(c, stream))) return rc;
+    const int sat_mode = (est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
+    if ((rc = dpe_score_pos(c, score_mode, sat_mode, stream))) return rc;
+    if ((rc = dpe_estimate(c, est_mode, nullptr, 1, stream))) return rc;
+    if (with_vel && (rc = dpe_score_vel(c, stream))) return rc;
+    return dpe_result_fetch(c, out, stream);
+}
+
+const void* dpe_dev_ptr(dpe_ctx* c, int which) {
+    if (!c) return nullptr;
+    switch (which) {
+        case DPE_PTR_SAMPLES: return c->iq;
+        case DPE_PTR_CODE_SCORES: return c->cs;
+        case DPE_PTR_POS_SCORES: return c->scores;
+        case DPE_PTR_ZVAL: return c->zval;
+        case DPE_PTR_RVAL: return c->rval;
+        case DPE_PTR_GRID: return c->grid;
+        case DPE_PTR_PARTIAL: return c->partial;
+        case DPE_PTR_CHIP_IDX: return c->chip_idx;
+        case DPE_PTR_XW: return c->xw;
+        case DPE_PTR_CARR_SCORES: return c->carr;
+        case DPE_PTR_VEL_SCORES: return c->vscores;
+        case DPE_PTR_VEL_GRID: return c->vgrid;
+        case DPE_PTR_REPLICA_SIGN: return c->rs;
+        case DPE_PTR_CA_TABLE: return c->ca;
+        default: return nullptr;
+    }
+}
+
+int dpe_debug_channel_flags(dpe_ctx* c, int32_t* idx_next, int32_t* no_flip, int C) {
+    DPE_REQUIRE(c && idx_next && no_flip, DPE_EINVAL, "null argument");
+    DPE_REQUIRE(C >= 1 && C <= c->maxC, DPE_EINVAL, "bad C");
+    DPE_CUDA(cudaDeviceSynchronize());
+    DPE_CUDA(cudaMemcpy(idx_next, c->idx_next, sizeof(int32_t) * C, cudaMemcpyDeviceToHost));
+    DPE_CUDA(cudaMemcpy(no_flip, c->no_flip, sizeof(int32_t) * C, cudaMemcpyDeviceToHost));
+    return DPE_OK;
+}
+
+int dpe_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, int64_t* f_idx, double* alpha,
+                   void* stream) {
+    DPE_REQUIRE(c && f_idx && alpha, DPE_EINVAL, "null argument");
+    DPE_REQUIRE(c->have_epoch, DPE_ESTATE, "debug_bins before epoch_set");
+    DPE_REQUIRE(i0 >= 0 && n >= 1 && i0 + n <= c->G, DPE_EINVAL, "candidate range outside the grid");
+    const size_t cnt = (size_t)n * c->epoch_C;
+    if (c->dbg_f) { cudaFree(c->dbg_f); cudaFree(c->dbg_alpha); c->dbg_f = nullptr; c->dbg_alpha = nullptr; }
+    int rc;
+    if ((rc = dev_alloc(&c->dbg_f, cnt))) return rc;
+    if ((rc = dev_alloc(&c->dbg_alpha, cnt))) return rc;
+    if ((rc = launch_debug_bins(c, i0, n, sat_mode, (cudaStream_t)stream))) return rc;
+    DPE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    DPE_CUDA(cudaMemcpy(f_idx, c->dbg_f, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost));
+    DPE_CUDA(cudaMemcpy(alpha, c->dbg_alpha, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+    return DPE_OK;
+}
+
+int dpe_debug_read(dpe_ctx* c, int which, size_t offset, void* dst, size_t nbytes) {
+    DPE_REQUIRE(c && dst, DPE_EINVAL, "null argument");
+    const char* p = static_cast<const char*>(dpe_dev_ptr(c, which));
+    DPE_REQUIRE(p, DPE_ESTATE, "buffer %d not allocated", which);
+    DPE_CUDA(cudaDeviceSynchronize());
+    DPE_CUDA(cudaMemcpy(dst, p + offset, nbytes, cudaMemcpyDeviceToHost));
+    return DPE_OK;
+}
+
+int64_t dpe_launch_count(dpe_ctx* c) { return c ? c->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// dpe_geom.cuh -- device helpers shared by the lookup and brute-force scoring
+// kernels: candidate ENU->ECEF, geometric back-calculation of the code-phase
+// bin (cudarecv/modules/src/batchcorrmanifold.cu:1760-1812) and the
+// deterministic block reduction.
+#pragma once
+#include "dpe_internal.cuh"
+
+namespace dpe {
+
+struct Cand { double px, py, pz, pt; };
+
+// batchcorrmanifold.cu:1760-1763
+__device__ __forceinline__ Cand cand_ecef(const EpochDev& e, const double* __restrict__ g4) {
+    const double2 a = *reinterpret_cast<const double2*>(g4);
+    const double2 b = *reinterpret_cast<const double2*>(g4 + 2);
+    Cand p;
+    p.px = e.R[0] * a.x + e.R[1] * a.y + e.R[2] * b.x + e.center[0];
+    p.py = e.R[3] * a.x + e.R[4] * a.y + e.R[5] * b.x + e.center[1];
+    p.pz = e.R[6] * a.x + e.R[7] * a.y + e.R[8] * b.x + e.center[2];
+    p.pt = b.y + e.center[3];
+    return p;
+}
+
+// batchcorrmanifold.cu:1779-1791: geometric back-calculation of the code phase
+// and its (fractional) fft-shifted correlogram index for channel c.
+__device__ __forceinline__ double code_index(const EpochDev& e, const Cand& p, const double* __restrict__ sat,
+                                             int c, double fs, double S) {
+    double los[3] = {sat[0] - p.px, sat[1] - p.py, sat[2] - p.pz};
+    const double range = norm(3, los);
+    const double pr = range - K_C * sat[3] + p.pt;
+    const double tx = e.rx_time - pr / K_C;
+    const double frac = tx - e.cp_ref_tow[c] - ((e.cp_end[c] - e.cp_ref[c]) * K_T_CA);
+    const double bc_rc = frac * K_F_CA;
+    const double rc0 = bc_rc - e.rc_end[c];
+    return (fs / e.fc[c]) * (-rc0) + S / 2.0;
+}
+
+struct Bin { int64_t f; double wf, wg; int l; bool ok; };   // v = cs[l+1]*wg + cs[l]*wf
+
+// batchcorrmanifold.cu:1795-1812 (row offset S*chan added before the floor, as there)
+__device__ __forceinline__ Bin make_bin(double idx_base, int c, int S, int W) {
+    Bin b;
+    const bool valid = (idx_base < (double)S) && (idx_base > 0.0);
+    const double idxo = idx_base + (double)((int64_t)S * c);
+    const double f = floor(idxo), g = floor(idxo + 1.0);
+    b.f = (int64_t)f;
+    b.wg = idxo - f;
+    b.wf = g - idxo;
+    const int64_t l = b.f - (int64_t)S * c - S / 2 + W;
+    b.l = (int)l;
+    b.ok = valid && l >= 0 && l <= 2 * (int64_t)W;
+    return b;
+}
+
+__device__ __forceinline__ double mag_pow(double re, double im, int L) {
+    const double m = sqrt(re * re + im * im);
+    if (L == 1) return m;
+    if (L == 2) return m * m;
+    return pow(m, (double)L);
+}
+
+// Block-level reduction of (score-weighted sums, sum, max/argmax, out-of-window)
+// with warp shuffles + shared memory, fixed order => bit-reproducible.
+// out[0..3]=sum s*p, [4]=sum s, [5]=max, [6]=global argmax (lowest on ties), [7]=oow
+__device__ __forceinline__ void block_reduce_store(double score, int64_t gidx, const Cand& p, bool active,
+                                                   int oow, double* __restrict__ out) {
+    __shared__ double sh[kReduceBlock / 32][8];
+    double v[5] = {0, 0, 0, 0, 0};
+    double mx = -1.0, mi = 9.0e18, oo = (double)oow;
+    if (active) {
+        v[0] = score * p.px; v[1] = score * p.py; v[2] = score * p.pz; v[3] = score * p.pt; v[4] = score;
+        mx = score; mi = (double)gidx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        oo += __shfl_xor_sync(0xffffffffu, oo, o);
+        const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const double omi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (omx > mx || (omx == mx && omi < mi)) { mx = omx; mi = omi; }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sh[warp][k] = v[k];
+        sh[warp][5] = mx; sh[warp][6] = mi; sh[warp][7] = oo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = sh[0][k];
+        for (int w = 1; w < kReduceBlock / 32; ++w) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) r[k] += sh[w][k];
+            r[7] += sh[w][7];
+            if (sh[w][5] > r[5] || (sh[w][5] == r[5] && sh[w][6] < r[6])) { r[5] = sh[w][5]; r[6] = sh[w][6]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[(size_t)blockIdx.x * 8 + k] = r[k];
+    }
+}
+
+}  // namespace dpe

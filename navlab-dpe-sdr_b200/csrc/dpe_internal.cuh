@@ -1,0 +1,129 @@
+// dpe_internal.cuh -- shared declarations of libdpe_b200 (sm_100a only).
+//
+// Data layout in HBM (one context = one flow = one GPU):
+//   iq        int16  [2*S]              staged 20 ms block (interleaved I,Q)
+//   ca        int8   [37][1024]         C/A chips, +/-1  (BCS chipsCACode_d)
+//   xw        float2 [C][S]             wiped samples x[n]*conj(carrier)      (natural order)
+//   rs        int8   [C][S]             no-flip replica sign r[n]
+//   bxr/bxi   float  [C][skewX(S_pad)]  wiped samples, re / im planes, float4-skewed for the
+//                                       brute-force kernel's conflict-free LDS.128
+//   brr       float  [C][skewR(S_pad+2H)] chosen replica (flip applied) with circular halo,
+//                                       word-skewed for conflict-free lane-strided LDS.32
+//   cpart     double2[C][NCHUNK][2][NLp] per-chunk partial correlograms (A: n<idxNext, B: rest)
+//   cs        double2[C][NL]            fft-shifted "CodeScores" window, lag k = l - W
+//   grid      double [G][4]             candidates (ENU metres + clock metres)
+//   scores    double [G]                "PosScores"
+//   pair_*    per (channel, candidate) lag / alpha / v for the brute-force path
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/dpe_b200.h"
+
+// utils/inc/consthelper.h:5-27 of the reference
+#define K_C      (299792458.0)
+#define K_PI     (3.1415926535898)
+#define K_F_L1   (1.57542e9)
+#define K_F_CA   (1.023e6)
+#define K_L_CA   (1023)
+#define K_T_CA   (0.001)
+#define K_OEDOT  (7.2921151467e-5)
+
+namespace dpe {
+
+constexpr int kCorrChunk = 1024;       // samples per partial-correlogram block
+constexpr int kLagTile = 8;            // lags per thread in the correlogram kernel
+constexpr int kPartialLen = DPE_PARTIAL_LEN;
+constexpr int kReduceBlock = 256;
+
+// brute-force kernel geometry
+constexpr int kBfNC = 16;              // candidates per warp (one group)
+constexpr int kBfNS = 8;               // contiguous samples per lane per chunk
+constexpr int kBfChunk = 32 * kBfNS;   // samples per warp-chunk (256)
+constexpr int kBfTile = 1024;          // samples per TMA stage
+constexpr int kBfWarps = 8;            // consumer warps per CTA
+constexpr int kBfStages = 4;
+
+// Device copy of the per-epoch parameters (+ values derived on the device).
+struct EpochDev {
+    int32_t C, doppler_sign;
+    double rx_time;
+    double center[8];
+    double R[9];
+    uint8_t prn[DPE_MAX_CHAN + 3];
+    double rc_start[DPE_MAX_CHAN], ri_start[DPE_MAX_CHAN], fc[DPE_MAX_CHAN], fi[DPE_MAX_CHAN];
+    int32_t cp_start[DPE_MAX_CHAN], cp_ref[DPE_MAX_CHAN];
+    double rc_end[DPE_MAX_CHAN];
+    int32_t cp_end[DPE_MAX_CHAN], cp_ref_tow[DPE_MAX_CHAN];
+};
+
+// word-skew for the replica plane: lanes stride 8 words -> stride 9 (conflict-free LDS.32)
+__host__ __device__ inline int64_t skewR(int64_t x) { return x + (x >> 3); }
+// float4-skew for the sample planes: one pad float4 every 8 float4 (conflict-free LDS.128
+// when lane l reads float4 2l and 2l+1)
+__host__ __device__ inline int64_t skewX(int64_t x) { return x + 4 * (x >> 5); }
+
+}  // namespace dpe
+
+struct dpe_ctx {
+    dpe_cfg cfg;
+    int64_t S, S_pad, G, Gv;
+    int32_t W, NL, NLp, H;             // lag half width, lags, padded lags, replica halo
+    int32_t nchunk;                    // correlogram chunks per channel
+    int32_t maxC, T;
+    int sm_count;
+    // device buffers
+    int16_t* iq_own; const int16_t* iq;
+    int8_t* ca;
+    dpe::EpochDev* ep;
+    double* sat;                       // [C][T][8]
+    float2* xw; int8_t* rs; int16_t* chip_idx;
+    int32_t* idx_next; int32_t* no_flip;
+    double2* cpart; double2* cs;
+    float *bxr, *bxi, *brr;
+    int64_t bx_stride, br_stride;      // per-channel plane strides (floats)
+    double* grid; double* scores;
+    double* blk_partial; int32_t n_blk_partial;
+    double* partial; double* zval; double* rval; double* result;  // result: device mirror of dpe_result
+    // brute-force work lists
+    int16_t* pair_k; float* pair_a; double2* pair_v;   // [C][G]
+    int32_t* hist;                     // [C][NB] counts, NB = 2W+1
+    int32_t* cursor; int64_t* bucket_base;
+    int32_t* hdr;                      // group headers {c, krel, n, pad}
+    int32_t* ent_j; float* ent_a;      // bucketed entries
+    int32_t* n_groups;                 // device scalar: total groups (multiple of kBfWarps)
+    int64_t max_groups;
+    // debug
+    int64_t* dbg_f; double* dbg_alpha;
+    // velocity (section 8 f-1)
+    double* vgrid; double* vscores; double2* carr;
+    // state
+    int have_block, have_epoch, have_prepare, have_corr, have_scores;
+    int epoch_C;
+    int64_t launches;
+    dpe::EpochDev ep_host;
+};
+
+namespace dpe {
+void set_error(const char* fmt, ...);
+#define DPE_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            dpe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                 \
+                           cudaGetErrorString(e__));                                     \
+            return DPE_ECUDA;                                                            \
+        }                                                                                \
+    } while (0)
+
+// launchers (each returns DPE_OK / DPE_ECUDA and bumps ctx->launches)
+int launch_gen_ca(dpe_ctx* c, cudaStream_t s);
+int launch_prepare(dpe_ctx* c, cudaStream_t s);
+int launch_correlogram(dpe_ctx* c, cudaStream_t s);
+int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
+int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
+int launch_reduce_partials(dpe_ctx* c, cudaStream_t s);
+size_t brute_smem_bytes(int H);
+int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, cudaStream_t s);
+int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStream_t s);
+}  // namespace dpe

@@ -1,0 +1,192 @@
+// dpe_score.cu -- candidate scoring on the position-clock grid (sm_100a):
+//   geometry -> correlogram bin (FP64, same expression order as the reference),
+//   lookup + lerp + sum_prn |.|^L, fused block-level arg-max / weighted sums,
+//   and the final estimate.
+//
+// Replaces (cudarecv/modules/src/batchcorrmanifold.cu):
+//   BCM_PosMeasML :1710-1828, thrust::max_element :2589, BCM_MakePosMeas :1977-2016,
+//   BCM_PosMeasReduction :816-1056, BCM_ReduceAndPosMeas :1365-1510.
+// The reference runs <<<8,64>>> grid-stride + a separate device-wide max + a
+// 1-block kernel with host syncs in between; here scoring, arg-max and weighted
+// accumulation are one pass with a deterministic two-level reduction.
+#include "dpe_geom.cuh"
+
+namespace dpe {
+
+// ---------------------------------------------------------------------------
+// k_score_lookup: one thread per candidate (the reference's BCM_PosMeasML with
+// the arg-max / weighted accumulation fused in).  sat_mode: middle time-grid
+// state (:1773-1775) or per-time-index state (:865-873).
+// ---------------------------------------------------------------------------
+template <int SAT_MODE>
+__global__ void __launch_bounds__(kReduceBlock)
+k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
+               const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
+               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial) {
+    __shared__ EpochDev e;
+    for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < G;
+    double score = 0.0;
+    int oow = 0;
+    Cand p = {0, 0, 0, 0};
+    if (active) {
+        p = cand_ecef(e, grid + 4 * j);
+        const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
+        for (int c = 0; c < e.C; ++c) {
+            const double idx = code_index(e, p, sat + ((size_t)c * T + it) * 8, c, fs, (double)S);
+            const Bin b = make_bin(idx, c, S, W);
+            if (b.ok) {
+                const double2 lo = cs[(size_t)c * NL + b.l], hi = cs[(size_t)c * NL + b.l + 1];
+                const double re = hi.x * b.wg + lo.x * b.wf;     // :1808-1812
+                const double im = hi.y * b.wg + lo.y * b.wf;
+                score += mag_pow(re, im, lpower);                // :1816
+            } else {
+                ++oow;
+            }
+        }
+        scores[j] = score;
+    }
+    block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
+}
+
+// Bins only (parity tests: "code-phase bins bit-exact").
+template <int SAT_MODE>
+__global__ void k_debug_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
+                             const double* __restrict__ sat, double fs, int S, int W, int T,
+                             int64_t i0, int64_t n, int64_t grid_offset, int64_t* __restrict__ f_idx,
+                             double* __restrict__ alpha) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const EpochDev& e = *ep;
+    const int64_t j = i0 + t;
+    const Cand p = cand_ecef(e, grid + 4 * j);
+    const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
+    for (int c = 0; c < e.C; ++c) {
+        const double idx = code_index(e, p, sat + ((size_t)c * T + it) * 8, c, fs, (double)S);
+        const Bin b = make_bin(idx, c, S, W);
+        f_idx[t * e.C + c] = b.f;
+        alpha[t * e.C + c] = b.wg;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Estimate: level-2 reduction of the block partials (one CTA, fixed order) and
+// the final zVal / RVal.  partial[0..7] as block partials, [8..11] = ECEF / clock
+// of this rank's arg-max candidate.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kReduceBlock)
+k_reduce_partials(const double* __restrict__ blk, int n_blk, const double* __restrict__ grid,
+                  const EpochDev* __restrict__ ep, int64_t grid_offset, double* __restrict__ partial) {
+    __shared__ double sh[kReduceBlock][8];
+    double r[8] = {0, 0, 0, 0, 0, -1.0, 9.0e18, 0};
+    for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
+        const double* q = blk + (size_t)b * 8;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] += q[k];
+        r[7] += q[7];
+        if (q[5] > r[5] || (q[5] == r[5] && q[6] < r[6])) { r[5] = q[5]; r[6] = q[6]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = r[k];
+    __syncthreads();
+    for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            double* a = sh[threadIdx.x];
+            const double* b = sh[threadIdx.x + s];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a[k] += b[k];
+            a[7] += b[7];
+            if (b[5] > a[5] || (b[5] == a[5] && b[6] < a[6])) { a[5] = b[5]; a[6] = b[6]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) partial[k] = sh[0][k];
+        for (int k = 8; k < kPartialLen; ++k) partial[k] = 0.0;
+        if (sh[0][5] >= 0.0) {
+            const int64_t j = (int64_t)sh[0][6] - grid_offset;
+            const Cand p = cand_ecef(*ep, grid + 4 * j);         // BCM_MakePosMeas :1990-2000
+            partial[8] = p.px; partial[9] = p.py; partial[10] = p.pz; partial[11] = p.pt;
+        }
+    }
+}
+
+// One thread: combine the per-rank partials (rank order = ascending grid offset,
+// so "first maximum" = lowest global index, like thrust::max_element / np.argmax).
+// result layout mirrors dpe_result (doubles; indices exact below 2^53).
+__global__ void k_finalize(const double* __restrict__ parts, int nranks, int est_mode,
+                           double* __restrict__ zval, double* __restrict__ rval, double* __restrict__ res) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double sum[5] = {0, 0, 0, 0, 0}, oow = 0, mx = -1.0, mi = 9.0e18;
+    int best = -1;
+    for (int r = 0; r < nranks; ++r) {
+        const double* q = parts + (size_t)r * kPartialLen;
+        for (int k = 0; k < 5; ++k) sum[k] += q[k];
+        oow += q[7];
+        if (q[5] > mx || (q[5] == mx && q[6] < mi)) { mx = q[5]; mi = q[6]; best = r; }
+    }
+    double z[4] = {0, 0, 0, 0};
+    if (est_mode == DPE_EST_WEIGHTED) {                       // BCM_ReduceAndPosMeas :1497-1500
+        for (int k = 0; k < 4; ++k) z[k] = sum[k] / sum[4];
+    } else if (best >= 0) {                                   // BCM_MakePosMeas
+        for (int k = 0; k < 4; ++k) z[k] = parts[(size_t)best * kPartialLen + 8 + k];
+    }
+    for (int k = 0; k < 4; ++k) zval[k] = z[k];
+    for (int r = 0; r < 4; ++r)                               // RVal rows 0-3 <- identity (:2008-2014)
+        for (int k = 0; k < 8; ++k) rval[r * 8 + k] = (r == k) ? 1.0 : 0.0;
+    res[0] = z[0]; res[1] = z[1]; res[2] = z[2]; res[3] = z[3];
+    res[8] = mx; res[9] = sum[4]; res[10] = mi; res[11] = oow;
+}
+
+// ---------------------------------------------------------------------------
+int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
+    const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
+    if (sat_mode == DPE_SAT_PER_TIME)
+        k_score_lookup<DPE_SAT_PER_TIME><<<nblk, kReduceBlock, 0, s>>>(
+            c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
+            c->cfg.grid_offset, c->scores, c->blk_partial);
+    else
+        k_score_lookup<DPE_SAT_MIDDLE><<<nblk, kReduceBlock, 0, s>>>(
+            c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
+            c->cfg.grid_offset, c->scores, c->blk_partial);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    c->n_blk_partial = nblk;
+    return launch_reduce_partials(c, s);
+}
+
+int launch_reduce_partials(dpe_ctx* c, cudaStream_t s) {
+    k_reduce_partials<<<1, kReduceBlock, 0, s>>>(c->blk_partial, c->n_blk_partial, c->grid, c->ep,
+                                                 c->cfg.grid_offset, c->partial);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
+int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, cudaStream_t s) {
+    const double* parts = gathered ? gathered : c->partial;
+    if (!gathered) nranks = 1;
+    k_finalize<<<1, 32, 0, s>>>(parts, nranks, est_mode, c->zval, c->rval, c->result);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
+int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStream_t s) {
+    const int nb = (int)((n + 255) / 256);
+    if (sat_mode == DPE_SAT_PER_TIME)
+        k_debug_bins<DPE_SAT_PER_TIME><<<nb, 256, 0, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S, c->W,
+                                                         c->T, i0, n, c->cfg.grid_offset, c->dbg_f, c->dbg_alpha);
+    else
+        k_debug_bins<DPE_SAT_MIDDLE><<<nb, 256, 0, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S, c->W,
+                                                       c->T, i0, n, c->cfg.grid_offset, c->dbg_f, c->dbg_alpha);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
+}  // namespace dpe

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Generate golden vectors from the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Runs on a GPU box: writes a synthetic L1 C/A capture + handoff CSV + grid CSV in
+the reference's own file formats (synth.Scenario.write_files), runs the
+reference's DPEFlow through oracle/_ref/ref_dpe (built by oracle/Makefile from
+/root/reference/cudarecv, sm_100a), and packs what the reference consumed and
+produced per epoch into one .npz:
+
+  inputs  (cuChanMgr / cuEKF outputs before the epoch): prn, rc_start, ri_start,
+          rc_end, fc, fi, cp_start, cp_end, cp_ref, cp_ref_tow, sat_states [C*T][8],
+          enu2ecef, x_kk1, rx_time, iq (the int16 block SampleBlock handed over)
+  outputs (after BatchCorrManifold::Update): code_scores_win [C][2W+2] complex,
+          pos_scores [G], zval [8], and x_k1k1 after the epoch.
+
+The .npz is committed under tests/golden/ (this script is how it was made); the
+CPU tests pin oracle/dpe_oracle.py against it and the GPU tests pin the CUDA path.
+
+usage: python oracle/make_golden_ref.py --out gpurun_out/golden [--epochs 3] [--n 9]
+"""
+import argparse
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dpe_pkg  # noqa: E402
+
+synth = dpe_pkg.submodule("synth")
+
+I32 = ("cp_ref", "cp_start", "cp_end", "cp_ref_tow")
+F64 = ("rx_time", "tx_time", "rc_start", "ri_start", "rc_end", "ri_end", "fc", "fi", "sat_states", "sat_raw",
+       "enu2ecef", "x_kk1", "x_k1k1", "code_scores_win", "pos_scores", "zval", "time_grid")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/golden")
+    ap.add_argument("--work", default="/tmp/refrun")
+    ap.add_argument("--epochs", type=int, default=3)
+    ap.add_argument("--n", type=int, default=9)
+    ap.add_argument("--W", type=int, default=32)
+    ap.add_argument("--offset", type=float, nargs=4, default=[7.0, -4.0, 3.0, 8.0],
+                    help="ECEF x,y,z and clock (m) offset of the handed-off state from the truth")
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dpe")
+    if not os.path.exists(exe):
+        sys.exit("oracle/_ref/ref_dpe missing: run `make -C oracle` where /root/reference exists")
+
+    sc = synth.Scenario()
+    grid, _ = synth.uniform_grid(a.n, (5.0, 5.0, 5.0, 6.0))
+    files = sc.write_files(a.work, a.epochs + 2, grid=grid)
+    # hand the reference a state that is `offset` away from the truth so the arg-max is not the centre
+    lines = open(files["handoff"]).read().splitlines()
+    for i, l in enumerate(lines):
+        if l.startswith("X_ECEF,"):
+            v = [float(x) for x in l.split(",")[1:]]
+            for k in range(4):
+                v[k] += a.offset[k]
+            lines[i] = "X_ECEF," + ",".join(repr(x) for x in v)
+    open(files["handoff"], "w").write("\n".join(lines) + "\n")
+
+    dump = os.path.join(a.work, "dump")
+    cmd = [exe, files["dat"], files["handoff"], files["rinex"], files["grid"], str(a.n), "5", str(a.epochs), dump,
+           str(a.W), repr(sc.cfg.fs), "1"]
+    print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    open(os.path.join(a.out, "ref_run.log"), "w").write(r.stdout)
+    print(r.stdout[-3000:])
+    if r.returncode != 0:
+        sys.exit("reference run failed (%d)" % r.returncode)
+
+    meta = dict(l.split() for l in open(os.path.join(dump, "meta.txt")))
+    C, CT = int(meta["C"]), int(meta["CT"])
+    pack = dict(C=C, T=CT // C, S=sc.S, fs=sc.cfg.fs, W=a.W, n=a.n, epochs=a.epochs, grid=grid,
+                offset=np.array(a.offset), truth0=sc.rx_state(sc.cfg.rx_time0))
+    for e in range(a.epochs):
+        def rd(name, dt):
+            return np.fromfile(os.path.join(dump, "e%03d_%s.bin" % (e, name)), dtype=dt)
+        for k in F64:
+            pack["e%d_%s" % (e, k)] = rd(k, np.float64)
+        for k in I32:
+            pack["e%d_%s" % (e, k)] = rd(k, np.int32)
+        pack["e%d_prn" % e] = rd("prn", np.uint8)
+        pack["e%d_iq" % e] = rd("iq", np.int16)
+    path = os.path.join(a.out, "ref_epochs_n%d.npz" % a.n)
+    np.savez_compressed(path, **pack)
+    print("wrote", path, os.path.getsize(path), "bytes")
+    if os.path.exists(os.path.join(dump, "XFile.csv")):
+        open(os.path.join(a.out, "ref_XFile.csv"), "w").write(open(os.path.join(dump, "XFile.csv")).read())
+
+
+if __name__ == "__main__":
+    main()

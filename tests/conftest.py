@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import dpe_pkg
+    return dpe_pkg.load()
+
+
+@pytest.fixture(scope="session")
+def capi():
+    import dpe_pkg
+    return dpe_pkg.submodule("capi")
+
+
+@pytest.fixture(scope="session")
+def synth():
+    import dpe_pkg
+    return dpe_pkg.submodule("synth")
