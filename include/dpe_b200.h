@@ -189,6 +189,13 @@ int dpe_replica_prepare(dpe_ctx* ctx, void* stream);
  * DPE_FLAG_BRUTE_TILES is set.                                                   */
 int dpe_correlogram(dpe_ctx* ctx, void* stream);
 
+/* dpe_code_scores_set: use a correlogram produced elsewhere (e.g. the reference's own
+ * BatchCorrScores feeding this BatchCorrManifold through the "CodeScores" port,
+ * batchcorrmanifold.cu:2261): `cs` = [C][2W+2] complex doubles (host or device), entry
+ * l of channel c = fft-shifted bin S/2 - W + l of that channel's row.  Marks the
+ * correlogram stage done; needs dpe_epoch_set first.  Lookup scoring only.       */
+int dpe_code_scores_set(dpe_ctx* ctx, const double* cs, int C, void* stream);
+
 /* dpe_score_pos: score every candidate of this context (BCM_PosMeasML /
  * BCM_PosMeasReduction scoring part) into "PosScores" and reduce the block-level
  * arg-max / weighted sums into the per-rank partial (DPE_PTR_PARTIAL):
@@ -233,6 +240,26 @@ int dpe_debug_bins(dpe_ctx* ctx, int64_t i0, int64_t n, int sat_mode, int64_t* f
 int dpe_debug_read(dpe_ctx* ctx, int which, size_t offset, void* dst, size_t nbytes);
 /* number of kernels launched by this context since creation                     */
 int64_t dpe_launch_count(dpe_ctx* ctx);
+
+/* ---- per-stage device timing (bench.py's roofline.achieved) --------------------
+ * When enabled, every stage is bracketed by cudaEvents on the stream it is
+ * launched on.  dpe_profile_read synchronises, adds the elapsed milliseconds of
+ * every bracket recorded since the last read to ms[stage] (DPE_N_STAGES entries),
+ * the number of brackets to count[stage], and clears the record.                 */
+enum {
+    DPE_STAGE_PREPARE = 0,       /* k_prepare                                        */
+    DPE_STAGE_CORRELOGRAM = 1,   /* k_corr_partial + k_corr_finalize (+ replica plane)*/
+    DPE_STAGE_LOOKUP = 2,        /* k_score_lookup + k_reduce_partials               */
+    DPE_STAGE_BRUTE_BINS = 3,    /* k_pair_bins + k_bucket_scan + k_scatter          */
+    DPE_STAGE_BRUTE_CORR = 4,    /* k_brute (the north-star kernel) alone            */
+    DPE_STAGE_BRUTE_SCORE = 5,   /* k_score_pairs + k_reduce_partials                */
+    DPE_STAGE_ESTIMATE = 6,      /* k_finalize                                       */
+    DPE_N_STAGES = 8
+};
+int dpe_profile_enable(dpe_ctx* ctx, int on);
+int dpe_profile_read(dpe_ctx* ctx, double* ms, int64_t* count);
+/* valid (candidate, PRN) pairs the last brute-force pass correlated (synchronises) */
+int64_t dpe_brute_pairs(dpe_ctx* ctx);
 
 /* ---- micro-benchmarks (roofline denominators measured in the same run) -------
  * fp32: dependent-free FFMA2 streams on every SM; returns achieved TFLOP/s.

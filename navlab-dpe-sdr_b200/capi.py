@@ -26,12 +26,16 @@ SAT_MIDDLE, SAT_PER_TIME = 0, 1
  PTR_CHIP_IDX, PTR_XW, PTR_CARR_SCORES, PTR_VEL_SCORES, PTR_VEL_GRID, PTR_REPLICA_SIGN,
  PTR_CA_TABLE) = range(14)
 FLAG_KEEP_CHIP_IDX, FLAG_BRUTE_TILES, FLAG_KEEP_BINS = 1, 2, 4
+(STAGE_PREPARE, STAGE_CORRELOGRAM, STAGE_LOOKUP, STAGE_BRUTE_BINS, STAGE_BRUTE_CORR, STAGE_BRUTE_SCORE,
+ STAGE_ESTIMATE) = range(7)
 
 EXPORTS = (
     "dpe_ctx_create", "dpe_ctx_destroy", "dpe_last_error", "dpe_abi_version", "dpe_grid_set",
     "dpe_vel_grid_set", "dpe_block_stage", "dpe_epoch_set", "dpe_replica_prepare", "dpe_correlogram",
+    "dpe_code_scores_set",
     "dpe_score_pos", "dpe_estimate", "dpe_score_vel", "dpe_result_fetch", "dpe_epoch_run", "dpe_dev_ptr",
-    "dpe_debug_channel_flags", "dpe_debug_bins", "dpe_debug_read", "dpe_launch_count", "dpe_microbench_fp32",
+    "dpe_debug_channel_flags", "dpe_debug_bins", "dpe_debug_read", "dpe_launch_count", "dpe_profile_enable", "dpe_profile_read",
+    "dpe_brute_pairs", "dpe_microbench_fp32",
     "dpe_microbench_hbm")
 
 
@@ -88,6 +92,7 @@ def load_library(path: str | None = None):
     lib.dpe_epoch_set.argtypes = [vp, C.POINTER(DpeEpoch), vp, vp]
     lib.dpe_replica_prepare.argtypes = [vp, vp]
     lib.dpe_correlogram.argtypes = [vp, vp]
+    lib.dpe_code_scores_set.argtypes = [vp, vp, i32, vp]
     lib.dpe_score_pos.argtypes = [vp, i32, i32, vp]
     lib.dpe_estimate.argtypes = [vp, i32, vp, i32, vp]
     lib.dpe_score_vel.argtypes = [vp, vp]
@@ -100,6 +105,10 @@ def load_library(path: str | None = None):
     lib.dpe_debug_read.argtypes = [vp, i32, C.c_size_t, vp, C.c_size_t]
     lib.dpe_launch_count.argtypes = [vp]
     lib.dpe_launch_count.restype = i64
+    lib.dpe_profile_enable.argtypes = [vp, i32]
+    lib.dpe_profile_read.argtypes = [vp, vp, vp]
+    lib.dpe_brute_pairs.argtypes = [vp]
+    lib.dpe_brute_pairs.restype = i64
     lib.dpe_microbench_fp32.argtypes = [i32, i32, C.POINTER(C.c_double)]
     lib.dpe_microbench_hbm.argtypes = [i32, C.c_size_t, C.POINTER(C.c_double)]
     if path is None:
@@ -201,6 +210,12 @@ class Context:
     def correlogram(self, stream=0):
         _check(self.lib, self.lib.dpe_correlogram(self.h, C.c_void_p(stream)))
 
+    def code_scores_set(self, cs, stream=0):
+        """cs: complex128 [C][2W+2] window of an externally produced correlogram."""
+        cs = np.ascontiguousarray(cs, dtype=np.complex128)
+        self._cs = cs
+        _check(self.lib, self.lib.dpe_code_scores_set(self.h, _ptr(cs), cs.shape[0], C.c_void_p(stream)))
+
     def score_pos(self, score_mode=SCORE_LOOKUP, sat_mode=SAT_MIDDLE, stream=0):
         _check(self.lib, self.lib.dpe_score_pos(self.h, score_mode, sat_mode, C.c_void_p(stream)))
 
@@ -229,6 +244,19 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.dpe_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        _check(self.lib, self.lib.dpe_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """(ms[8], count[8]) accumulated per stage since the last read (synchronises)."""
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = np.zeros(8, dtype=np.int64)
+        _check(self.lib, self.lib.dpe_profile_read(self.h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt
+
+    def brute_pairs(self) -> int:
+        return int(self.lib.dpe_brute_pairs(self.h))
 
     def channel_flags(self, n_chan):
         a = np.zeros(n_chan, dtype=np.int32)

@@ -198,9 +198,12 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
         const int c = h.x, k = h.y - W, n_valid = h.z;
-        float al[kBfNC];
+        float2 al[kBfNC];                                   // (alpha, alpha): FFMA2 has no scalar broadcast
 #pragma unroll
-        for (int j = 0; j < kBfNC; ++j) al[j] = (j < n_valid) ? ent_a[(size_t)g * kBfNC + j] : 0.f;
+        for (int j = 0; j < kBfNC; ++j) {
+            const float a = (j < n_valid) ? ent_a[(size_t)g * kBfNC + j] : 0.f;
+            al[j] = make_float2(a, a);
+        }
         float2 are[kBfNC], aim[kBfNC];
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) { are[j] = make_float2(0.f, 0.f); aim[j] = make_float2(0.f, 0.f); }
@@ -224,9 +227,12 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
                 float rr[kBfNS + 1];
 #pragma unroll
                 for (int i = 0; i <= kBfNS; ++i) rr[i] = prr[off[i] + ch * 288];
-                float d[kBfNS];
+                float2 dp[4], r0[4];                        // (r1 - r0) and r0 of samples 2q, 2q+1
 #pragma unroll
-                for (int i = 0; i < kBfNS; ++i) d[i] = rr[i] - rr[i + 1];
+                for (int q = 0; q < 4; ++q) {
+                    dp[q] = make_float2(rr[2 * q] - rr[2 * q + 1], rr[2 * q + 1] - rr[2 * q + 2]);
+                    r0[q] = make_float2(rr[2 * q + 1], rr[2 * q + 2]);
+                }
                 const float2 xre[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w),
                                        make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
                 const float2 xim[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
@@ -235,9 +241,8 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
                 for (int j = 0; j < kBfNC; ++j) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float2 bp;                          // blended replica of samples 2q, 2q+1
-                        bp.x = fmaf(al[j], d[2 * q], rr[2 * q + 1]);
-                        bp.y = fmaf(al[j], d[2 * q + 1], rr[2 * q + 2]);
+                        // blended replica of samples 2q, 2q+1: r0 + alpha (r1 - r0)
+                        const float2 bp = __ffma2_rn(al[j], dp[q], r0[q]);
                         are[j] = __ffma2_rn(xre[q], bp, are[j]);
                         aim[j] = __ffma2_rn(xim[q], bp, aim[j]);
                     }
@@ -299,6 +304,7 @@ size_t brute_smem_bytes(int H) {
 
 int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int C = c->epoch_C, NB = 2 * c->W + 1, nbuck = C * NB;
+    prof_begin(c, DPE_STAGE_BRUTE_BINS, s);
     DPE_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * nbuck, s));
     DPE_CUDA(cudaMemsetAsync(c->cursor, 0, sizeof(int32_t) * nbuck, s));
     const int nblk = (int)((c->G + 255) / 256);
@@ -321,6 +327,7 @@ int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
                                  reinterpret_cast<int32_t*>(c->ent_j), c->ent_a);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
+    prof_end(c, s);
     return DPE_OK;
 }
 
@@ -333,19 +340,24 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
         DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
+    prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
     k_brute<<<c->sm_count, (kBfWarps + 1) * 32, smem, s>>>(
         c->bxr, c->bxi, c->brr, c->bx_stride, c->br_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
         c->H, c->W);
+    prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
+    prof_begin(c, DPE_STAGE_BRUTE_SCORE, s);
     const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
     k_score_pairs<<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_k, c->pair_v, c->cfg.lpower, c->G,
                                                 c->cfg.grid_offset, c->scores, c->blk_partial);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
-    return launch_reduce_partials(c, s);
+    rc = launch_reduce_partials(c, s);
+    prof_end(c, s);
+    return rc;
 }
 
 }  // namespace dpe

@@ -20,6 +20,19 @@ void set_error(const char* fmt, ...) {
 
 using namespace dpe;
 
+namespace dpe {
+void prof_begin(dpe_ctx* c, int stage, cudaStream_t s) {
+    if (!c->prof_on || c->prof_n >= kProfMax) return;
+    c->prof_stage[c->prof_n] = stage;
+    cudaEventRecord(c->prof_ev[2 * c->prof_n], s);
+}
+void prof_end(dpe_ctx* c, cudaStream_t s) {
+    if (!c->prof_on || c->prof_n >= kProfMax) return;
+    cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], s);
+    c->prof_n++;
+}
+}  // namespace dpe
+
 #define DPE_REQUIRE(cond, code, ...)            \
     do {                                        \
         if (!(cond)) {                          \
@@ -160,6 +173,11 @@ int dpe_ctx_destroy(dpe_ctx* c) {
                     c->vgrid, c->vscores, c->carr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (c->prof_ev) {
+        for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(c->prof_ev[i]);
+        delete[] c->prof_ev;
+        delete[] c->prof_stage;
+    }
     delete c;
     return DPE_OK;
 }
@@ -246,6 +264,17 @@ int dpe_correlogram(dpe_ctx* c, void* stream) {
     return DPE_OK;
 }
 
+int dpe_code_scores_set(dpe_ctx* c, const double* cs, int C, void* stream) {
+    DPE_REQUIRE(c && cs, DPE_EINVAL, "null argument");
+    DPE_REQUIRE(c->have_epoch, DPE_ESTATE, "code_scores_set before epoch_set");
+    DPE_REQUIRE(C == c->epoch_C, DPE_EINVAL, "C=%d, epoch has %d channels", C, c->epoch_C);
+    DPE_CUDA(cudaMemcpyAsync(c->cs, cs, sizeof(double2) * (size_t)C * c->NL, cudaMemcpyDefault,
+                             (cudaStream_t)stream));
+    c->have_corr = 1;
+    c->have_prepare = 0;       // the brute-force planes do not belong to this correlogram
+    return DPE_OK;
+}
+
 int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
     DPE_REQUIRE(c->have_corr, DPE_ESTATE, "score_pos before correlogram");
@@ -256,6 +285,8 @@ int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
     } else if (score_mode == DPE_SCORE_BRUTE) {
         DPE_REQUIRE(c->cfg.flags & DPE_FLAG_BRUTE_TILES, DPE_ESTATE,
                     "context created without DPE_FLAG_BRUTE_TILES");
+        DPE_REQUIRE(c->have_prepare, DPE_ESTATE,
+                    "brute-force scoring needs this context's own replica_prepare + correlogram");
         rc = launch_score_brute(c, sat_mode, (cudaStream_t)stream);
     } else {
         set_error("bad score_mode %d", score_mode);
@@ -368,5 +399,46 @@ int dpe_debug_read(dpe_ctx* c, int which, size_t offset, void* dst, size_t nbyte
 }
 
 int64_t dpe_launch_count(dpe_ctx* c) { return c ? c->launches : -1; }
+
+int dpe_profile_enable(dpe_ctx* c, int on) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    if (on && !c->prof_ev) {
+        c->prof_ev = new (std::nothrow) cudaEvent_t[2 * kProfMax];
+        c->prof_stage = new (std::nothrow) int[kProfMax];
+        DPE_REQUIRE(c->prof_ev && c->prof_stage, DPE_ENOMEM, "out of host memory");
+        for (int i = 0; i < 2 * kProfMax; ++i) DPE_CUDA(cudaEventCreate(&c->prof_ev[i]));
+    }
+    c->prof_on = on ? 1 : 0;
+    c->prof_n = 0;
+    return DPE_OK;
+}
+
+int dpe_profile_read(dpe_ctx* c, double* ms, int64_t* count) {
+    DPE_REQUIRE(c && ms && count, DPE_EINVAL, "null argument");
+    DPE_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < c->prof_n; ++i) {
+        float t = 0.f;
+        DPE_CUDA(cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        ms[c->prof_stage[i]] += t;
+        count[c->prof_stage[i]] += 1;
+    }
+    c->prof_n = 0;
+    return DPE_OK;
+}
+
+int64_t dpe_brute_pairs(dpe_ctx* c) {
+    if (!c || !c->hist) return -1;
+    const int n = c->epoch_C * (2 * c->W + 1);
+    int32_t* h = new (std::nothrow) int32_t[n];
+    if (!h) return -1;
+    int64_t tot = -1;
+    if (cudaDeviceSynchronize() == cudaSuccess &&
+        cudaMemcpy(h, c->hist, sizeof(int32_t) * n, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        tot = 0;
+        for (int i = 0; i < n; ++i) tot += h[i];
+    }
+    delete[] h;
+    return tot;
+}
 
 }  // extern "C"

@@ -35,6 +35,7 @@ constexpr int kCorrChunk = 1024;       // samples per partial-correlogram block
 constexpr int kLagTile = 8;            // lags per thread in the correlogram kernel
 constexpr int kPartialLen = DPE_PARTIAL_LEN;
 constexpr int kReduceBlock = 256;
+constexpr int kProfMax = 8192;
 
 // brute-force kernel geometry
 constexpr int kBfNC = 16;              // candidates per warp (one group)
@@ -102,6 +103,10 @@ struct dpe_ctx {
     int epoch_C;
     int64_t launches;
     dpe::EpochDev ep_host;
+    // per-stage event brackets (dpe_profile_*)
+    int prof_on; int prof_n;                 // brackets recorded since the last read
+    cudaEvent_t* prof_ev;                    // [2 * kProfMax]
+    int* prof_stage;                         // [kProfMax]
 };
 
 namespace dpe {
@@ -115,6 +120,10 @@ void set_error(const char* fmt, ...);
             return DPE_ECUDA;                                                            \
         }                                                                                \
     } while (0)
+
+// stage brackets: no-ops unless dpe_profile_enable(ctx, 1)
+void prof_begin(dpe_ctx* c, int stage, cudaStream_t s);
+void prof_end(dpe_ctx* c, cudaStream_t s);
 
 // launchers (each returns DPE_OK / DPE_ECUDA and bumps ctx->launches)
 int launch_gen_ca(dpe_ctx* c, cudaStream_t s);

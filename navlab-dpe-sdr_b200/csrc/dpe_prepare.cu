@@ -272,9 +272,11 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S, S_pad = (int)c->S_pad;
     const bool brute = (c->cfg.flags & DPE_FLAG_BRUTE_TILES) != 0;
     dim3 grid((S_pad / 4 + 255) / 256, c->epoch_C);
+    prof_begin(c, DPE_STAGE_PREPARE, s);
     k_prepare<<<grid, 256, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, brute ? S_pad : ((S + 3) / 4) * 4,
                                    c->xw, c->rs, c->chip_idx, c->idx_next,
                                    brute ? c->bxr : nullptr, brute ? c->bxi : nullptr, c->bx_stride);
+    prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;
@@ -286,6 +288,7 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
     const size_t smem = (size_t)(nx + (nx >> 3) + 1) * sizeof(float2) +
                         (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float);
     dim3 grid(c->nchunk, c->epoch_C);
+    prof_begin(c, DPE_STAGE_CORRELOGRAM, s);
     k_corr_partial<<<grid, 256, smem, s>>>(c->xw, c->rs, c->idx_next, c->ep, S, c->W, c->NLp,
                                            c->nchunk, c->cpart);
     c->launches++;
@@ -303,6 +306,7 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
         c->launches++;
         DPE_CUDA(cudaGetLastError());
     }
+    prof_end(c, s);
     return DPE_OK;
 }
 

@@ -145,6 +145,7 @@ __global__ void k_finalize(const double* __restrict__ parts, int nranks, int est
 // ---------------------------------------------------------------------------
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
+    prof_begin(c, DPE_STAGE_LOOKUP, s);
     if (sat_mode == DPE_SAT_PER_TIME)
         k_score_lookup<DPE_SAT_PER_TIME><<<nblk, kReduceBlock, 0, s>>>(
             c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
@@ -156,7 +157,9 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
-    return launch_reduce_partials(c, s);
+    const int rc = launch_reduce_partials(c, s);
+    prof_end(c, s);
+    return rc;
 }
 
 int launch_reduce_partials(dpe_ctx* c, cudaStream_t s) {
@@ -170,7 +173,9 @@ int launch_reduce_partials(dpe_ctx* c, cudaStream_t s) {
 int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, cudaStream_t s) {
     const double* parts = gathered ? gathered : c->partial;
     if (!gathered) nranks = 1;
+    prof_begin(c, DPE_STAGE_ESTIMATE, s);
     k_finalize<<<1, 32, 0, s>>>(parts, nranks, est_mode, c->zval, c->rval, c->result);
+    prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;

@@ -225,14 +225,18 @@ class Scenario:
                     doppler_sign=cfg.doppler_sign, **ch)
 
     # ---- files in the reference's formats ------------------------------------
-    def write_files(self, out_dir, n_blocks, grid=None):
-        """samples .dat (int16 I,Q), handoff CSV, grid CSV ('x,y,z,delta_t')."""
+    def write_files(self, out_dir, n_blocks, grid=None, handoff_block=0):
+        """samples .dat (int16 I,Q), handoff CSV, grid CSV ('x,y,z,delta_t').
+
+        ``handoff_block``: block the handoff (and ``bytes_read``) refers to.  The
+        reference treats ``lseek(fd, StartByte) == 0`` as a failure
+        (sampleblock.cu:123-128), so its own runs need handoff_block >= 1."""
         os.makedirs(out_dir, exist_ok=True)
         dat = os.path.join(out_dir, "synthetic_l1ca_%dkHz.dat" % int(self.cfg.fs / 1e3))
         with open(dat, "wb") as f:
             for b in range(n_blocks):
                 f.write(self.block(b).tobytes())
-        h = self.handoff(0)
+        h = self.handoff(handoff_block)
         csv = os.path.join(out_dir, "handoff_params_synth.csv")
         with open(csv, "w") as f:
             f.write("rxTime,%r\n" % float(h["rxTime"]))

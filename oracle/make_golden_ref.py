@@ -53,7 +53,10 @@ def main():
 
     sc = synth.Scenario()
     grid, _ = synth.uniform_grid(a.n, (5.0, 5.0, 5.0, 6.0))
-    files = sc.write_files(a.work, a.epochs + 2, grid=grid)
+    # StartByte 0 is rejected by the reference (sampleblock.cu:123-128) -> hand off at block 1.  The file
+    # must outlast the reader's 32-block read-ahead: at EOF the reference frees its buffers while the
+    # flow may still be using the last one (sampleblock.cu:449-462).
+    files = sc.write_files(a.work, a.epochs + 40, grid=grid, handoff_block=1)
     # hand the reference a state that is `offset` away from the truth so the arg-max is not the centre
     lines = open(files["handoff"]).read().splitlines()
     for i, l in enumerate(lines):
@@ -76,8 +79,8 @@ def main():
 
     meta = dict(l.split() for l in open(os.path.join(dump, "meta.txt")))
     C, CT = int(meta["C"]), int(meta["CT"])
-    pack = dict(C=C, T=CT // C, S=sc.S, fs=sc.cfg.fs, W=a.W, n=a.n, epochs=a.epochs, grid=grid,
-                offset=np.array(a.offset), truth0=sc.rx_state(sc.cfg.rx_time0))
+    pack = dict(first_block=1, C=C, T=CT // C, S=sc.S, fs=sc.cfg.fs, W=a.W, n=a.n, epochs=a.epochs, grid=grid,
+                offset=np.array(a.offset), truth0=sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T))
     for e in range(a.epochs):
         def rd(name, dt):
             return np.fromfile(os.path.join(dump, "e%03d_%s.bin" % (e, name)), dtype=dt)

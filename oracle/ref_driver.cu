@@ -18,6 +18,7 @@
 // usage: ref_dpe <samples.dat> <handoff.csv> <rinex.n> <grid.csv> <pos_dim> <vel_dim>
 //                <epochs> <out_dir> [lag_halfwidth=32] [fs=2.5e6]
 #include <cuda_runtime.h>
+#include <cufft.h>
 #include <sys/stat.h>
 #include <sys/time.h>
 #include <unistd.h>
@@ -161,6 +162,15 @@ int main(int argc, char** argv) {
     mkdir(out.c_str(), 0755);
     if (!getenv("HOME")) setenv("HOME", "/tmp", 1);
 
+    // Load cuFFT's kernels before the flow starts: the reference creates its plans inside the first
+    // Update (batchcorrscores.cu:1007-1035) and its reader thread gives up after 1.5 s
+    // (sampleblock.cu:432); a cold library load on a fresh box can take longer than that.
+    {
+        cufftHandle warm;
+        if (cufftPlan1d(&warm, 50000, CUFFT_Z2Z, 8) == CUFFT_SUCCESS) cufftDestroy(warm);
+        if (cufftPlan1d(&warm, 524288, CUFFT_Z2Z, 8) == CUFFT_SUCCESS) cufftDestroy(warm);
+        cudaDeviceSynchronize();
+    }
     RefHarness flow;
     if (flow.LoadFlow(NULL)) { fprintf(stderr, "LoadFlow failed\n"); return 1; }
     int rc = 0;
