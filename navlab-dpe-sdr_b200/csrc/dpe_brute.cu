@@ -10,13 +10,15 @@
 // Mapping (B200, FP32-pipe bound; the block and the replica live in SMEM / L2):
 //   * pairs are bucketed by (PRN, k) so that the 16 pairs of a warp ("group")
 //     share the replica window; lanes own runs of 8 contiguous samples, the 16
-//     candidates live in registers: per sample-pair 1 FFMA (blend) + 1 FFMA2
-//     (complex accumulate, packed over two consecutive samples);
+//     candidates live in registers: per pair of consecutive samples 1 FFMA2 (blend,
+//     alpha as broadcast operand) + 2 FFMA2 (re / im accumulate) -- scalar FFMA tops out
+//     at 49.7 TFLOP/s on B200, FFMA2 at 67.9 (dpe_microbench_fp32);
 //   * sample / replica tiles of 1024 samples are staged by 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier, 4 stages) issued by a dedicated producer warp;
+//     (cp.async.bulk + mbarrier full/empty pairs, 4 stages);
 //     the planes are stored pre-skewed in HBM so the staged tiles are read with
 //     conflict-free LDS.128 (samples) and lane-stride-9 LDS.32 (replica);
-//   * persistent CTAs (one per SM), 8 consumer warps + 1 producer warp;
+//   * persistent CTAs (one per SM), 8 warps (2 per scheduler, up to 255 registers); the TMA
+//     refill duty rotates over the warps instead of living in a 9th producer warp;
 //   * lane partials are combined with warp shuffles in FP64.
 #include "dpe_geom.cuh"
 
@@ -56,11 +58,13 @@ k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, co
 // ---------------------------------------------------------------------------
 // pass 2: bucket -> group layout.  Every bucket is padded to whole groups of
 // kBfNC pairs, every channel to whole CTAs of kBfWarps groups.
+//   k_bucket_scan    (1 CTA)  group base of every bucket, total group count
+//   k_group_headers  (many)   {channel, lag, valid pairs} of every group
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep, int W,
-              int64_t* __restrict__ bucket_base, int4* __restrict__ hdr, int32_t* __restrict__ n_groups,
-              int64_t max_groups) {
+              int32_t* __restrict__ group_base, int64_t* __restrict__ bucket_base,
+              int32_t* __restrict__ n_groups, int64_t max_groups) {
     extern __shared__ int32_t sm[];        // [nbuck] counts, then [nbuck+1] group bases
     const int NB = 2 * W + 1;
     const int C = ep->C;
@@ -82,35 +86,53 @@ k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep,
         *n_groups = (g <= max_groups) ? g : 0;
     }
     __syncthreads();
-    const int total = gb[nbuck];
-    if (total > max_groups) return;
+    for (int i = threadIdx.x; i <= nbuck; i += blockDim.x) group_base[i] = gb[i];
     for (int i = threadIdx.x; i < nbuck; i += blockDim.x) bucket_base[i] = (int64_t)gb[i] * kBfNC;
-    for (int g = threadIdx.x; g < total; g += blockDim.x) {
-        int lo = 0, hi = nbuck - 1;            // last bucket with gb <= g
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (gb[mid] <= g) lo = mid; else hi = mid - 1;
-        }
-        const int q = g - gb[lo];
-        const int ng = (cnt[lo] + kBfNC - 1) / kBfNC;
-        int n = 0;
-        if (q < ng) { n = cnt[lo] - q * kBfNC; if (n > kBfNC) n = kBfNC; }
-        hdr[g] = make_int4(lo / NB, lo % NB, n, 0);
-    }
 }
 
-// pass 3: scatter the pairs into their bucket
+__global__ void __launch_bounds__(256)
+k_group_headers(const int32_t* __restrict__ hist, const int32_t* __restrict__ group_base,
+                const EpochDev* __restrict__ ep, int W, int4* __restrict__ hdr, int64_t max_groups) {
+    extern __shared__ int32_t sm[];        // [nbuck+1] group bases
+    const int NB = 2 * W + 1;
+    const int nbuck = ep->C * NB;
+    for (int i = threadIdx.x; i <= nbuck; i += blockDim.x) sm[i] = group_base[i];
+    __syncthreads();
+    const int total = sm[nbuck];
+    if (total > max_groups) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    int lo = 0, hi = nbuck - 1;                // last bucket with base <= g
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sm[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int q = g - sm[lo];
+    const int cnt = hist[lo];
+    const int ng = (cnt + kBfNC - 1) / kBfNC;
+    int n = 0;
+    if (q < ng) { n = cnt - q * kBfNC; if (n > kBfNC) n = kBfNC; }
+    hdr[g] = make_int4(lo / NB, lo % NB, n, 0);
+}
+
+// pass 3: scatter the pairs into their bucket.  Neighbouring candidates mostly share the
+// lag, so the slot counter is bumped once per (warp, bucket) and the lanes take ranks.
 __global__ void __launch_bounds__(256)
 k_scatter(const int16_t* __restrict__ pair_k, const float* __restrict__ pair_a, int64_t G, int W,
           const int64_t* __restrict__ bucket_base, int32_t* __restrict__ cursor,
           int32_t* __restrict__ ent_j, float* __restrict__ ent_a) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
-    if (j >= G) return;
-    const int k = pair_k[(size_t)c * G + j];
-    if (k < 0) return;
-    const int i = c * (2 * W + 1) + k;
-    const int64_t pos = bucket_base[i] + atomicAdd(&cursor[i], 1);
+    const int lane = threadIdx.x & 31;
+    const int k = (j < G) ? (int)pair_k[(size_t)c * G + j] : -1;
+    const int key = (k >= 0) ? c * (2 * W + 1) + k : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader && key >= 0) base = atomicAdd(&cursor[key], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key < 0) return;
+    const int64_t pos = bucket_base[key] + base + __popc(peers & ((1u << lane) - 1u));
     ent_j[pos] = (int32_t)j;
     ent_a[pos] = pair_a[(size_t)c * G + j];
 }
@@ -143,10 +165,48 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 constexpr int kXTileF = kBfTile + kBfTile / 8;            // 1152 floats: float4-skewed 1024-sample plane tile
 
+// Register image of one warp-chunk (256 samples): per lane 8 contiguous samples (re / im as
+// pairs for FFMA2) and the 9 replica values r[m-k-1 .. m-k+7] its blend needs.
+struct BruteChunk {
+    float4 a0, a1, b0, b1;
+    float rr[kBfNS + 1];
+    __device__ __forceinline__ void load(const float4* __restrict__ pxr, const float4* __restrict__ pxi,
+                                         const float* __restrict__ prr, const int (&off)[kBfNS + 1], int ch) {
+        a0 = pxr[ch * 72]; a1 = pxr[ch * 72 + 1];
+        b0 = pxi[ch * 72]; b1 = pxi[ch * 72 + 1];
+#pragma unroll
+        for (int i = 0; i <= kBfNS; ++i) rr[i] = prr[off[i] + ch * 288];
+    }
+    __device__ __forceinline__ void accumulate(const float (&al)[kBfNC], float2 (&are)[kBfNC],
+                                               float2 (&aim)[kBfNC]) const {
+        float2 dp[4], r0[4];                                // (r1 - r0) and r0 of samples 2q, 2q+1
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dp[q] = make_float2(rr[2 * q] - rr[2 * q + 1], rr[2 * q + 1] - rr[2 * q + 2]);
+            r0[q] = make_float2(rr[2 * q + 1], rr[2 * q + 2]);
+        }
+        const float2 xre[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w),
+                               make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+        const float2 xim[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                               make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+        for (int j = 0; j < kBfNC; ++j) {
+            const float2 a2 = make_float2(al[j], al[j]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // blended replica of samples 2q, 2q+1: r0 + alpha (r1 - r0)
+                const float2 bp = __ffma2_rn(a2, dp[q], r0[q]);
+                are[j] = __ffma2_rn(xre[q], bp, are[j]);
+                aim[j] = __ffma2_rn(xim[q], bp, aim[j]);
+            }
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // k_brute: persistent; CTA slot = kBfWarps groups of one channel.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__((kBfWarps + 1) * 32, 1)
+__global__ void __launch_bounds__(kBfWarps * 32, 1)
 k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const float* __restrict__ brr,
         int64_t bx_stride, int64_t br_stride, const int4* __restrict__ hdr,
         const int32_t* __restrict__ ent_j, const float* __restrict__ ent_a,
@@ -167,30 +227,28 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
 
     const int n_slots = *n_groups / kBfWarps;
     const int ntiles = S_pad / kBfTile;
+    const int my_slots = (blockIdx.x < n_slots) ? (n_slots - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t my_tiles = (uint32_t)my_slots * ntiles;  // tiles this CTA streams, numbered 0..my_tiles-1
     uint32_t it = 0;                                       // running tile counter (same on all warps)
 
-    if (warp == kBfWarps) {
-        // ===== producer warp: one elected lane streams the tiles =====
-        if (lane == 0) {
-            const uint32_t bytes_x = kXTileF * 4, bytes_r = (uint32_t)rr_len * 4;
-            for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-                const int c = hdr[(size_t)slot * kBfWarps].x;
-                const float* sxr = bxr + c * bx_stride;
-                const float* sxi = bxi + c * bx_stride;
-                const float* srr = brr + c * br_stride;
-                for (int t = 0; t < ntiles; ++t, ++it) {
-                    const int s = it % kBfStages;
-                    mbar_wait(&empty_bar[s], ((it / kBfStages) & 1) ^ 1);
-                    float* dst = stage0 + (size_t)s * stage_f;
-                    mbar_expect_tx(&full_bar[s], 2 * bytes_x + bytes_r);
-                    tma_load_1d(dst, sxr + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
-                    tma_load_1d(dst + kXTileF, sxi + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
-                    tma_load_1d(dst + 2 * kXTileF, srr + (size_t)t * kXTileF, bytes_r, &full_bar[s]);
-                }
-            }
-        }
-        return;
-    }
+    // TMA producer duty (one elected lane): stream tile `jt` of this CTA's sequence into stage jt % stages.
+    // There is no dedicated producer warp: 9 warps would put 3 on one scheduler and cap the kernel at
+    // 168 registers per thread (16K registers per SM sub-partition); the duty rotates over the 8 warps.
+    auto issue_tile = [&](uint32_t jt) {
+        if (jt >= my_tiles) return;
+        const int slot = blockIdx.x + (int)(jt / ntiles) * gridDim.x;
+        const int t = (int)(jt % ntiles);
+        const int c = hdr[(size_t)slot * kBfWarps].x;
+        const int s = jt % kBfStages;
+        const uint32_t bytes_x = kXTileF * 4, bytes_r = (uint32_t)rr_len * 4;
+        float* dst = stage0 + (size_t)s * stage_f;
+        mbar_expect_tx(&full_bar[s], 2 * bytes_x + bytes_r);
+        tma_load_1d(dst, bxr + c * bx_stride + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
+        tma_load_1d(dst + kXTileF, bxi + c * bx_stride + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
+        tma_load_1d(dst + 2 * kXTileF, brr + c * br_stride + (size_t)t * kXTileF, bytes_r, &full_bar[s]);
+    };
+    if (threadIdx.x == 0)
+        for (uint32_t jt = 0; jt + 1 < kBfStages; ++jt) issue_tile(jt);       // prologue: stages-1 tiles in flight
 
     // ===== consumer warps =====
     const int lane_f4 = 2 * lane + (lane >> 2);            // float4 index of this lane's run (skewX)
@@ -198,16 +256,14 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
         const int c = h.x, k = h.y - W, n_valid = h.z;
-        float2 al[kBfNC];                                   // (alpha, alpha): FFMA2 has no scalar broadcast
+        float al[kBfNC];                                    // FFMA2 takes alpha as a broadcast .F32 operand
 #pragma unroll
-        for (int j = 0; j < kBfNC; ++j) {
-            const float a = (j < n_valid) ? ent_a[(size_t)g * kBfNC + j] : 0.f;
-            al[j] = make_float2(a, a);
-        }
+        for (int j = 0; j < kBfNC; ++j) al[j] = (j < n_valid) ? ent_a[(size_t)g * kBfNC + j] : 0.f;
         float2 are[kBfNC], aim[kBfNC];
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) { are[j] = make_float2(0.f, 0.f); aim[j] = make_float2(0.f, 0.f); }
-        // replica window: lane run starts at local x' = Lu + chunk*256 + lane*8, Lu = H - k - 1
+        // replica window: lane run starts at local x' = Lu + chunk*256 + lane*8, Lu = H - k - 1;
+        // word offsets of its 9 replica values in the skewed tile (constant over the whole block)
         const int Lu = H - k - 1;
         int off[kBfNS + 1];
 #pragma unroll
@@ -220,36 +276,26 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
             const float4* pxr = reinterpret_cast<const float4*>(st) + lane_f4;
             const float4* pxi = reinterpret_cast<const float4*>(st + kXTileF) + lane_f4;
             const float* prr = st + 2 * kXTileF;
-#pragma unroll 1
+            // software pipeline over the 4 chunks of the tile: the shared-memory operands of chunk
+            // ch+1 are in flight while chunk ch is computed (2 warps per scheduler are not enough to
+            // hide the LDS latency otherwise: they run in lock step)
+            BruteChunk cur, nxt;
+            cur.load(pxr, pxi, prr, off, 0);
+#pragma unroll
             for (int ch = 0; ch < kBfTile / kBfChunk; ++ch) {
-                const float4 a0 = pxr[ch * 72], a1 = pxr[ch * 72 + 1];
-                const float4 b0 = pxi[ch * 72], b1 = pxi[ch * 72 + 1];
-                float rr[kBfNS + 1];
-#pragma unroll
-                for (int i = 0; i <= kBfNS; ++i) rr[i] = prr[off[i] + ch * 288];
-                float2 dp[4], r0[4];                        // (r1 - r0) and r0 of samples 2q, 2q+1
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    dp[q] = make_float2(rr[2 * q] - rr[2 * q + 1], rr[2 * q + 1] - rr[2 * q + 2]);
-                    r0[q] = make_float2(rr[2 * q + 1], rr[2 * q + 2]);
-                }
-                const float2 xre[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w),
-                                       make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
-                const float2 xim[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
-                                       make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-#pragma unroll
-                for (int j = 0; j < kBfNC; ++j) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        // blended replica of samples 2q, 2q+1: r0 + alpha (r1 - r0)
-                        const float2 bp = __ffma2_rn(al[j], dp[q], r0[q]);
-                        are[j] = __ffma2_rn(xre[q], bp, are[j]);
-                        aim[j] = __ffma2_rn(xim[q], bp, aim[j]);
-                    }
-                }
+                if (ch + 1 < kBfTile / kBfChunk) nxt.load(pxr, pxi, prr, off, ch + 1);
+                cur.accumulate(al, are, aim);
+                cur = nxt;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            // refill duty of tile `it`: reload the stage tile it-1 used (everyone released it about a
+            // tile ago, so the wait is normally already satisfied) with tile it+stages-1
+            if (warp == (int)(it % kBfWarps)) {
+                if (it >= 1) mbar_wait(&empty_bar[(it - 1) % kBfStages], ((it - 1) / kBfStages) & 1);
+                if (lane == 0) issue_tile(it + kBfStages - 1);
+                __syncwarp();
+            }
         }
 
         // lane partials -> FP64 -> warp butterfly; lane j keeps candidate j
@@ -317,9 +363,12 @@ int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
             c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->hist);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    k_bucket_scan<<<1, 1024, sizeof(int32_t) * (2 * nbuck + 1), s>>>(c->hist, c->ep, c->W, c->bucket_base,
-                                                                   reinterpret_cast<int4*>(c->hdr), c->n_groups,
-                                                                   c->max_groups);
+    k_bucket_scan<<<1, 256, sizeof(int32_t) * (2 * nbuck + 1), s>>>(c->hist, c->ep, c->W, c->group_base,
+                                                                  c->bucket_base, c->n_groups, c->max_groups);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    k_group_headers<<<(int)((c->max_groups + 255) / 256), 256, sizeof(int32_t) * (nbuck + 1), s>>>(
+        c->hist, c->group_base, c->ep, c->W, reinterpret_cast<int4*>(c->hdr), c->max_groups);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     dim3 gs(nblk, C);
@@ -341,7 +390,7 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
         attr_set = true;
     }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
-    k_brute<<<c->sm_count, (kBfWarps + 1) * 32, smem, s>>>(
+    k_brute<<<c->sm_count, kBfWarps * 32, smem, s>>>(
         c->bxr, c->bxi, c->brr, c->bx_stride, c->br_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
         c->H, c->W);

@@ -145,6 +145,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->hist, C * NB);
         DPE_ALLOC(c->cursor, C * NB);
         DPE_ALLOC(c->bucket_base, C * NB);
+        DPE_ALLOC(c->group_base, C * NB + 1);
         DPE_ALLOC(c->hdr, c->max_groups * 4);
         DPE_ALLOC(c->ent_j, c->max_groups * kBfNC);
         DPE_ALLOC(c->ent_a, c->max_groups * kBfNC);
@@ -169,7 +170,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
                     c->cpart, c->cs, c->bxr, c->bxi, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
-                    c->bucket_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
+                    c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
                     c->vgrid, c->vscores, c->carr};
     for (void* p : ptrs)
         if (p) cudaFree(p);

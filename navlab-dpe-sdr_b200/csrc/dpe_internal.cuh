@@ -89,7 +89,7 @@ struct dpe_ctx {
     // brute-force work lists
     int16_t* pair_k; float* pair_a; double2* pair_v;   // [C][G]
     int32_t* hist;                     // [C][NB] counts, NB = 2W+1
-    int32_t* cursor; int64_t* bucket_base;
+    int32_t* cursor; int64_t* bucket_base; int32_t* group_base;
     int32_t* hdr;                      // group headers {c, krel, n, pad}
     int32_t* ent_j; float* ent_a;      // bucketed entries
     int32_t* n_groups;                 // device scalar: total groups (multiple of kBfWarps)
