@@ -163,41 +163,37 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(s2u(dst)), "l"(src), "r"(bytes), "r"(s2u(bar)) : "memory");
 }
 
-constexpr int kXTileF = kBfTile + kBfTile / 8;            // 1152 floats: float4-skewed 1024-sample plane tile
+constexpr int kXTileF = (int)skewX(kBfTile);               // 2560 floats: float4-skewed (re,im) tile of 1024 samples
+constexpr int kRTileStep = kBfTile + kBfTile / 8;          // 1152: word-skewed replica plane advance per tile
 
-// Register image of one warp-chunk (256 samples): per lane 8 contiguous samples (re / im as
-// pairs for FFMA2) and the 9 replica values r[m-k-1 .. m-k+7] its blend needs.
+// Register image of one warp-chunk (256 samples): per lane 8 contiguous samples as (re,im) pairs
+// and the 9 replica values r[m-k-1 .. m-k+7] its blend needs.
 struct BruteChunk {
-    float4 a0, a1, b0, b1;
+    float4 x[4];
     float rr[kBfNS + 1];
-    __device__ __forceinline__ void load(const float4* __restrict__ pxr, const float4* __restrict__ pxi,
-                                         const float* __restrict__ prr, const int (&off)[kBfNS + 1], int ch) {
-        a0 = pxr[ch * 72]; a1 = pxr[ch * 72 + 1];
-        b0 = pxi[ch * 72]; b1 = pxi[ch * 72 + 1];
+    __device__ __forceinline__ void load(const float4* __restrict__ px, const float* __restrict__ prr,
+                                         const int (&off)[kBfNS + 1], int ch) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = px[ch * 160 + i];
 #pragma unroll
         for (int i = 0; i <= kBfNS; ++i) rr[i] = prr[off[i] + ch * 288];
     }
-    __device__ __forceinline__ void accumulate(const float (&al)[kBfNC], float2 (&are)[kBfNC],
-                                               float2 (&aim)[kBfNC]) const {
-        float2 dp[4], r0[4];                                // (r1 - r0) and r0 of samples 2q, 2q+1
+    // FFMA2 operand economy (B200: an FFMA2 with three uncached 64-bit sources needs a third
+    // register-file cycle): the blend takes alpha as a scalar .F32 operand and (r1-r0, r0) pairs
+    // shared by all candidates; the accumulate takes the blended chip as a scalar .F32 operand
+    // and the (re,im) sample pair shared by all candidates.  Per 2 samples and candidate:
+    // 1 FFMA2 blend + 2 FFMA2 accumulate = 12 FLOP.
+    __device__ __forceinline__ void accumulate(const float (&al)[kBfNC], float2 (&acc)[kBfNC]) const {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            dp[q] = make_float2(rr[2 * q] - rr[2 * q + 1], rr[2 * q + 1] - rr[2 * q + 2]);
-            r0[q] = make_float2(rr[2 * q + 1], rr[2 * q + 2]);
-        }
-        const float2 xre[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w),
-                               make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
-        const float2 xim[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
-                               make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+            const float2 dp = make_float2(rr[2 * q] - rr[2 * q + 1], rr[2 * q + 1] - rr[2 * q + 2]);
+            const float2 r0 = make_float2(rr[2 * q + 1], rr[2 * q + 2]);
+            const float2 xa = make_float2(x[q].x, x[q].y), xb = make_float2(x[q].z, x[q].w);
 #pragma unroll
-        for (int j = 0; j < kBfNC; ++j) {
-            const float2 a2 = make_float2(al[j], al[j]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                // blended replica of samples 2q, 2q+1: r0 + alpha (r1 - r0)
-                const float2 bp = __ffma2_rn(a2, dp[q], r0[q]);
-                are[j] = __ffma2_rn(xre[q], bp, are[j]);
-                aim[j] = __ffma2_rn(xim[q], bp, aim[j]);
+            for (int j = 0; j < kBfNC; ++j) {
+                const float2 bp = __ffma2_rn(make_float2(al[j], al[j]), dp, r0);   // r0 + alpha (r1 - r0)
+                acc[j] = __ffma2_rn(make_float2(bp.x, bp.x), xa, acc[j]);
+                acc[j] = __ffma2_rn(make_float2(bp.y, bp.y), xb, acc[j]);
             }
         }
     }
@@ -207,7 +203,7 @@ struct BruteChunk {
 // k_brute: persistent; CTA slot = kBfWarps groups of one channel.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBfWarps * 32, 1)
-k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const float* __restrict__ brr,
+k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
         int64_t bx_stride, int64_t br_stride, const int4* __restrict__ hdr,
         const int32_t* __restrict__ ent_j, const float* __restrict__ ent_a,
         const int32_t* __restrict__ n_groups, double2* __restrict__ pair_v, int64_t G, int S_pad,
@@ -216,7 +212,7 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
     __shared__ __align__(8) uint64_t full_bar[kBfStages], empty_bar[kBfStages];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr_len = (int)skewR(kBfTile + 2 * H);        // floats, multiple of 4
-    const int stage_f = 2 * kXTileF + rr_len;              // floats per stage
+    const int stage_f = kXTileF + rr_len;                  // floats per stage
     float* const stage0 = reinterpret_cast<float*>(smem);
 
     if (threadIdx.x == 0) {
@@ -242,16 +238,15 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
         const int s = jt % kBfStages;
         const uint32_t bytes_x = kXTileF * 4, bytes_r = (uint32_t)rr_len * 4;
         float* dst = stage0 + (size_t)s * stage_f;
-        mbar_expect_tx(&full_bar[s], 2 * bytes_x + bytes_r);
-        tma_load_1d(dst, bxr + c * bx_stride + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
-        tma_load_1d(dst + kXTileF, bxi + c * bx_stride + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
-        tma_load_1d(dst + 2 * kXTileF, brr + c * br_stride + (size_t)t * kXTileF, bytes_r, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], bytes_x + bytes_r);
+        tma_load_1d(dst, bx + c * bx_stride + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
+        tma_load_1d(dst + kXTileF, brr + c * br_stride + (size_t)t * kRTileStep, bytes_r, &full_bar[s]);
     };
     if (threadIdx.x == 0)
         for (uint32_t jt = 0; jt + 1 < kBfStages; ++jt) issue_tile(jt);       // prologue: stages-1 tiles in flight
 
     // ===== consumer warps =====
-    const int lane_f4 = 2 * lane + (lane >> 2);            // float4 index of this lane's run (skewX)
+    const int lane_f4 = 5 * lane;                          // float4 index of this lane's run (skewX)
     for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
@@ -259,9 +254,9 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
         float al[kBfNC];                                    // FFMA2 takes alpha as a broadcast .F32 operand
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) al[j] = (j < n_valid) ? ent_a[(size_t)g * kBfNC + j] : 0.f;
-        float2 are[kBfNC], aim[kBfNC];
+        float2 acc[kBfNC];                                  // (re, im) of this lane's samples
 #pragma unroll
-        for (int j = 0; j < kBfNC; ++j) { are[j] = make_float2(0.f, 0.f); aim[j] = make_float2(0.f, 0.f); }
+        for (int j = 0; j < kBfNC; ++j) acc[j] = make_float2(0.f, 0.f);
         // replica window: lane run starts at local x' = Lu + chunk*256 + lane*8, Lu = H - k - 1;
         // word offsets of its 9 replica values in the skewed tile (constant over the whole block)
         const int Lu = H - k - 1;
@@ -273,18 +268,17 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
             const int s = it % kBfStages;
             mbar_wait(&full_bar[s], (it / kBfStages) & 1);
             const float* st = stage0 + (size_t)s * stage_f;
-            const float4* pxr = reinterpret_cast<const float4*>(st) + lane_f4;
-            const float4* pxi = reinterpret_cast<const float4*>(st + kXTileF) + lane_f4;
-            const float* prr = st + 2 * kXTileF;
+            const float4* px = reinterpret_cast<const float4*>(st) + lane_f4;
+            const float* prr = st + kXTileF;
             // software pipeline over the 4 chunks of the tile: the shared-memory operands of chunk
             // ch+1 are in flight while chunk ch is computed (2 warps per scheduler are not enough to
             // hide the LDS latency otherwise: they run in lock step)
             BruteChunk cur, nxt;
-            cur.load(pxr, pxi, prr, off, 0);
+            cur.load(px, prr, off, 0);
 #pragma unroll
             for (int ch = 0; ch < kBfTile / kBfChunk; ++ch) {
-                if (ch + 1 < kBfTile / kBfChunk) nxt.load(pxr, pxi, prr, off, ch + 1);
-                cur.accumulate(al, are, aim);
+                if (ch + 1 < kBfTile / kBfChunk) nxt.load(px, prr, off, ch + 1);
+                cur.accumulate(al, acc);
                 cur = nxt;
             }
             __syncwarp();
@@ -302,8 +296,7 @@ k_brute(const float* __restrict__ bxr, const float* __restrict__ bxi, const floa
         double outr = 0.0, outi = 0.0;
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) {
-            double re = (double)are[j].x + (double)are[j].y;
-            double im = (double)aim[j].x + (double)aim[j].y;
+            double re = (double)acc[j].x, im = (double)acc[j].y;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 re += __shfl_xor_sync(0xffffffffu, re, o);
@@ -345,7 +338,7 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
 }
 
 size_t brute_smem_bytes(int H) {
-    return (size_t)kBfStages * (2 * kXTileF + skewR(kBfTile + 2 * H)) * sizeof(float);
+    return (size_t)kBfStages * (kXTileF + skewR(kBfTile + 2 * H)) * sizeof(float);
 }
 
 int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
@@ -391,7 +384,7 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
     k_brute<<<c->sm_count, kBfWarps * 32, smem, s>>>(
-        c->bxr, c->bxi, c->brr, c->bx_stride, c->br_stride, reinterpret_cast<const int4*>(c->hdr),
+        c->bx, c->brr, c->bx_stride, c->br_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
         c->H, c->W);
     prof_end(c, s);

@@ -132,8 +132,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     if (brute) {
         c->bx_stride = skewX(c->S_pad);
         c->br_stride = skewR(c->S_pad + 2 * c->H);
-        DPE_ALLOC(c->bxr, C * c->bx_stride);
-        DPE_ALLOC(c->bxi, C * c->bx_stride);
+        DPE_ALLOC(c->bx, C * c->bx_stride);
         DPE_ALLOC(c->brr, C * c->br_stride);
         const size_t NB = 2 * c->W + 1;
         DPE_REQUIRE(sizeof(int32_t) * (2 * C * NB + 1) <= 48 * 1024, DPE_EINVAL,
@@ -168,7 +167,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     if (!c) return DPE_OK;
     cudaSetDevice(c->cfg.device);
     void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
-                    c->cpart, c->cs, c->bxr, c->bxi, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
+                    c->cpart, c->cs, c->bx, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
                     c->vgrid, c->vscores, c->carr};

@@ -5,7 +5,7 @@
 //   ca        int8   [37][1024]         C/A chips, +/-1  (BCS chipsCACode_d)
 //   xw        float2 [C][S]             wiped samples x[n]*conj(carrier)      (natural order)
 //   rs        int8   [C][S]             no-flip replica sign r[n]
-//   bxr/bxi   float  [C][skewX(S_pad)]  wiped samples, re / im planes, float4-skewed for the
+//   bx        float2 [C][skewX(S_pad)/2] wiped samples (re,im interleaved), float4-skewed for the
 //                                       brute-force kernel's conflict-free LDS.128
 //   brr       float  [C][skewR(S_pad+2H)] chosen replica (flip applied) with circular halo,
 //                                       word-skewed for conflict-free lane-strided LDS.32
@@ -38,7 +38,7 @@ constexpr int kReduceBlock = 256;
 constexpr int kProfMax = 8192;
 
 // brute-force kernel geometry
-constexpr int kBfNC = 16;              // candidates per warp (one group)
+constexpr int kBfNC = 32;              // candidates per warp (one group)
 constexpr int kBfNS = 8;               // contiguous samples per lane per chunk
 constexpr int kBfChunk = 32 * kBfNS;   // samples per warp-chunk (256)
 constexpr int kBfTile = 1024;          // samples per TMA stage
@@ -59,10 +59,11 @@ struct EpochDev {
 };
 
 // word-skew for the replica plane: lanes stride 8 words -> stride 9 (conflict-free LDS.32)
-__host__ __device__ inline int64_t skewR(int64_t x) { return x + (x >> 3); }
-// float4-skew for the sample planes: one pad float4 every 8 float4 (conflict-free LDS.128
-// when lane l reads float4 2l and 2l+1)
-__host__ __device__ inline int64_t skewX(int64_t x) { return x + 4 * (x >> 5); }
+__host__ __device__ constexpr inline int64_t skewR(int64_t x) { return x + (x >> 3); }
+// float4-skew of the interleaved (re,im) sample plane: float offset of sample n.  One float4 holds
+// two samples; one pad float4 after every 4 (lane l reads float4 4l..4l+3 -> physical 5l..5l+3,
+// conflict-free LDS.128 because 5 is odd).
+__host__ __device__ constexpr inline int64_t skewX(int64_t n) { return 4 * ((n >> 1) + (n >> 3)) + 2 * (n & 1); }
 
 }  // namespace dpe
 
@@ -81,7 +82,7 @@ struct dpe_ctx {
     float2* xw; int8_t* rs; int16_t* chip_idx;
     int32_t* idx_next; int32_t* no_flip;
     double2* cpart; double2* cs;
-    float *bxr, *bxi, *brr;
+    float *bx, *brr;
     int64_t bx_stride, br_stride;      // per-channel plane strides (floats)
     double* grid; double* scores;
     double* blk_partial; int32_t n_blk_partial;

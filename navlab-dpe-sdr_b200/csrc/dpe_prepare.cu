@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(256)
 k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
           const EpochDev* __restrict__ ep, double fs, int S, int S_pad,
           float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
-          int32_t* __restrict__ idx_next, float* __restrict__ bxr, float* __restrict__ bxi,
-          int64_t bx_stride) {
+          int32_t* __restrict__ idx_next, float* __restrict__ bx, int64_t bx_stride) {
     __shared__ int8_t code_s[1024];
     const int c = blockIdx.y;
     const EpochDev& e = *ep;
@@ -111,10 +110,10 @@ k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
             xw[(size_t)c * S + n] = make_float2(xr[q], xi[q]);
         }
     }
-    if (bxr) {  // float4-skewed planes for the brute-force kernel (zero beyond S)
-        const int64_t p = skewX(n0);
-        *reinterpret_cast<float4*>(bxr + c * bx_stride + p) = make_float4(xr[0], xr[1], xr[2], xr[3]);
-        *reinterpret_cast<float4*>(bxi + c * bx_stride + p) = make_float4(xi[0], xi[1], xi[2], xi[3]);
+    if (bx) {  // float4-skewed interleaved plane for the brute-force kernel (zero beyond S)
+        float4* p = reinterpret_cast<float4*>(bx + c * bx_stride + skewX(n0));   // n0 % 4 == 0: two adjacent float4
+        p[0] = make_float4(xr[0], xi[0], xr[1], xi[1]);
+        p[1] = make_float4(xr[2], xi[2], xr[3], xi[3]);
     }
 }
 
@@ -275,7 +274,7 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     prof_begin(c, DPE_STAGE_PREPARE, s);
     k_prepare<<<grid, 256, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, brute ? S_pad : ((S + 3) / 4) * 4,
                                    c->xw, c->rs, c->chip_idx, c->idx_next,
-                                   brute ? c->bxr : nullptr, brute ? c->bxi : nullptr, c->bx_stride);
+                                   brute ? c->bx : nullptr, c->bx_stride);
     prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
