@@ -147,13 +147,14 @@ def run_ours(args):
     gathered = torch.zeros(world * capi.DPE_PARTIAL_LEN, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     recv = torch.empty(2 * S, dtype=torch.int16, device=dev)
+    recv_u8 = recv.view(torch.uint8)                               # NCCL has no int16: broadcast the bytes
 
     def step_resident(i):
         b = i % n_blocks
         if world > 1:
             if rank == 0:
                 recv.copy_(blocks_dev[b], non_blocking=True)
-            dist.broadcast(recv, 0)
+            dist.broadcast(recv_u8, 0)
             ctx.block_stage(recv, stream)
         else:
             ctx.block_stage(blocks_dev[b], stream)
@@ -173,7 +174,7 @@ def run_ours(args):
         if world > 1:
             if rank == 0:
                 recv.copy_(blocks_host[b], non_blocking=True)     # H2D from pinned memory, then NVLink broadcast
-            dist.broadcast(recv, 0)
+            dist.broadcast(recv_u8, 0)
             ctx.block_stage(recv, stream)
             ctx.epoch_set(ep_structs[b], sats[b], stream)
             ctx.replica_prepare(stream)

@@ -176,6 +176,18 @@ int dpe_block_stage(dpe_ctx* ctx, const int16_t* iq, int64_t S, void* stream);
  * as produced by CHM_GridPrep, cuchanmgr.cu:853-923).                            */
 int dpe_epoch_set(dpe_ctx* ctx, const dpe_epoch* ep, const double* sat_states, void* stream);
 
+/* dpe_epoch_set_part: the same upload split the way the reference splits its modules.
+ *   DPE_PART_CHANNELS  what BatchCorrScores reads (batchcorrscores.cu:681-692): C, prn,
+ *                      rc_start, ri_start, fc, fi, cp_start, cp_ref, doppler_sign
+ *   DPE_PART_GEOMETRY  what BatchCorrManifold reads (batchcorrmanifold.cu:2261-2279): fc,
+ *                      rc_end, cp_end, cp_ref, cp_ref_tow, rx_time, center, enu2ecef and
+ *                      sat_states ([C][T][8]; may be NULL when the part is not selected)
+ * Fields of the other part are ignored.  C must agree between the two parts.        */
+#define DPE_PART_CHANNELS 1u
+#define DPE_PART_GEOMETRY 2u
+int dpe_epoch_set_part(dpe_ctx* ctx, const dpe_epoch* ep, const double* sat_states, unsigned parts,
+                       void* stream);
+
 /* dpe_replica_prepare: int16 unpack, carrier NCO wipe-off, C/A chip index and
  * replica sign, nav-bit edge, per-lag partial correlations.  Replaces BCS_Load,
  * BCS_NavBitBoundary, BCS_ComputeDopplerWipeoff, BCS_ComputeCodeReplica,
@@ -240,6 +252,17 @@ int dpe_debug_bins(dpe_ctx* ctx, int64_t i0, int64_t n, int sat_mode, int64_t* f
 int dpe_debug_read(dpe_ctx* ctx, int which, size_t offset, void* dst, size_t nbytes);
 /* number of kernels launched by this context since creation                     */
 int64_t dpe_launch_count(dpe_ctx* ctx);
+
+/* ---- runtime helpers for host code that does not link the CUDA runtime ------------
+ * (the C++ flow mirror in navlab-dpe-sdr_b200/host/ links libdpe_b200.so only).
+ * dpe_stream_*: the flow's stream (Flow::Start creates one, flow.cu:33).  dpe_host_alloc:
+ * page-locked host memory for the sample ring (cudaMallocHost, sampleblock.cu:205).   */
+int dpe_stream_create(void** stream);
+int dpe_stream_destroy(void* stream);
+int dpe_stream_sync(void* stream);
+int dpe_host_alloc(void** ptr, size_t bytes);
+int dpe_host_free(void* ptr);
+int dpe_device_count(void);
 
 /* ---- per-stage device timing (bench.py's roofline.achieved) --------------------
  * When enabled, every stage is bracketed by cudaEvents on the stream it is

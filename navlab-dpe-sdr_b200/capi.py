@@ -26,16 +26,18 @@ SAT_MIDDLE, SAT_PER_TIME = 0, 1
  PTR_CHIP_IDX, PTR_XW, PTR_CARR_SCORES, PTR_VEL_SCORES, PTR_VEL_GRID, PTR_REPLICA_SIGN,
  PTR_CA_TABLE) = range(14)
 FLAG_KEEP_CHIP_IDX, FLAG_BRUTE_TILES, FLAG_KEEP_BINS = 1, 2, 4
+PART_CHANNELS, PART_GEOMETRY = 1, 2
 (STAGE_PREPARE, STAGE_CORRELOGRAM, STAGE_LOOKUP, STAGE_BRUTE_BINS, STAGE_BRUTE_CORR, STAGE_BRUTE_SCORE,
  STAGE_ESTIMATE) = range(7)
 
 EXPORTS = (
     "dpe_ctx_create", "dpe_ctx_destroy", "dpe_last_error", "dpe_abi_version", "dpe_grid_set",
-    "dpe_vel_grid_set", "dpe_block_stage", "dpe_epoch_set", "dpe_replica_prepare", "dpe_correlogram",
+    "dpe_vel_grid_set", "dpe_block_stage", "dpe_epoch_set", "dpe_epoch_set_part", "dpe_replica_prepare", "dpe_correlogram",
     "dpe_code_scores_set",
     "dpe_score_pos", "dpe_estimate", "dpe_score_vel", "dpe_result_fetch", "dpe_epoch_run", "dpe_dev_ptr",
     "dpe_debug_channel_flags", "dpe_debug_bins", "dpe_debug_read", "dpe_launch_count", "dpe_profile_enable", "dpe_profile_read",
-    "dpe_brute_pairs", "dpe_microbench_fp32",
+    "dpe_brute_pairs", "dpe_stream_create", "dpe_stream_destroy", "dpe_stream_sync", "dpe_host_alloc",
+    "dpe_host_free", "dpe_device_count", "dpe_microbench_fp32",
     "dpe_microbench_hbm")
 
 
@@ -90,6 +92,7 @@ def load_library(path: str | None = None):
     lib.dpe_vel_grid_set.argtypes = [vp, vp, i64, vp]
     lib.dpe_block_stage.argtypes = [vp, vp, i64, vp]
     lib.dpe_epoch_set.argtypes = [vp, C.POINTER(DpeEpoch), vp, vp]
+    lib.dpe_epoch_set_part.argtypes = [vp, C.POINTER(DpeEpoch), vp, C.c_uint, vp]
     lib.dpe_replica_prepare.argtypes = [vp, vp]
     lib.dpe_correlogram.argtypes = [vp, vp]
     lib.dpe_code_scores_set.argtypes = [vp, vp, i32, vp]
@@ -203,6 +206,15 @@ class Context:
         assert sat.size == e.C * self.T * 8, "sat_states must be [C][T][8]"
         self._ep, self._sat = e, sat
         _check(self.lib, self.lib.dpe_epoch_set(self.h, C.byref(e), _ptr(sat), C.c_void_p(stream)))
+
+    def epoch_set_part(self, ep, parts, sat_states=None, stream=0):
+        e = ep if isinstance(ep, DpeEpoch) else make_epoch(ep)
+        sat = None
+        if parts & PART_GEOMETRY:
+            sat = sat_states if sat_states is not None else ep["sat_states"]
+            sat = np.ascontiguousarray(sat, dtype=np.float64)
+        self._ep, self._sat = e, sat
+        _check(self.lib, self.lib.dpe_epoch_set_part(self.h, C.byref(e), _ptr(sat), parts, C.c_void_p(stream)))
 
     def replica_prepare(self, stream=0):
         _check(self.lib, self.lib.dpe_replica_prepare(self.h, C.c_void_p(stream)))

@@ -216,38 +216,62 @@ int dpe_block_stage(dpe_ctx* c, const int16_t* iq, int64_t S, void* stream) {
     return DPE_OK;
 }
 
-int dpe_epoch_set(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, void* stream) {
-    DPE_REQUIRE(c && ep && sat_states, DPE_EINVAL, "dpe_epoch_set: null argument");
+int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, unsigned parts,
+                       void* stream) {
+    DPE_REQUIRE(c && ep, DPE_EINVAL, "dpe_epoch_set: null argument");
+    DPE_REQUIRE(parts && !(parts & ~(DPE_PART_CHANNELS | DPE_PART_GEOMETRY)), DPE_EINVAL, "bad parts mask %u", parts);
     DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
+    DPE_REQUIRE(!(parts & DPE_PART_GEOMETRY) || sat_states, DPE_EINVAL, "geometry part without sat_states");
     EpochDev& h = c->ep_host;
-    memset(&h, 0, sizeof(h));
+    if (c->have_epoch && h.C != ep->C) {           // channel count changed: both parts must be set again
+        c->have_epoch = 0;
+    }
     h.C = ep->C;
-    h.doppler_sign = ep->doppler_sign;
-    h.rx_time = ep->rx_time;
-    memcpy(h.center, ep->center, sizeof(h.center));
-    memcpy(h.R, ep->enu2ecef, sizeof(h.R));
-    for (int i = 0; i < ep->C; ++i) {
-        DPE_REQUIRE(ep->prn[i] >= 1 && ep->prn[i] <= DPE_MAX_CHAN, DPE_EINVAL, "PRN %d out of range", ep->prn[i]);
+    for (int i = 0; i < ep->C; ++i)
         DPE_REQUIRE(ep->fc[i] > 0, DPE_EINVAL, "code frequency of channel %d not positive", i);
-        h.prn[i] = ep->prn[i];
-        h.rc_start[i] = ep->rc_start[i]; h.ri_start[i] = ep->ri_start[i];
-        h.fc[i] = ep->fc[i]; h.fi[i] = ep->fi[i];
-        h.cp_start[i] = ep->cp_start[i]; h.cp_ref[i] = ep->cp_ref[i];
-        h.rc_end[i] = ep->rc_end[i]; h.cp_end[i] = ep->cp_end[i]; h.cp_ref_tow[i] = ep->cp_ref_tow[i];
+    if (parts & DPE_PART_CHANNELS) {
+        h.doppler_sign = ep->doppler_sign;
+        for (int i = 0; i < ep->C; ++i) {
+            DPE_REQUIRE(ep->prn[i] >= 1 && ep->prn[i] <= DPE_MAX_CHAN, DPE_EINVAL, "PRN %d out of range",
+                        ep->prn[i]);
+            h.prn[i] = ep->prn[i];
+            h.rc_start[i] = ep->rc_start[i]; h.ri_start[i] = ep->ri_start[i];
+            h.fc[i] = ep->fc[i]; h.fi[i] = ep->fi[i];
+            h.cp_start[i] = ep->cp_start[i]; h.cp_ref[i] = ep->cp_ref[i];
+        }
+    }
+    if (parts & DPE_PART_GEOMETRY) {
+        h.rx_time = ep->rx_time;
+        memcpy(h.center, ep->center, sizeof(h.center));
+        memcpy(h.R, ep->enu2ecef, sizeof(h.R));
+        for (int i = 0; i < ep->C; ++i) {
+            h.fc[i] = ep->fc[i];
+            h.cp_ref[i] = ep->cp_ref[i];
+            h.rc_end[i] = ep->rc_end[i]; h.cp_end[i] = ep->cp_end[i]; h.cp_ref_tow[i] = ep->cp_ref_tow[i];
+        }
     }
     cudaStream_t s = (cudaStream_t)stream;
+    // ep_host is pageable: cudaMemcpyAsync stages it before returning, so it may be rewritten next call
     DPE_CUDA(cudaMemcpyAsync(c->ep, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    DPE_CUDA(cudaMemcpyAsync(c->sat, sat_states, sizeof(double) * 8 * (size_t)ep->C * c->T,
-                             cudaMemcpyDefault, s));
+    if (parts & DPE_PART_GEOMETRY)
+        DPE_CUDA(cudaMemcpyAsync(c->sat, sat_states, sizeof(double) * 8 * (size_t)ep->C * c->T,
+                                 cudaMemcpyDefault, s));
     c->epoch_C = ep->C;
-    c->have_epoch = 1;
-    c->have_prepare = c->have_corr = c->have_scores = 0;
+    c->have_epoch |= (int)parts;
+    if (parts & DPE_PART_CHANNELS) c->have_prepare = c->have_corr = 0;
+    c->have_scores = 0;
     return DPE_OK;
+}
+
+int dpe_epoch_set(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, void* stream) {
+    DPE_REQUIRE(sat_states, DPE_EINVAL, "dpe_epoch_set: null argument");
+    return dpe_epoch_set_part(c, ep, sat_states, DPE_PART_CHANNELS | DPE_PART_GEOMETRY, stream);
 }
 
 int dpe_replica_prepare(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
-    DPE_REQUIRE(c->have_block && c->have_epoch, DPE_ESTATE, "replica_prepare before block_stage/epoch_set");
+    DPE_REQUIRE(c->have_block && (c->have_epoch & DPE_PART_CHANNELS), DPE_ESTATE,
+                "replica_prepare before block_stage / the channel part of epoch_set");
     int rc = launch_prepare(c, (cudaStream_t)stream);
     if (rc) return rc;
     c->have_prepare = 1;
@@ -278,6 +302,7 @@ int dpe_code_scores_set(dpe_ctx* c, const double* cs, int C, void* stream) {
 int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
     DPE_REQUIRE(c->have_corr, DPE_ESTATE, "score_pos before correlogram");
+    DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_pos before the geometry part of epoch_set");
     DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
     int rc;
     if (score_mode == DPE_SCORE_LOOKUP) {
@@ -375,7 +400,7 @@ int dpe_debug_channel_flags(dpe_ctx* c, int32_t* idx_next, int32_t* no_flip, int
 int dpe_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, int64_t* f_idx, double* alpha,
                    void* stream) {
     DPE_REQUIRE(c && f_idx && alpha, DPE_EINVAL, "null argument");
-    DPE_REQUIRE(c->have_epoch, DPE_ESTATE, "debug_bins before epoch_set");
+    DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "debug_bins before the geometry part of epoch_set");
     DPE_REQUIRE(i0 >= 0 && n >= 1 && i0 + n <= c->G, DPE_EINVAL, "candidate range outside the grid");
     const size_t cnt = (size_t)n * c->epoch_C;
     if (c->dbg_f) { cudaFree(c->dbg_f); cudaFree(c->dbg_alpha); c->dbg_f = nullptr; c->dbg_alpha = nullptr; }
@@ -399,6 +424,36 @@ int dpe_debug_read(dpe_ctx* c, int which, size_t offset, void* dst, size_t nbyte
 }
 
 int64_t dpe_launch_count(dpe_ctx* c) { return c ? c->launches : -1; }
+
+int dpe_stream_create(void** stream) {
+    DPE_REQUIRE(stream, DPE_EINVAL, "null argument");
+    cudaStream_t s;
+    DPE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return DPE_OK;
+}
+int dpe_stream_destroy(void* stream) {
+    DPE_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return DPE_OK;
+}
+int dpe_stream_sync(void* stream) {
+    DPE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return DPE_OK;
+}
+int dpe_host_alloc(void** ptr, size_t bytes) {
+    DPE_REQUIRE(ptr && bytes, DPE_EINVAL, "bad argument");
+    DPE_CUDA(cudaMallocHost(ptr, bytes));
+    return DPE_OK;
+}
+int dpe_host_free(void* ptr) {
+    if (ptr) DPE_CUDA(cudaFreeHost(ptr));
+    return DPE_OK;
+}
+int dpe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 int dpe_profile_enable(dpe_ctx* c, int on) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");

@@ -1,0 +1,181 @@
+// modules.h -- the seven modules of the DPE flow, same names / ports / params as the reference
+// (cudarecv/dsp/src/dpeflow.cpp:56-62, port tables in each module's constructor).  The three
+// hot-path modules (SampleBlock, BatchCorrScores, BatchCorrManifold) do their device work
+// exclusively through the C ABI of libdpe_b200.so; the others are host C++ (north star).
+#ifndef DPE_HOST_MODULES_H_
+#define DPE_HOST_MODULES_H_
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "../../include/dpe_b200.h"
+#include "gnss.h"
+#include "module.h"
+
+namespace dsp {
+
+/** One dpe_ctx per flow, shared by the modules of that flow (they all receive the same
+ *  `void* cuFlowStream`, which keys the registry).  BatchCorrManifold::Start creates it. */
+struct SharedCtx {
+    dpe_ctx* ctx = nullptr;
+    dpe_epoch ep;                 // filled in two halves by BatchCorrScores / BatchCorrManifold
+    int score_mode = DPE_SCORE_LOOKUP;
+    int est_mode = DPE_EST_ARGMAX;
+};
+SharedCtx* SharedFor(void* cuFlowStream);
+void SharedRelease(void* cuFlowStream);
+inline void* StreamOf(void* cuFlowStream) { return *static_cast<void**>(cuFlowStream); }
+
+/** Parses the RINEX navigation file and the handoff CSV (dpinit.cpp:118-201); ends the flow
+ *  after MaxEpochs iterations (3000 in the reference, dpinit.cpp:231). */
+class DPInit : public Module {
+  public:
+    DPInit();
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override { Started = false; return 0; }
+
+  private:
+    static const unsigned int kNameCap = 1024;
+    char HandoffFilename[kNameCap] = {0}, RINEXFilename[kNameCap] = {0};
+    float initDeltaX = 0, initDeltaY = 0, initDeltaZ = 0, initDeltaT = 0;
+    int MaxEpochs = 3000;
+    bool Started = false;
+    long loopCounter = 0;
+    long long initByte = 0;
+    char initPRN[gnss::kPrnMax] = {0};
+    double initRC[gnss::kPrnMax], initRI[gnss::kPrnMax], initFC[gnss::kPrnMax], initFI[gnss::kPrnMax];
+    int initCP[gnss::kPrnMax], initCPTimestamp[gnss::kPrnMax], initCPRefTOW[gnss::kPrnMax];
+    double initX[8], initP[64], initRxTime = 0;
+    int initK = 0;
+    std::vector<gnss::EphSet> initEph;
+};
+
+/** File reader thread -> ring of page-locked 20 ms blocks (sampleblock.cu:312-515). */
+class SampleBlock : public Module {
+  public:
+    SampleBlock();
+    ~SampleBlock() override;
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override;
+
+  private:
+    static const unsigned int kNameCap = 1024;
+    static const int kNumBlocks = 32;              // NumBlocksDefault of the reference
+    char Filename[kNameCap] = {0}, Hostname[kNameCap] = {0};
+    int PortNo = 0;
+    double SamplingFrequency = 2.5e6, SampleLength = 0.02;
+    bool RunLive = false;
+    char InputSourceType = 0;
+    int64_t BlockLength = 0;                       // samples per block (64-bit: 10 MHz works)
+    std::vector<int16_t*> Blocks;                  // pinned host ring
+    FILE* fp = nullptr;
+    std::thread reader;
+    std::mutex mu;
+    std::condition_variable cv;
+    int filled = 0, freeSlots = 0, loadIdx = 0, procIdx = -1;
+    bool eof = false, firstUpdate = true, Started = false;
+    std::atomic<bool> KeepRunning{false};
+    void ReaderThread();
+};
+
+/** int16 unpack, wipe-off, replica, windowed code correlogram: dpe_block_stage +
+ *  dpe_epoch_set_part(CHANNELS) + dpe_replica_prepare + dpe_correlogram. */
+class BatchCorrScores : public Module {
+  public:
+    BatchCorrScores();
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override { Started = false; return 0; }
+
+  private:
+    bool Started = false;
+    int numFFTPoints = 0;
+};
+
+/** Position-clock manifold: owns the grid (generated or CSV), dpe_epoch_set_part(GEOMETRY) +
+ *  dpe_score_pos + dpe_estimate + dpe_result_fetch -> zVal / RVal. */
+class BatchCorrManifold : public Module {
+  public:
+    BatchCorrManifold();
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override;
+
+  private:
+    static const unsigned int kNameCap = 1024;
+    int posGridDimSize = 25, velGridDimSize = 25, gridType = 0, LPower = 1;
+    float gridDimSpacing = 1.0f;
+    bool loadPosGrid = false;
+    char Filename[kNameCap] = "", loadPosGridFilename[kNameCap] = "";
+    // extensions (not in the reference): scoring path, estimator, lag window
+    bool bruteForce = false, weightedMean = false;
+    int lagHalfwidth = 32;
+    bool Started = false;
+    void* flowStream = nullptr;
+    std::vector<double> grid, timeGrid;
+    double zVal[16], RVal[64];
+    dpe_result last;
+};
+
+/** EKF disabled in the DPE flow: measurement copied into the state (cuekf.cu:147-159,577-592). */
+class cuEKF : public Module {
+  public:
+    cuEKF();
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override { Started = false; return 0; }
+
+  private:
+    double SampleLength = 0.02;
+    bool EnableEKF = false, Started = false;
+    double xkk1[8], xk1k1[8], Pkk1[64];
+};
+
+/** Channel manager + satellite states on the host (cuchanmgr.cu:240-923 runs them on the GPU). */
+class cuChanMgr : public Module {
+  public:
+    cuChanMgr();
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override { Started = false; return 0; }
+
+  private:
+    int dopplerSign = 1;
+    bool Started = false;
+    int numChan = 0, timeDim = 1;
+    double T = 0.02, rxTime = 0;
+    uint8_t PRNs[gnss::kPrnMax];
+    double rcStart[gnss::kPrnMax], rcEnd[gnss::kPrnMax], riStart[gnss::kPrnMax], riEnd[gnss::kPrnMax];
+    double fc[gnss::kPrnMax], fi[gnss::kPrnMax], txTime[gnss::kPrnMax];
+    int cpStart[gnss::kPrnMax], cpEnd[gnss::kPrnMax], cpRef[gnss::kPrnMax], cpRefTOW[gnss::kPrnMax];
+    int dopplerSignArr[gnss::kPrnMax];
+    gnss::SatState sat[gnss::kPrnMax];
+    std::vector<gnss::SatState> batchSat;
+    double enu2ecef[9];
+    const std::vector<gnss::EphSet>* nav = nullptr;
+    int TimeUpdate(int i, const double* x, double rxT);
+    void GridPrep(const double* xkk1, const double* timeGrid);
+};
+
+/** Port tap -> CSV ("%f, " per value, one row per Update) or binary (datalogger.cu:141-213). */
+class DataLogger : public Module {
+  public:
+    explicit DataLogger(const char* name = "DataLogger");
+    int Start(void*) override;
+    int Update(void*) override;
+    int Stop() override;
+
+  private:
+    static const unsigned int kNameCap = 1024;
+    char Filename[kNameCap] = {0};
+    bool csv = true, Started = false;
+    FILE* fp = nullptr;
+};
+
+}  // namespace dsp
+#endif

@@ -1,0 +1,233 @@
+// modules_dpe.cpp -- BatchCorrScores and BatchCorrManifold: the two hot-path modules.  Their
+// Update() bodies gather the same input ports as the reference's modules and make C-ABI calls;
+// no device code, no CUDA runtime here.
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include "modules.h"
+
+namespace dsp {
+
+static std::mutex g_mu;
+static std::map<void*, SharedCtx*> g_shared;
+
+SharedCtx* SharedFor(void* key) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    SharedCtx*& p = g_shared[key];
+    if (!p) { p = new SharedCtx(); std::memset(&p->ep, 0, sizeof(p->ep)); }
+    return p;
+}
+
+void SharedRelease(void* key) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::map<void*, SharedCtx*>::iterator it = g_shared.find(key);
+    if (it == g_shared.end()) return;
+    if (it->second->ctx) dpe_ctx_destroy(it->second->ctx);
+    delete it->second;
+    g_shared.erase(it);
+}
+
+#define DPE_CALL(stmt)                                                                          \
+    do {                                                                                        \
+        if ((stmt) != DPE_OK) {                                                                 \
+            std::cerr << "[" << ModuleName << "] " #stmt " failed: " << dpe_last_error() << std::endl; \
+            return -1;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// BatchCorrScores (input table: cudarecv/modules/src/batchcorrscores.cu:681-698)
+// ------------------------------------------------------------------------------------------
+BatchCorrScores::BatchCorrScores() {
+    ModuleName = "BatchCorrScores";
+    AllocateInputs(11);
+    ConfigExpectedInput(0, "Samples", UNDEFINED_t, VALUE_CMPX, VECTORLENGTH_ANY);
+    ConfigExpectedInput(1, "ValidPRNs", CHAR_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(2, "CodePhaseStart", DOUBLE_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(3, "CarrierPhaseStart", DOUBLE_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(4, "CodeFrequency", DOUBLE_t, FREQUENCY_HZ, VECTORLENGTH_ANY);
+    ConfigExpectedInput(5, "CarrierFrequency", DOUBLE_t, FREQUENCY_HZ, VECTORLENGTH_ANY);
+    ConfigExpectedInput(6, "cpElapsedStart", INT_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(7, "cpReference", INT_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(8, "DopplerSign", INT_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(9, "SamplingFrequency", DOUBLE_t, FREQUENCY_HZ, 1);
+    ConfigExpectedInput(10, "SampleLength", DOUBLE_t, VALUE, 1);
+    AllocateOutputs(3);
+    ConfigOutput(0, "CodeScores", UNDEFINED_t, VALUE_CMPX, CUDA_DEVICE, VECTORLENGTH_ANY, nullptr, 0);
+    ConfigOutput(1, "CarrScores", UNDEFINED_t, VALUE_CMPX, CUDA_DEVICE, VECTORLENGTH_ANY, nullptr, 0);
+    ConfigOutput(2, "NumFFTPoints", INT_t, VALUE, HOST, 1, &numFFTPoints, 0);
+}
+
+int BatchCorrScores::Start(void*) {
+    if (Started) return 0;
+    if (!InputsConnected()) return -1;
+    const double fs = *In<double>(9), T = *In<double>(10);
+    const int64_t S = (int64_t)(fs * T + 0.5);
+    int64_t p2 = 1;
+    while (p2 < S) p2 <<= 1;
+    numFFTPoints = (int)(p2 * 8);                  // carrSTot, batchcorrscores.cu:761
+    Started = true;
+    return 0;
+}
+
+int BatchCorrScores::Update(void* cuFlowStream) {
+    if (!Started) return -1;
+    SharedCtx* sh = SharedFor(cuFlowStream);
+    if (!sh->ctx) { std::cerr << "[" << ModuleName << "] no context (BatchCorrManifold not started)" << std::endl; return -1; }
+    void* stream = StreamOf(cuFlowStream);
+    const int C = (int)InLen(1);
+    dpe_epoch& ep = sh->ep;
+    ep.C = C;
+    ep.doppler_sign = In<int>(8)[0];
+    for (int i = 0; i < C; ++i) {
+        ep.prn[i] = (uint8_t)In<char>(1)[i];
+        ep.rc_start[i] = In<double>(2)[i];
+        ep.ri_start[i] = In<double>(3)[i];
+        ep.fc[i] = In<double>(4)[i];
+        ep.fi[i] = In<double>(5)[i];
+        ep.cp_start[i] = In<int>(6)[i];
+        ep.cp_ref[i] = In<int>(7)[i];
+    }
+    DPE_CALL(dpe_block_stage(sh->ctx, In<int16_t>(0), InLen(0), stream));
+    DPE_CALL(dpe_epoch_set_part(sh->ctx, &ep, nullptr, DPE_PART_CHANNELS, stream));
+    DPE_CALL(dpe_replica_prepare(sh->ctx, stream));
+    DPE_CALL(dpe_correlogram(sh->ctx, stream));
+    // the window of CodeScores a position grid can reach: [C][2W+2] complex doubles on the device
+    UpdateOutput(0, C, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_CODE_SCORES)), 0);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchCorrManifold (input table: cudarecv/modules/src/batchcorrmanifold.cu:2261-2300)
+// ------------------------------------------------------------------------------------------
+BatchCorrManifold::BatchCorrManifold() {
+    ModuleName = "BatchCorrManifold";
+    AllocateInputs(19);
+    ConfigExpectedInput(0, "CodeScores", UNDEFINED_t, VALUE_CMPX, VECTORLENGTH_ANY);
+    ConfigExpectedInput(1, "CarrScores", UNDEFINED_t, VALUE_CMPX, VECTORLENGTH_ANY);
+    ConfigExpectedInput(2, "xCurrkk1", DOUBLE_t, STATE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(3, "txTime", DOUBLE_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(4, "SatStates", DOUBLE_t, STATE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(5, "rxTime", DOUBLE_t, VALUE, 1);
+    ConfigExpectedInput(6, "SampleLength", DOUBLE_t, VALUE, 1);
+    ConfigExpectedInput(7, "SamplingFrequency", DOUBLE_t, FREQUENCY_HZ, 1);
+    ConfigExpectedInput(8, "CodeFrequency", DOUBLE_t, FREQUENCY_HZ, VECTORLENGTH_ANY);
+    ConfigExpectedInput(9, "CarrierFrequency", DOUBLE_t, FREQUENCY_HZ, VECTORLENGTH_ANY);
+    ConfigExpectedInput(10, "DopplerSign", INT_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(11, "NumFFTPoints", INT_t, VALUE, 1);
+    ConfigExpectedInput(12, "ENU2ECEFMat", DOUBLE_t, VALUE, 9);
+    ConfigExpectedInput(13, "SatStatesOld", DOUBLE_t, STATE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(14, "CodePhase", DOUBLE_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(15, "CarrierPhase", DOUBLE_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(16, "cpRefTOW", INT_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(17, "cpElapsedEnd", INT_t, VALUE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(18, "cpRef", INT_t, VALUE, VECTORLENGTH_ANY);
+    InsertParam("PosGridDimSize", &posGridDimSize, INT_t, sizeof(int), sizeof(int));
+    InsertParam("VelGridDimSize", &velGridDimSize, INT_t, sizeof(int), sizeof(int));
+    InsertParam("GridDimSpacing", &gridDimSpacing, FLOAT_t, sizeof(float), sizeof(float));
+    InsertParam("GridType", &gridType, INT_t, sizeof(int), sizeof(int));
+    InsertParam("LPower", &LPower, INT_t, sizeof(int), sizeof(int));
+    InsertParam("GridLogFileName", Filename, CHAR_t, kNameCap, 0);
+    InsertParam("LoadPosGrid", &loadPosGrid, BOOL_t, sizeof(bool), sizeof(bool));
+    InsertParam("LoadPosGridFilename", loadPosGridFilename, CHAR_t, kNameCap, 0);
+    InsertParam("BruteForce", &bruteForce, BOOL_t, sizeof(bool), sizeof(bool));          // north-star kernel
+    InsertParam("WeightedMean", &weightedMean, BOOL_t, sizeof(bool), sizeof(bool));      // dormant Method 1
+    InsertParam("LagHalfwidth", &lagHalfwidth, INT_t, sizeof(int), sizeof(int));
+    AllocateOutputs(4);
+    ConfigOutput(0, "zVal", DOUBLE_t, STATE, HOST, 8, zVal, 0);
+    ConfigOutput(1, "RVal", DOUBLE_t, COVARIANCE, HOST, 64, RVal, 0);
+    ConfigOutput(2, "TimeGrid", DOUBLE_t, VALUE, HOST, VECTORLENGTH_ANY, nullptr, 0);
+    ConfigOutput(3, "PosScores", DOUBLE_t, GRID, CUDA_DEVICE, VECTORLENGTH_ANY, nullptr, 0);
+    std::memset(zVal, 0, sizeof(zVal));
+    for (int i = 0; i < 64; ++i) RVal[i] = (i % 9 == 0) ? 1.0 : 0.0;
+}
+
+int BatchCorrManifold::Start(void* cuFlowStream) {
+    if (Started) return 0;
+    if (!InputsConnected()) return -1;
+    const int dims[4] = {posGridDimSize, posGridDimSize, posGridDimSize, posGridDimSize};
+    const double sp[4] = {gridDimSpacing, gridDimSpacing, gridDimSpacing, gridDimSpacing};
+    if (gridType != 0 && gridType != 2) { std::clog << "[" << ModuleName << "] unsupported manifold type" << std::endl; return -1; }
+    gnss::MakeGrid(dims, sp, gridType, &grid, &timeGrid);     // timeGrid always comes from the generated grid
+    if (loadPosGrid) {                                        // (batchcorrmanifold.cu:2416-2448)
+        std::vector<double> g;
+        if (gnss::ReadGridCsv(loadPosGridFilename, &g)) {
+            std::clog << "[" << ModuleName << "] Open loadGridFile failed: " << loadPosGridFilename << std::endl;
+            return -1;
+        }
+        if (g.size() != grid.size()) {
+            std::clog << "[" << ModuleName << "] grid file holds " << g.size() / 4 << " points, PosGridDimSize^4 = "
+                      << grid.size() / 4 << std::endl;
+            return -1;
+        }
+        grid.swap(g);
+    }
+    const double fs = *In<double>(7), T = *In<double>(6);
+    dpe_cfg cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = DPE_ABI_VERSION;
+    cfg.device = 0;
+    cfg.fs = fs;
+    cfg.S = (int64_t)(fs * T + 0.5);
+    cfg.max_chan = DPE_MAX_CHAN;
+    cfg.time_dim = posGridDimSize;
+    cfg.G = cfg.G_total = (int64_t)grid.size() / 4;
+    cfg.lpower = LPower;
+    cfg.lag_halfwidth = lagHalfwidth;
+    cfg.flags = bruteForce ? DPE_FLAG_BRUTE_TILES : 0;
+    SharedCtx* sh = SharedFor(cuFlowStream);
+    if (sh->ctx) { dpe_ctx_destroy(sh->ctx); sh->ctx = nullptr; }
+    DPE_CALL(dpe_ctx_create(&sh->ctx, &cfg));
+    sh->score_mode = bruteForce ? DPE_SCORE_BRUTE : DPE_SCORE_LOOKUP;
+    sh->est_mode = weightedMean ? DPE_EST_WEIGHTED : DPE_EST_ARGMAX;
+    void* stream = StreamOf(cuFlowStream);
+    DPE_CALL(dpe_grid_set(sh->ctx, grid.data(), cfg.G, stream));
+    DPE_CALL(dpe_stream_sync(stream));
+    UpdateOutput(2, (int64_t)timeGrid.size(), timeGrid.data(), 0);
+    UpdateOutput(3, cfg.G, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_POS_SCORES)), 0);
+    flowStream = cuFlowStream;
+    Started = true;
+    return 0;
+}
+
+int BatchCorrManifold::Update(void* cuFlowStream) {
+    if (!Started) return -1;
+    SharedCtx* sh = SharedFor(cuFlowStream);
+    void* stream = StreamOf(cuFlowStream);
+    dpe_epoch& ep = sh->ep;
+    const int C = (int)InLen(8);
+    if (C != ep.C) { std::cerr << "[" << ModuleName << "] channel count differs from BatchCorrScores" << std::endl; return -1; }
+    for (int i = 0; i < C; ++i) {
+        ep.fc[i] = In<double>(8)[i];
+        ep.rc_end[i] = In<double>(14)[i];
+        ep.cp_ref_tow[i] = In<int>(16)[i];
+        ep.cp_end[i] = In<int>(17)[i];
+        ep.cp_ref[i] = In<int>(18)[i];
+    }
+    ep.rx_time = *In<double>(5);
+    for (int i = 0; i < 8; ++i) ep.center[i] = In<double>(2)[i];
+    for (int i = 0; i < 9; ++i) ep.enu2ecef[i] = In<double>(12)[i];
+    DPE_CALL(dpe_epoch_set_part(sh->ctx, &ep, In<double>(4), DPE_PART_GEOMETRY, stream));
+    const int sat_mode = (sh->est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
+    DPE_CALL(dpe_score_pos(sh->ctx, sh->score_mode, sat_mode, stream));
+    DPE_CALL(dpe_estimate(sh->ctx, sh->est_mode, nullptr, 1, stream));
+    DPE_CALL(dpe_result_fetch(sh->ctx, &last, stream));
+    if (last.out_of_window)
+        std::clog << "[" << ModuleName << "] " << last.out_of_window << " candidate-PRN pairs outside the lag window"
+                  << std::endl;
+    for (int i = 0; i < 4; ++i) zVal[i] = last.z[i];
+    // velocity / drift half of zVal: the velocity manifold is not built in this round;
+    // the prediction is passed through so the 8-state hand-over to cuEKF / cuChanMgr stays defined
+    for (int i = 4; i < 8; ++i) zVal[i] = ep.center[i];
+    return 0;
+}
+
+int BatchCorrManifold::Stop() {
+    if (Started && flowStream) SharedRelease(flowStream);
+    Started = false;
+    return 0;
+}
+
+}  // namespace dsp

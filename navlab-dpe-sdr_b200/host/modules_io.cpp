@@ -1,0 +1,277 @@
+// modules_io.cpp -- DPInit, SampleBlock, cuEKF (pass-through), DataLogger: the host modules
+// either side of the hot path.
+#include <cerrno>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include "modules.h"
+
+namespace dsp {
+
+// ------------------------------------------------------------------------------------------
+// DPInit (cudarecv/modules/src/dpinit.cpp:66-238)
+// ------------------------------------------------------------------------------------------
+DPInit::DPInit() {
+    ModuleName = "DPInit";
+    AllocateInputs(0);
+    AllocateOutputs(14);
+    ConfigOutput(0, "StartByte", INT_t, VALUE, HOST, 1, &initByte, 0);
+    ConfigOutput(1, "InitPRN", CHAR_t, VALUE, HOST, VECTORLENGTH_ANY, initPRN, 0);
+    ConfigOutput(2, "InitCodePhase", DOUBLE_t, VALUE, HOST, VECTORLENGTH_ANY, initRC, 0);
+    ConfigOutput(3, "InitCarrierPhase", DOUBLE_t, VALUE, HOST, VECTORLENGTH_ANY, initRI, 0);
+    ConfigOutput(4, "InitCodeFrequency", DOUBLE_t, FREQUENCY_HZ, HOST, VECTORLENGTH_ANY, initFC, 0);
+    ConfigOutput(5, "InitCarrierFrequency", DOUBLE_t, FREQUENCY_HZ, HOST, VECTORLENGTH_ANY, initFI, 0);
+    ConfigOutput(6, "InitElapsedCodePeriods", INT_t, VALUE, HOST, VECTORLENGTH_ANY, initCP, 0);
+    ConfigOutput(7, "InitReferenceCodePeriods", INT_t, VALUE, HOST, VECTORLENGTH_ANY, initCPTimestamp, 0);
+    ConfigOutput(8, "InitCPRefTOW", INT_t, VALUE, HOST, VECTORLENGTH_ANY, initCPRefTOW, 0);
+    ConfigOutput(9, "InitX", DOUBLE_t, STATE, HOST, VECTORLENGTH_ANY, initX, 0);
+    ConfigOutput(10, "InitP", DOUBLE_t, COVARIANCE, HOST, VECTORLENGTH_ANY, initP, 0);
+    ConfigOutput(11, "InitK", INT_t, VALUE, HOST, 1, &initK, 0);
+    ConfigOutput(12, "InitRXTime", DOUBLE_t, VALUE, HOST, 1, &initRxTime, 0);
+    ConfigOutput(13, "InitEph", UNDEFINED_t, EPHEMS, HOST, 1, &initEph, 0);
+    InsertParam("HandoffFilename", HandoffFilename, CHAR_t, kNameCap, 0);
+    InsertParam("RINEXFilename", RINEXFilename, CHAR_t, kNameCap, 0);
+    InsertParam("InitDeltaX", &initDeltaX, FLOAT_t, sizeof(float), sizeof(float));
+    InsertParam("InitDeltaY", &initDeltaY, FLOAT_t, sizeof(float), sizeof(float));
+    InsertParam("InitDeltaZ", &initDeltaZ, FLOAT_t, sizeof(float), sizeof(float));
+    InsertParam("InitDeltaT", &initDeltaT, FLOAT_t, sizeof(float), sizeof(float));
+    InsertParam("MaxEpochs", &MaxEpochs, INT_t, sizeof(int), sizeof(int));      // 3000 in the reference
+    std::memset(initX, 0, sizeof(initX));
+}
+
+int DPInit::Start(void*) {
+    if (Started) return 0;
+    if (gnss::ReadRinexNav(RINEXFilename, &initEph)) {
+        std::clog << "[" << ModuleName << "] Open RINEXParamsFile failed: " << RINEXFilename << std::endl;
+        return -1;
+    }
+    gnss::Handoff h;
+    if (gnss::ReadHandoff(HandoffFilename, &h)) {
+        std::clog << "[" << ModuleName << "] Open handoffParamsFile failed: " << HandoffFilename << std::endl;
+        return -1;
+    }
+    const int n = (int)h.prn.size();
+    if (n > gnss::kPrnMax) return -1;
+    for (int i = 0; i < n; ++i) {
+        initPRN[i] = (char)h.prn[i];
+        initRC[i] = h.rc[i]; initRI[i] = h.ri[i]; initFC[i] = h.fc[i]; initFI[i] = h.fi[i];
+        initCP[i] = h.cp[i]; initCPTimestamp[i] = h.cp_timestamp[i]; initCPRefTOW[i] = h.TOW[i];
+    }
+    for (int i = 0; i < 8; ++i) initX[i] = h.X_ECEF[i];
+    // InitDelta{X,Y,Z,T}: ECEF / clock offset of the first grid centre (PerturbInitialization, dpinit.cpp:55-61)
+    initX[0] += initDeltaX; initX[1] += initDeltaY; initX[2] += initDeltaZ; initX[3] += initDeltaT;
+    for (int i = 0; i < 64; ++i) initP[i] = (i % 9 == 0) ? 1.0 : 0.0;
+    initK = 0;
+    initRxTime = h.rxTime;
+    initByte = h.bytes_read;
+    loopCounter = 0;
+    for (int id = 1; id <= 8; ++id) UpdateOutput((unsigned char)id, n, outputs[id].Data, 0);
+    UpdateOutput(9, 8, initX, 0);
+    UpdateOutput(10, 64, initP, 0);
+    UpdateOutput(13, (int64_t)initEph.size(), &initEph, 0);
+    std::clog << "[" << ModuleName << "] Updated outputs" << std::endl;
+    Started = true;
+    return 0;
+}
+
+int DPInit::Update(void*) {
+    if (loopCounter % 500 == 0) std::clog << "[" << ModuleName << "] Started iteration " << loopCounter << std::endl;
+    loopCounter++;
+    return (loopCounter >= MaxEpochs) ? -1 : 0;       // "bootleg way to end the pipeline", dpinit.cpp:229-235
+}
+
+// ------------------------------------------------------------------------------------------
+// SampleBlock (cudarecv/modules/src/sampleblock.cu)
+// ------------------------------------------------------------------------------------------
+SampleBlock::SampleBlock() {
+    ModuleName = "SampleBlock";
+    AllocateInputs(1);
+    ConfigExpectedInput(0, "StartByte", INT_t, VALUE, 1);
+    AllocateOutputs(3);
+    // the reference hands over a device pointer filled by its reader thread; here the block stays in
+    // page-locked host memory and BatchCorrScores stages it with dpe_block_stage on the flow stream
+    ConfigOutput(0, "Samples", UNDEFINED_t, VALUE_CMPX, HOST, 2, nullptr, 0);
+    ConfigOutput(1, "SamplingFrequency", DOUBLE_t, FREQUENCY_HZ, HOST, 1, &SamplingFrequency, 0);
+    ConfigOutput(2, "SampleLength", DOUBLE_t, VALUE, HOST, 1, &SampleLength, 0);
+    InsertParam("Filename", Filename, CHAR_t, kNameCap, 0);
+    InsertParam("Hostname", Hostname, CHAR_t, kNameCap, 0);
+    InsertParam("PortNo", &PortNo, INT_t, sizeof(int), sizeof(int));
+    InsertParam("SamplingFrequency", &SamplingFrequency, DOUBLE_t, sizeof(double), sizeof(double));
+    InsertParam("SampleLength", &SampleLength, DOUBLE_t, sizeof(double), sizeof(double));
+    InsertParam("RunLive", &RunLive, BOOL_t, sizeof(bool), sizeof(bool));
+    InsertParam("InputSourceType", &InputSourceType, CHAR_t, sizeof(char), sizeof(char));
+}
+
+SampleBlock::~SampleBlock() { Stop(); }
+
+int SampleBlock::Start(void*) {
+    if (Started) return 0;
+    if (!InputsConnected()) return -1;
+    if (InputSourceType != 0) { std::cerr << "[SampleBlock] only the file source is built" << std::endl; return -1; }
+    fp = std::fopen(Filename, "rb");
+    if (!fp) { std::cerr << "[SampleBlock] Unable to open file: " << Filename << std::endl; return -1; }
+    const long long start = *In<long long>(0);
+    // the reference rejects StartByte 0 (lseek()==0 is read as a failure, sampleblock.cu:123-128); accepted here
+    if (start < 0 || fseeko(fp, (off_t)start, SEEK_SET)) {
+        std::cerr << "[SampleBlock] Failed to skip ahead in file: " << Filename << std::endl;
+        std::fclose(fp); fp = nullptr;
+        return -1;
+    }
+    std::clog << "[" << ModuleName << "] Starting reading at byte " << start << " in file " << Filename << std::endl;
+    BlockLength = (int64_t)(SamplingFrequency * SampleLength + 0.5);
+    Blocks.assign(kNumBlocks, nullptr);
+    for (int i = 0; i < kNumBlocks; ++i)
+        if (dpe_host_alloc((void**)&Blocks[i], sizeof(int16_t) * 2 * (size_t)BlockLength)) {
+            std::cerr << "[SampleBlock] Unable to allocate sample buffers: " << dpe_last_error() << std::endl;
+            return -1;
+        }
+    UpdateOutput(0, BlockLength, nullptr, 0);
+    filled = 0; freeSlots = kNumBlocks; loadIdx = 0; procIdx = -1; eof = false; firstUpdate = true;
+    KeepRunning = true;
+    reader = std::thread(&SampleBlock::ReaderThread, this);
+    Started = true;
+    return 0;
+}
+
+void SampleBlock::ReaderThread() {
+    const size_t bytes = sizeof(int16_t) * 2 * (size_t)BlockLength;
+    long blockCnt = 0;
+    while (KeepRunning) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return freeSlots > 0 || !KeepRunning; });
+            if (!KeepRunning) break;
+        }
+        const size_t got = std::fread(Blocks[loadIdx], 1, bytes, fp);
+        if (got != bytes) {                       // partial block at EOF is dropped like the reference does
+            std::lock_guard<std::mutex> lk(mu);
+            eof = true;
+            cv.notify_all();
+            std::clog << "[SampleBlock] Reached EOF." << std::endl << "[SampleBlock] blockCnt = " << blockCnt << std::endl;
+            break;
+        }
+        ++blockCnt;
+        loadIdx = (loadIdx + 1) % kNumBlocks;
+        std::lock_guard<std::mutex> lk(mu);
+        --freeSlots; ++filled;
+        cv.notify_all();
+    }
+}
+
+int SampleBlock::Update(void*) {
+    if (!Started) { std::cerr << "[SampleBlock] Thread not running." << std::endl; return -1; }
+    std::unique_lock<std::mutex> lk(mu);
+    if (firstUpdate) firstUpdate = false;
+    else { ++freeSlots; cv.notify_all(); }       // the block of the previous epoch may be refilled now
+    // 1.5 s like the reference (sampleblock.cu:484); buffers are only released in Stop(), after the flow ended
+    if (!cv.wait_for(lk, std::chrono::milliseconds(1500), [&] { return filled > 0 || eof; })) {
+        std::cerr << "[SampleBlock] Error: sem_timewait timeout: samplesAvailSem" << std::endl;
+        return -1;
+    }
+    if (filled == 0) return -1;                    // EOF: ends the flow
+    --filled;
+    procIdx = (procIdx + 1) % kNumBlocks;
+    outputs[0].Data = Blocks[procIdx];
+    return 0;
+}
+
+int SampleBlock::Stop() {
+    if (!Started) return 0;
+    KeepRunning = false;
+    { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
+    if (reader.joinable()) reader.join();
+    for (size_t i = 0; i < Blocks.size(); ++i) dpe_host_free(Blocks[i]);
+    Blocks.clear();
+    if (fp) { std::fclose(fp); fp = nullptr; }
+    Started = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// cuEKF: the DPE flow runs it with EnableEKF=false (dpeflow.cpp:90) => EKF_PassMeas
+// ------------------------------------------------------------------------------------------
+cuEKF::cuEKF() {
+    ModuleName = "cuEKF";
+    AllocateInputs(5);
+    ConfigExpectedInput(0, "InitX", DOUBLE_t, STATE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(1, "InitP", DOUBLE_t, COVARIANCE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(2, "InitK", INT_t, VALUE, 1);
+    ConfigExpectedInput(3, "zVal", DOUBLE_t, STATE, VECTORLENGTH_ANY);
+    ConfigExpectedInput(4, "RVal", DOUBLE_t, COVARIANCE, VECTORLENGTH_ANY);
+    AllocateOutputs(3);
+    ConfigOutput(0, "xCurrkk1", DOUBLE_t, STATE, HOST, 8, xkk1, 0);
+    ConfigOutput(1, "PCurrkk1", DOUBLE_t, COVARIANCE, HOST, 64, Pkk1, 0);
+    ConfigOutput(2, "xCurrk1k1", DOUBLE_t, STATE, HOST, 8, xk1k1, 0);
+    InsertParam("SampleLength", &SampleLength, DOUBLE_t, sizeof(double), sizeof(double));
+    InsertParam("EnableEKF", &EnableEKF, BOOL_t, sizeof(bool), sizeof(bool));
+}
+
+int cuEKF::Start(void*) {
+    if (Started) return 0;
+    if (!InputsConnected()) return -1;
+    if (EnableEKF) {
+        std::cerr << "[cuEKF] the 8-state filter is out of scope (SURVEY.md section 8 f-4); EnableEKF must be false"
+                  << std::endl;
+        return -1;
+    }
+    for (int i = 0; i < 8; ++i) xkk1[i] = xk1k1[i] = In<double>(0)[i];      // cuekf.cu:338-344
+    for (int i = 0; i < 64; ++i) Pkk1[i] = In<double>(1)[i];
+    Started = true;
+    return 0;
+}
+
+int cuEKF::Update(void*) {
+    // exactly 8 values (the reference copies 16, reading past zVal)
+    for (int i = 0; i < 8; ++i) xk1k1[i] = xkk1[i] = In<double>(3)[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// DataLogger (cudarecv/modules/src/datalogger.cu): "%f" values, ", " separated, one row per epoch
+// ------------------------------------------------------------------------------------------
+DataLogger::DataLogger(const char* name) {
+    ModuleName = name;
+    AllocateInputs(1);
+    ConfigExpectedInput(0, "Data", DATATYPE_ANY, VALUETYPE_ANY, VECTORLENGTH_ANY);
+    AllocateOutputs(0);
+    InsertParam("Filename", Filename, CHAR_t, kNameCap, 0);
+    InsertParam("CSV", &csv, BOOL_t, sizeof(bool), sizeof(bool));
+}
+
+int DataLogger::Start(void*) {
+    if (Started) return 0;
+    if (!InputsConnected()) return -1;
+    if (inputs[0]->MemLoc != HOST) { std::cerr << "[" << ModuleName << "] only HOST ports can be logged" << std::endl; return -1; }
+    fp = std::fopen(Filename, csv ? "w" : "wb");
+    if (!fp) { std::cerr << "[" << ModuleName << "] cannot open " << Filename << std::endl; return -1; }
+    Started = true;
+    return 0;
+}
+
+int DataLogger::Update(void*) {
+    const Port* p = inputs[0];
+    const int64_t n = p->Length;
+    if (!csv) {
+        const size_t sz = (p->Datatype == DOUBLE_t) ? 8 : (p->Datatype == INT_t || p->Datatype == FLOAT_t) ? 4 : 1;
+        return std::fwrite(p->Data, sz, (size_t)n, fp) == (size_t)n ? 0 : -1;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        double v = 0;
+        switch (p->Datatype) {
+            case DOUBLE_t: v = static_cast<const double*>(p->Data)[i]; break;
+            case FLOAT_t: v = static_cast<const float*>(p->Data)[i]; break;
+            case INT_t: v = static_cast<const int*>(p->Data)[i]; break;
+            default: v = static_cast<const char*>(p->Data)[i]; break;
+        }
+        std::fprintf(fp, (i + 1 < n) ? "%f, " : "%f\n", v);
+    }
+    return 0;
+}
+
+int DataLogger::Stop() {
+    if (fp) { std::fclose(fp); fp = nullptr; }
+    Started = false;
+    return 0;
+}
+
+}  // namespace dsp

@@ -1,0 +1,251 @@
+"""Host-side mirror of the reference's dsp module / flow / console interface
+(navlab-dpe-sdr_b200/host/, libdpe_flow.so).  CPU part: console grammar, host GPS code against
+the oracle, N>1 partial combination over gloo.  GPU part: `newflow dpe / setparam / loadflow /
+startflow` end to end on synthetic files against the oracle closed loop and the reference's own
+epochs (tests/golden/ref_epochs_n9.npz)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import orc, synth
+from oracle import chanmgr_oracle as chm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def flowapi():
+    import dpe_pkg
+    fa = dpe_pkg.submodule("flowapi")
+    if not os.path.exists(fa.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return fa
+
+
+def test_flow_library_exports(flowapi):
+    import ctypes
+    lib = ctypes.CDLL(flowapi.LIB_PATH)
+    for name in flowapi.EXPORTS:
+        assert hasattr(lib, name)
+
+
+def test_console_grammar_and_param_typing(flowapi):
+    sh = flowapi.Shell()
+    assert sh.exec("bogus") == -1
+    assert sh.exec("newf") == -1                       # missing option
+    assert sh.exec("NEW dpe") == -1                    # mandatory part is NEWF
+    assert sh.exec("newflow acq") == -1                # the stale dofile's flow type does not exist
+    assert sh.exec("newf dpe rx") == 0                 # "DPE", 3 mandatory letters, case-insensitive
+    assert sh.exec("loadflow rx") == 0
+    assert sh.exec("loadflow rx") == -1                # already loaded
+    assert sh.exec("setparam rx BatchCorrManifold PosGridDimSize 9") == 0
+    assert sh.exec("setp rx BatchCorrManifold PosGridDimSize 9.0") == -1      # float literal into an INT param
+    assert sh.exec("setp rx BatchCorrManifold GridDimSpacing 5.0") == 0       # FLOAT param
+    assert sh.exec("setp rx SampleBlock SamplingFrequency 2.5e6") == -1       # reference quirk: no double literal
+    assert sh.exec("setp rx SampleBlock SamplingFrequency 2.5e6d") == 0       # extension: d suffix = double
+    assert sh.exec('setp rx SampleBlock Filename "/tmp/x.dat"') == 0
+    assert sh.exec("setp rx cuEKF EnableEKF false") == 0
+    assert sh.exec("setp rx NoSuchModule X 1") == -1
+    assert sh.exec("printport rx BatchCorrManifold zVal") == 0
+    assert sh.exec("printport rx BatchCorrManifold nope") == -1
+    assert sh.exec("addalias second 0") == 0 and sh.exec("lsflow") == 0 and sh.exec("actalias") == 0
+    z = sh.read_port("rx", "BatchCorrManifold", "zVal")
+    assert z.shape == (8,) and not z.any()
+    assert sh.exec("delflow rx") == 0 and sh.exec("loadflow rx") == -1
+    assert sh.exec("quit -f") == 1
+    sh.close()
+
+
+def test_console_binary_runs_a_dofile(flowapi, tmp_path):
+    do = tmp_path / "client.dofile"
+    do.write_text("# comment\nnewflow dpe\nloadflow 0\nsetparam 0 BatchCorrManifold LPower 2\nlsflow\nquit -f\n")
+    r = subprocess.run([flowapi.CONSOLE_PATH, "-f", str(do)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0
+    assert "0: DPE" in r.stdout and "Completed LoadFlow" in r.stderr
+
+
+def test_host_satellite_state_matches_oracle(flowapi):
+    sc = H.scenario()
+    nav = chm.read_rinex_nav(sc.cfg.rinex)
+    for prn in synth.PRNS_12:
+        for t in (414006.0, 414006.99, 417600.0):
+            ref = chm.get_sat_pos(chm.select_eph(nav, prn, t), t)
+            got = flowapi.sat_position(sc.cfg.rinex, prn, t)
+            assert np.max(np.abs(got[:3] - ref[:3])) < 1e-6            # metres
+            assert np.max(np.abs(got[4:7] - ref[4:7])) < 1e-9          # m/s
+            assert abs(got[3] - ref[3]) < 1e-15 and abs(got[7] - ref[7]) < 1e-18
+
+
+def test_host_grid_generation_matches_oracle(flowapi):
+    for gt in (orc.GRID_UNIFORM, orc.GRID_ARTHURBASIS):
+        for n in (5, 9, 12):
+            ref, _ = orc.init_pos_grid([n] * 4, [1.0, 2.0, 0.5, 6.0], gt)
+            got = flowapi.make_grid([n] * 4, [1.0, 2.0, 0.5, 6.0], gt)
+            assert np.array_equal(got, ref)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import dpe_pkg
+    sharding = dpe_pkg.submodule("sharding")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc, iq, grid, ep = H.epoch_case(n=7, center_offset=(6.0, -4.0, 3.0, 7.0))
+    if rank == 0:
+        blk = torch.from_numpy(iq.copy()).view(torch.uint8)          # NCCL / gloo have no int16: ship the bytes
+    else:
+        blk = torch.zeros(2 * iq.shape[0], dtype=torch.uint8)
+    dist.broadcast(blk, 0)                                           # the 20 ms block travels from rank 0
+    iq_r = blk.view(torch.int16).numpy()
+    lo, hi = sharding.shard_range(grid.shape[0], world, rank)
+    bcs = orc.batch_corr_scores(iq_r, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"])
+    r = H.oracle_pos(bcs, grid[lo:hi], ep)                          # this rank's shard of the grid
+    px, py, pz, pt = orc.candidate_ecef(grid[lo:hi], ep["center"], ep["enu2ecef"])
+    part = torch.from_numpy(sharding.make_partial(r["scores"], np.stack([px, py, pz, pt], 1), lo))
+    gathered = [torch.zeros_like(part) for _ in range(world)]
+    dist.all_gather(gathered, part)
+    res = {m: sharding.combine_partials(torch.stack(gathered).numpy(), m) for m in (0, 1)}
+    if rank == 0:
+        q.put((res, lo, hi))
+    dist.destroy_process_group()
+
+
+def test_sharded_estimate_over_gloo_world_size_2():
+    """N>1 path on CPU: block broadcast, contiguous grid shards, all-gather of the per-rank
+    partials, combination (lowest global index wins ties) == the single-rank answer."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    import queue as _queue
+    out = None
+    for _ in range(300):
+        try:
+            out = q.get(timeout=1)
+            break
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out is not None
+    res, lo, hi = out
+    sc, iq, grid, ep = H.epoch_case(n=7, center_offset=(6.0, -4.0, 3.0, 7.0))
+    bcs = H.oracle_bcs()
+    one = H.oracle_pos(bcs, grid, ep)
+    assert (lo, hi) == (0, (grid.shape[0] + 1) // 2)
+    assert res[0]["argmax"] == one["argmax"]
+    assert np.max(np.abs(res[0]["z"] - one["z"])) < 1e-9
+    w = H.oracle_pos(bcs, grid, ep, weighted=True, per_time=False)
+    assert np.max(np.abs(res[1]["z"] - w["z"])) < 1e-6
+    assert abs(res[0]["sum_score"] - one["scores"].sum()) / one["scores"].sum() < 1e-12
+
+
+def test_shard_ranges_cover_the_grid():
+    import dpe_pkg
+    sharding = dpe_pkg.submodule("sharding")
+    for G in (1, 7, 6561, 390625, 6765201):
+        for world in (1, 2, 3, 8):
+            r = [sharding.shard_range(G, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == G
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+    # ties: equal maxima on two ranks -> the lower global index
+    a = sharding.make_partial([1.0, 5.0], [[1, 1, 1, 1], [2, 2, 2, 2]], 0)
+    b = sharding.make_partial([5.0, 2.0], [[3, 3, 3, 3], [4, 4, 4, 4]], 2)
+    assert sharding.combine_partials([b, a])["argmax"] == 1
+    assert np.array_equal(sharding.combine_partials([a, b])["z"], [2, 2, 2, 2])
+
+
+# ---------------------------------------------------------------------------------------------
+def _write_scenario(tmp, n, epochs, first_block=1):
+    sc = H.scenario()
+    grid, _ = synth.uniform_grid(n, (5.0, 5.0, 5.0, 6.0))
+    files = sc.write_files(str(tmp), epochs + 2, grid=grid, handoff_block=first_block)
+    return sc, grid, files
+
+
+def _drive(flowapi, files, n, extra=(), epochs=-1, xfile=None):
+    sh = flowapi.Shell()
+    cmds = ["newflow dpe rx", "loadflow rx",
+            'setparam rx SampleBlock Filename "%s"' % files["dat"],
+            'setparam rx DPInit HandoffFilename "%s"' % files["handoff"],
+            'setparam rx DPInit RINEXFilename "%s"' % files["rinex"],
+            'setparam rx BatchCorrManifold LoadPosGridFilename "%s"' % files["grid"],
+            "setparam rx BatchCorrManifold LoadPosGrid true",
+            "setparam rx BatchCorrManifold PosGridDimSize %d" % n,
+            'setparam rx XECEFLogger Filename "%s"' % xfile] + list(extra)
+    for c in cmds:
+        assert sh.exec(c) == 0, c
+    assert sh.run_blocking("rx", epochs) == 0
+    return sh
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("brute", [False, True])
+def test_dpe_flow_end_to_end_against_oracle_closed_loop(flowapi, tmp_path, brute):
+    n, epochs = 7, 6
+    sc, grid, files = _write_scenario(tmp_path, n, epochs, first_block=0)
+    xfile = str(tmp_path / "XFile.csv")
+    extra = ["setparam rx DPInit InitDeltaX 6.0", "setparam rx DPInit InitDeltaY -4.0",
+             "setparam rx DPInit InitDeltaZ 3.0", "setparam rx DPInit InitDeltaT 7.0"]
+    if brute:
+        extra.append("setparam rx BatchCorrManifold BruteForce true")
+    sh = _drive(flowapi, files, n, extra, epochs, xfile)
+    st = sh.stats("rx")
+    assert st["run_count"] == epochs
+    rows = np.loadtxt(xfile, delimiter=",")
+    assert rows.shape == (epochs, 8)
+
+    # oracle closed loop: cuChanMgr restatement + BCS + BCM + pass-through EKF on the same files
+    nav = chm.read_rinex_nav(files["rinex"])
+    h = chm.read_handoff(files["handoff"])
+    x = h["X_ECEF"].copy()
+    x[:4] += (6.0, -4.0, 3.0, 7.0)
+    _, tg = synth.uniform_grid(n, (5.0, 5.0, 5.0, 6.0))
+    ch = chm.chanmgr_start(nav, h, sc.cfg.T, x)
+    for e in range(epochs):
+        sat, R = chm.grid_prep(ch, x, tg)
+        iq = sc.block(e)
+        bcs = orc.batch_corr_scores(iq, ch.prn, ch.rc_start, ch.ri_start, ch.fc, ch.fi, ch.cp_start, ch.cp_ref, sc.cfg.fs)
+        r = orc.pos_meas_ml(bcs["code_scores"], grid, x, R, sat, len(tg), ch.fc, ch.rc_end, ch.cp_ref_tow, ch.cp_end,
+                            ch.cp_ref, ch.rx_time, sc.cfg.fs, sc.S)
+        x = np.concatenate([r["z"], x[4:]])
+        # logged fix (6 decimals) vs oracle: position 0.1 m, clock 1 ns = 0.2998 m
+        assert np.max(np.abs(rows[e, :3] - x[:3])) < 0.1, "epoch %d" % e
+        assert abs(rows[e, 3] - x[3]) < 0.2998
+        chm.chanmgr_update(ch, nav, x)
+    # host channel manager == oracle channel manager after the run
+    assert np.max(np.abs(sh.read_port("rx", "cuChanMgr", "CodePhaseEnd") - ch.rc_end)) < 1e-6
+    assert np.max(np.abs(sh.read_port("rx", "cuChanMgr", "CarrierFrequency") - ch.fi)) < 1e-6
+    assert np.array_equal(sh.read_port("rx", "cuChanMgr", "cpElapsedEnd").astype(int), ch.cp_end)
+    sh.close()
+
+
+@pytest.mark.gpu
+def test_dpe_flow_reproduces_the_reference_epochs(flowapi, tmp_path):
+    """Same files, same offset as oracle/make_golden_ref.py fed to the UNMODIFIED reference: the
+    fixes and the channel parameters handed to BCS / BCM must agree epoch by epoch."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_epochs_n9.npz"))
+    n, epochs, first = int(g["n"]), int(g["epochs"]), int(g["first_block"])
+    sc, grid, files = _write_scenario(tmp_path, n, epochs + first, first_block=first)
+    off = g["offset"]
+    extra = ["setparam rx DPInit InitDeltaX %r" % float(off[0]), "setparam rx DPInit InitDeltaY %r" % float(off[1]),
+             "setparam rx DPInit InitDeltaZ %r" % float(off[2]), "setparam rx DPInit InitDeltaT %r" % float(off[3])]
+    xfile = str(tmp_path / "XFile.csv")
+    sh = _drive(flowapi, files, n, extra, epochs, xfile)
+    rows = np.loadtxt(xfile, delimiter=",")
+    for e in range(epochs):
+        ref = g["e%d_x_k1k1" % e]
+        assert np.max(np.abs(rows[e, :3] - ref[:3])) < 0.1 and abs(rows[e, 3] - ref[3]) < 0.2998
+    sh.close()
