@@ -270,6 +270,10 @@ def run_ours(args):
                                     "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                         algorithmic="6 FLOP x S x valid (candidate,PRN) pairs per launch",
                         kernel_ms=k_ms, kernel_share=stage_ms[capi.STAGE_BRUTE_CORR] / max(stage_ms.sum(), 1e-9))
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        nominal = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        roofline.update(peak_nominal=nominal, frac_nominal=achieved / nominal,
+                        nominal_source="148 SM x 128 FP32 lanes x 2 FLOP x %.0f MHz (median SM clock under load)" % mhz)
     else:
         n = max(int(stage_cnt[capi.STAGE_LOOKUP]), 1)
         k_ms = stage_ms[capi.STAGE_LOOKUP] / n

@@ -143,7 +143,8 @@ typedef struct dpe_result {
     int64_t argmax;              /* GLOBAL candidate index (lowest index on ties) */
     int64_t out_of_window;       /* (candidate, PRN) pairs that could not be scored */
     double  vel_max_score;
-    int64_t vel_argmax;
+    int64_t vel_argmax;          /* index into the velocity grid                  */
+    int64_t vel_out_of_window;
 } dpe_result;
 
 /* ---- lifetime ---------------------------------------------------------------
@@ -277,6 +278,7 @@ enum {
     DPE_STAGE_BRUTE_CORR = 4,    /* k_brute (the north-star kernel) alone            */
     DPE_STAGE_BRUTE_SCORE = 5,   /* k_score_pairs + k_reduce_partials                */
     DPE_STAGE_ESTIMATE = 6,      /* k_finalize                                       */
+    DPE_STAGE_VELOCITY = 7,      /* velocity manifold: DC, baseband, windowed DFT, scoring */
     DPE_N_STAGES = 8
 };
 int dpe_profile_enable(dpe_ctx* ctx, int on);

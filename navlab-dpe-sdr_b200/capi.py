@@ -28,7 +28,7 @@ SAT_MIDDLE, SAT_PER_TIME = 0, 1
 FLAG_KEEP_CHIP_IDX, FLAG_BRUTE_TILES, FLAG_KEEP_BINS = 1, 2, 4
 PART_CHANNELS, PART_GEOMETRY = 1, 2
 (STAGE_PREPARE, STAGE_CORRELOGRAM, STAGE_LOOKUP, STAGE_BRUTE_BINS, STAGE_BRUTE_CORR, STAGE_BRUTE_SCORE,
- STAGE_ESTIMATE) = range(7)
+ STAGE_ESTIMATE, STAGE_VELOCITY) = range(8)
 
 EXPORTS = (
     "dpe_ctx_create", "dpe_ctx_destroy", "dpe_last_error", "dpe_abi_version", "dpe_grid_set",
@@ -61,7 +61,7 @@ class DpeEpoch(C.Structure):
 class DpeResult(C.Structure):
     _fields_ = [("z", C.c_double * 8), ("max_score", C.c_double), ("sum_score", C.c_double),
                 ("argmax", C.c_int64), ("out_of_window", C.c_int64), ("vel_max_score", C.c_double),
-                ("vel_argmax", C.c_int64)]
+                ("vel_argmax", C.c_int64), ("vel_out_of_window", C.c_int64)]
 
 
 class DpeError(RuntimeError):
@@ -192,6 +192,14 @@ class Context:
         self._keep = [g]
         n = g.shape[0]
         _check(self.lib, self.lib.dpe_grid_set(self.h, _ptr(g), n, C.c_void_p(stream)))
+
+    def vel_grid_set(self, vgrid, stream=0):
+        g = np.ascontiguousarray(vgrid, dtype=np.float64)
+        self._vgrid = g
+        _check(self.lib, self.lib.dpe_vel_grid_set(self.h, _ptr(g), g.shape[0], C.c_void_p(stream)))
+
+    def score_vel(self, stream=0):
+        _check(self.lib, self.lib.dpe_score_vel(self.h, C.c_void_p(stream)))
 
     def block_stage(self, iq, stream=0):
         if isinstance(iq, np.ndarray):

@@ -150,6 +150,24 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->ent_a, c->max_groups * kBfNC);
         DPE_ALLOC(c->n_groups, 1);
     }
+    if (cfg->Gv > 0) {
+        DPE_REQUIRE(cfg->Gv < (1ll << 31), DPE_EINVAL, "Gv out of range");
+        int64_t nf = cfg->n_fft;
+        if (nf <= 0) { nf = 1; while (nf < c->S) nf <<= 1; nf *= 8; }      // carrSTot, batchcorrscores.cu:761
+        DPE_REQUIRE((nf & (nf - 1)) == 0 && nf >= c->S && nf <= (1 << 26), DPE_EINVAL,
+                    "n_fft must be a power of two >= S");
+        c->n_fft = (int32_t)nf;
+        c->Wd = cfg->dopp_halfwidth > 0 ? cfg->dopp_halfwidth : 64;
+        DPE_REQUIRE(2 * c->Wd + 2 < nf, DPE_EINVAL, "Doppler window wider than the spectrum");
+        c->NBd = 2 * c->Wd + 2;
+        DPE_ALLOC(c->vgrid, (size_t)cfg->Gv * 4);
+        DPE_ALLOC(c->vscores, (size_t)cfg->Gv);
+        DPE_ALLOC(c->carr, C * c->NBd);
+        DPE_ALLOC(c->dc_sum, 2);
+        DPE_ALLOC(c->bb, C * S);
+        DPE_ALLOC(c->vpart, C * c->nchunk * c->NBd);
+        DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
+    }
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
     if (rc) { dpe_ctx_destroy(c); return rc; }
@@ -170,7 +188,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
                     c->cpart, c->cs, c->bx, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
-                    c->vgrid, c->vscores, c->carr};
+                    c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->prof_ev) {
@@ -190,10 +208,13 @@ int dpe_grid_set(dpe_ctx* c, const double* enu_dt, int64_t G, void* stream) {
 }
 
 int dpe_vel_grid_set(dpe_ctx* c, const double* venu_ddt, int64_t Gv, void* stream) {
-    (void)venu_ddt; (void)Gv; (void)stream;
-    DPE_REQUIRE(c, DPE_EINVAL, "null context");
-    set_error("velocity manifold not built in this round (SURVEY.md section 8 f-1)");
-    return DPE_ESTATE;
+    DPE_REQUIRE(c && venu_ddt, DPE_EINVAL, "dpe_vel_grid_set: null argument");
+    DPE_REQUIRE(c->Gv > 0, DPE_ESTATE, "context created without a velocity grid (cfg.Gv = 0)");
+    DPE_REQUIRE(Gv == c->Gv, DPE_EINVAL, "dpe_vel_grid_set: Gv=%lld, context holds %lld", (long long)Gv,
+                (long long)c->Gv);
+    DPE_CUDA(cudaMemcpyAsync(c->vgrid, venu_ddt, sizeof(double) * 4 * Gv, cudaMemcpyDefault, (cudaStream_t)stream));
+    c->have_vgrid = 1;
+    return DPE_OK;
 }
 
 int dpe_block_stage(dpe_ctx* c, const int16_t* iq, int64_t S, void* stream) {
@@ -331,10 +352,11 @@ int dpe_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, v
 }
 
 int dpe_score_vel(dpe_ctx* c, void* stream) {
-    (void)stream;
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
-    set_error("velocity manifold not built in this round (SURVEY.md section 8 f-1)");
-    return DPE_ESTATE;
+    DPE_REQUIRE(c->Gv > 0 && c->have_vgrid, DPE_ESTATE, "score_vel without a velocity grid");
+    DPE_REQUIRE(c->have_prepare && c->have_corr, DPE_ESTATE, "score_vel before replica_prepare / correlogram");
+    DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_vel before the geometry part of epoch_set");
+    return launch_score_vel(c, (cudaStream_t)stream);
 }
 
 int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
@@ -350,6 +372,7 @@ int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
     out->out_of_window = (int64_t)r[11];
     out->vel_max_score = r[12];
     out->vel_argmax = (int64_t)r[13];
+    out->vel_out_of_window = (int64_t)r[14];
     return DPE_OK;
 }
 

@@ -98,7 +98,9 @@ struct dpe_ctx {
     // debug
     int64_t* dbg_f; double* dbg_alpha;
     // velocity (section 8 f-1)
-    double* vgrid; double* vscores; double2* carr;
+    double* vgrid; double* vscores; double2* carr;       // [Gv][4], [Gv], [C][NBd]
+    long long* dc_sum; float2* bb; double2* vpart; double* vblk_partial;
+    int32_t Wd, NBd, n_fft; int have_vgrid;
     // state
     int have_block, have_epoch, have_prepare, have_corr, have_scores;
     int epoch_C;
@@ -133,6 +135,7 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_reduce_partials(dpe_ctx* c, cudaStream_t s);
+int launch_score_vel(dpe_ctx* c, cudaStream_t s);
 size_t brute_smem_bytes(int H);
 int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, cudaStream_t s);
 int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStream_t s);

@@ -1,0 +1,213 @@
+// dpe_vel.cu -- velocity / clock-drift manifold.
+//
+// Reference (cudarecv/modules/src): the DC-removed, wiped, replica-stripped block is zero-padded to
+// N_c = 8 * 2^ceil(log2 S) points and transformed by one batched Z2Z FFT -> "CarrScores"
+// (batchcorrscores.cu:1158-1180, BCS_SubtractDCOffset :470-485, BCS_ChoosyBatchMultiplyAndPad
+// :422-452); BCM_VelMeasML then looks every velocity candidate's Doppler bin up with a lerp
+// (batchcorrmanifold.cu:1861-1963), thrust::max_element, BCM_MakeVelMeas (:2030-2068).
+//
+// Here: a velocity grid of +-V m/s only reaches Doppler bins within +-Wd of the prompt
+// (bin width fs / N_c = 4.77 Hz at 2.5 MHz), so those 2*Wd+2 bins of the zero-padded spectrum are
+// evaluated directly,  carr[m] = sum_n bb[n] exp(-j 2 pi n m / N_c),  with the twiddle angle
+// reduced exactly in integers (n*m mod N_c) before sincospif; FP32 inside a 1024-sample chunk,
+// FP64 across chunks.  The scoring kernel is the position one with a Doppler geometry.
+#include "dpe_geom.cuh"
+
+namespace dpe {
+
+// integer sum of the block (exact; the reference reduces doubles with thrust, :1065)
+__global__ void __launch_bounds__(256) k_dc_sum(const int16_t* __restrict__ iq, int S, long long* __restrict__ out) {
+    long long si = 0, sq = 0;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < S; n += gridDim.x * blockDim.x) {
+        const short2 v = reinterpret_cast<const short2*>(iq)[n];
+        si += v.x; sq += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)si);
+        atomicAdd(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)sq);
+    }
+}
+
+// bb[n] = (x[n] - mean) * conj(carrier)[n] * chosen replica[n]     (FP64 like k_prepare, FP32 out)
+__global__ void __launch_bounds__(256)
+k_carrier_baseband(const int16_t* __restrict__ iq, const long long* __restrict__ dc, const int8_t* __restrict__ rs,
+                   const int32_t* __restrict__ idx_next, const int32_t* __restrict__ no_flip,
+                   const EpochDev* __restrict__ ep, double fs, int S, float2* __restrict__ bb) {
+    const int c = blockIdx.y;
+    const EpochDev& e = *ep;
+    if (c >= e.C) return;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= S) return;
+    const double inv = 1.0 / (double)(float)S;                  // ComplexDivide(..., (float) S), :1065-1066
+    const double mr = (double)dc[0] * inv, mi = (double)dc[1] * inv;
+    double t = (double)n / fs;
+    t = round(t * 1.0e9) / 1.0e9;
+    double sn, cs;
+    sincos(2 * K_PI * (e.fi[c] * t + e.ri_start[c]), &sn, &cs);
+    const short2 v = reinterpret_cast<const short2*>(iq)[n];
+    const double I = (double)v.x - mr, Q = (double)v.y - mi;
+    double r = (double)rs[(size_t)c * S + n];
+    if (!no_flip[c] && n >= idx_next[c]) r = -r;
+    bb[(size_t)c * S + n] = make_float2((float)((I * cs + Q * sn) * r), (float)((Q * cs - I * sn) * r));
+}
+
+// One CTA per (1024-sample chunk, channel); warp w owns bins w, w+8, ...; lanes stride the samples.
+__global__ void __launch_bounds__(256)
+k_carr_partial(const float2* __restrict__ bb, const EpochDev* __restrict__ ep, int S, int Wd, int NBd, int n_fft,
+               int nchunk, double2* __restrict__ vpart) {
+    __shared__ float2 xs[kCorrChunk];
+    const int c = blockIdx.y;
+    if (c >= ep->C) return;
+    const int chunk = blockIdx.x, n0 = chunk * kCorrChunk;
+    for (int i = threadIdx.x; i < kCorrChunk; i += blockDim.x)
+        xs[i] = (n0 + i < S) ? bb[(size_t)c * S + n0 + i] : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned mask = (unsigned)n_fft - 1u;                 // n_fft is a power of two
+    const float scale = 2.0f / (float)n_fft;
+    for (int l = warp; l < NBd; l += 8) {
+        const int m = l - Wd;                                   // bin relative to 0 Hz
+        float ar = 0.f, ai = 0.f;
+#pragma unroll 4
+        for (int i = lane; i < kCorrChunk; i += 32) {
+            const unsigned k = ((unsigned)(n0 + i) * (unsigned)m) & mask;     // n*m mod N_c (two's complement ok)
+            float sn, cs;
+            sincospif((float)k * scale, &sn, &cs);              // exp(-j 2 pi k / N_c) = cs - j sn
+            const float2 x = xs[i];
+            ar = fmaf(x.x, cs, fmaf(x.y, sn, ar));
+            ai = fmaf(x.y, cs, fmaf(-x.x, sn, ai));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o);
+            ai += __shfl_xor_sync(0xffffffffu, ai, o);
+        }
+        if (lane == 0) vpart[((size_t)c * nchunk + chunk) * NBd + l] = make_double2((double)ar, (double)ai);
+    }
+}
+
+__global__ void k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ ep, int NBd,
+                                int nchunk, double2* __restrict__ carr) {
+    const int c = blockIdx.x;
+    if (c >= ep->C) return;
+    for (int l = threadIdx.x; l < NBd; l += blockDim.x) {
+        double re = 0, im = 0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const double2 p = vpart[((size_t)c * nchunk + ch) * NBd + l];
+            re += p.x; im += p.y;
+        }
+        carr[(size_t)c * NBd + l] = make_double2(re, im);
+    }
+}
+
+// BCM_VelMeasML with the arg-max fused (batchcorrmanifold.cu:1896-1962); partial layout as the
+// position kernels' (sum s*v, sum s, max, argmax, out-of-window).
+__global__ void __launch_bounds__(kReduceBlock)
+k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
+            const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
+            double* __restrict__ vscores, double* __restrict__ blk_partial) {
+    __shared__ EpochDev e;
+    for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < Gv;
+    double score = 0.0;
+    int oow = 0;
+    Cand v = {0, 0, 0, 0};
+    if (active) {
+        const double* g = vgrid + 4 * j;
+        v.px = e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4];
+        v.py = e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5];
+        v.pz = e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6];
+        v.pt = g[3] + e.center[7];
+        const double ex = v.px - K_OEDOT * e.center[1], ey = v.py + K_OEDOT * e.center[0], ez = v.pz;
+        for (int c = 0; c < e.C; ++c) {
+            const double* s = sat + ((size_t)c * T + T / 2) * 8;
+            double los[3] = {s[0] - e.center[0], s[1] - e.center[1], s[2] - e.center[2]};
+            const double range = norm(3, los);
+            const double rate = ((los[0] / range) * (ex - s[4])) + ((los[1] / range) * (ey - s[5])) +
+                                ((los[2] / range) * (ez - s[6]));
+            const double bc_fi = K_F_L1 * ((rate - v.pt) / K_C + s[7]) / e.doppler_sign;
+            const double fi0 = bc_fi - e.fi[c];
+            const double idx_base = (n_fft / fs) * fi0 + n_fft / 2.0;
+            const bool valid = (idx_base < n_fft) && (idx_base > 0);
+            const double idxo = idx_base + (double)((int64_t)n_fft * c);
+            const double f = floor(idxo), gg = floor(idxo + 1.0);
+            const int64_t l = (int64_t)f - (int64_t)n_fft * c - n_fft / 2 + Wd;
+            if (valid && l >= 0 && l + 1 < NBd) {
+                const double2 lo = carr[(size_t)c * NBd + l], hi = carr[(size_t)c * NBd + l + 1];
+                const double wg = idxo - f, wf = gg - idxo;
+                score += mag_pow(hi.x * wg + lo.x * wf, hi.y * wg + lo.y * wf, lpower);
+            } else {
+                ++oow;
+            }
+        }
+        vscores[j] = score;
+    }
+    block_reduce_store(score, j, v, active, oow, blk_partial);
+}
+
+// level-2 reduction + BCM_MakeVelMeas: zVal[4:8], RVal rows 4-7, result slots
+__global__ void __launch_bounds__(kReduceBlock)
+k_vel_finalize(const double* __restrict__ blk, int n_blk, const double* __restrict__ vgrid,
+               const EpochDev* __restrict__ ep, double* __restrict__ zval, double* __restrict__ rval,
+               double* __restrict__ res) {
+    __shared__ double sh[kReduceBlock][3];
+    double mx = -1.0, mi = 9.0e18, oo = 0;
+    for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
+        const double* q = blk + (size_t)b * 8;
+        oo += q[7];
+        if (q[5] > mx || (q[5] == mx && q[6] < mi)) { mx = q[5]; mi = q[6]; }
+    }
+    sh[threadIdx.x][0] = mx; sh[threadIdx.x][1] = mi; sh[threadIdx.x][2] = oo;
+    __syncthreads();
+    for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            double* a = sh[threadIdx.x];
+            const double* b = sh[threadIdx.x + s];
+            a[2] += b[2];
+            if (b[0] > a[0] || (b[0] == a[0] && b[1] < a[1])) { a[0] = b[0]; a[1] = b[1]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const EpochDev& e = *ep;
+        const int64_t j = (int64_t)sh[0][1];
+        const double* g = vgrid + 4 * j;
+        const double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
+                             e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
+                             e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
+        for (int k = 0; k < 4; ++k) { zval[4 + k] = z[k]; res[4 + k] = z[k]; }
+        for (int r = 4; r < 8; ++r)
+            for (int k = 0; k < 8; ++k) rval[r * 8 + k] = (r == k) ? 1.0 : 0.0;
+        res[12] = sh[0][0]; res[13] = (double)j; res[14] = sh[0][2];
+    }
+}
+
+int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
+    const int S = (int)c->S, C = c->epoch_C;
+    prof_begin(c, DPE_STAGE_VELOCITY, s);
+    DPE_CUDA(cudaMemsetAsync(c->dc_sum, 0, 2 * sizeof(long long), s));
+    k_dc_sum<<<32, 256, 0, s>>>(c->iq, S, c->dc_sum);
+    dim3 g1((S + 255) / 256, C);
+    k_carrier_baseband<<<g1, 256, 0, s>>>(c->iq, c->dc_sum, c->rs, c->idx_next, c->no_flip, c->ep, c->cfg.fs, S, c->bb);
+    dim3 g2(c->nchunk, C);
+    k_carr_partial<<<g2, 256, 0, s>>>(c->bb, c->ep, S, c->Wd, c->NBd, c->n_fft, c->nchunk, c->vpart);
+    k_carr_finalize<<<C, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->nchunk, c->carr);
+    const int nblk = (int)((c->Gv + kReduceBlock - 1) / kReduceBlock);
+    k_score_vel<<<nblk, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd,
+                                              c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial);
+    k_vel_finalize<<<1, kReduceBlock, 0, s>>>(c->vblk_partial, nblk, c->vgrid, c->ep, c->zval, c->rval, c->result);
+    c->launches += 6;
+    prof_end(c, s);
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
+}  // namespace dpe

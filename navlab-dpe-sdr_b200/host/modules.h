@@ -114,8 +114,8 @@ class BatchCorrManifold : public Module {
     char Filename[kNameCap] = "", loadPosGridFilename[kNameCap] = "";
     // extensions (not in the reference): scoring path, estimator, lag window
     bool bruteForce = false, weightedMean = false;
-    int lagHalfwidth = 32;
-    bool Started = false;
+    int lagHalfwidth = 32, doppHalfwidth = 64;
+    bool Started = false, haveVel = false;
     void* flowStream = nullptr;
     std::vector<double> grid, timeGrid;
     double zVal[16], RVal[64];

@@ -135,6 +135,7 @@ BatchCorrManifold::BatchCorrManifold() {
     InsertParam("BruteForce", &bruteForce, BOOL_t, sizeof(bool), sizeof(bool));          // north-star kernel
     InsertParam("WeightedMean", &weightedMean, BOOL_t, sizeof(bool), sizeof(bool));      // dormant Method 1
     InsertParam("LagHalfwidth", &lagHalfwidth, INT_t, sizeof(int), sizeof(int));
+    InsertParam("DopplerHalfwidth", &doppHalfwidth, INT_t, sizeof(int), sizeof(int));
     AllocateOutputs(4);
     ConfigOutput(0, "zVal", DOUBLE_t, STATE, HOST, 8, zVal, 0);
     ConfigOutput(1, "RVal", DOUBLE_t, COVARIANCE, HOST, 64, RVal, 0);
@@ -177,6 +178,14 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
     cfg.lpower = LPower;
     cfg.lag_halfwidth = lagHalfwidth;
     cfg.flags = bruteForce ? DPE_FLAG_BRUTE_TILES : 0;
+    // velocity / drift manifold: BCM_InitVelGrid (batchcorrmanifold.cu:265-316) is uniform for every grid type
+    std::vector<double> vgrid;
+    if (velGridDimSize > 0) {
+        const int vd[4] = {velGridDimSize, velGridDimSize, velGridDimSize, velGridDimSize};
+        gnss::MakeGrid(vd, sp, 0, &vgrid, nullptr);
+        cfg.Gv = (int64_t)vgrid.size() / 4;
+        cfg.dopp_halfwidth = doppHalfwidth;
+    }
     SharedCtx* sh = SharedFor(cuFlowStream);
     if (sh->ctx) { dpe_ctx_destroy(sh->ctx); sh->ctx = nullptr; }
     DPE_CALL(dpe_ctx_create(&sh->ctx, &cfg));
@@ -184,6 +193,8 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
     sh->est_mode = weightedMean ? DPE_EST_WEIGHTED : DPE_EST_ARGMAX;
     void* stream = StreamOf(cuFlowStream);
     DPE_CALL(dpe_grid_set(sh->ctx, grid.data(), cfg.G, stream));
+    if (cfg.Gv > 0) DPE_CALL(dpe_vel_grid_set(sh->ctx, vgrid.data(), cfg.Gv, stream));
+    haveVel = cfg.Gv > 0;
     DPE_CALL(dpe_stream_sync(stream));
     UpdateOutput(2, (int64_t)timeGrid.size(), timeGrid.data(), 0);
     UpdateOutput(3, cfg.G, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_POS_SCORES)), 0);
@@ -213,14 +224,17 @@ int BatchCorrManifold::Update(void* cuFlowStream) {
     const int sat_mode = (sh->est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
     DPE_CALL(dpe_score_pos(sh->ctx, sh->score_mode, sat_mode, stream));
     DPE_CALL(dpe_estimate(sh->ctx, sh->est_mode, nullptr, 1, stream));
+    if (haveVel) DPE_CALL(dpe_score_vel(sh->ctx, stream));
     DPE_CALL(dpe_result_fetch(sh->ctx, &last, stream));
     if (last.out_of_window)
         std::clog << "[" << ModuleName << "] " << last.out_of_window << " candidate-PRN pairs outside the lag window"
                   << std::endl;
     for (int i = 0; i < 4; ++i) zVal[i] = last.z[i];
-    // velocity / drift half of zVal: the velocity manifold is not built in this round;
-    // the prediction is passed through so the 8-state hand-over to cuEKF / cuChanMgr stays defined
-    for (int i = 4; i < 8; ++i) zVal[i] = ep.center[i];
+    if (last.vel_out_of_window)
+        std::clog << "[" << ModuleName << "] " << last.vel_out_of_window
+                  << " velocity candidate-PRN pairs outside the Doppler window" << std::endl;
+    // velocity / drift half: the velocity manifold's arg-max, or (VelGridDimSize = 0) the prediction passed through
+    for (int i = 4; i < 8; ++i) zVal[i] = haveVel ? last.z[i] : ep.center[i];
     return 0;
 }
 

@@ -221,3 +221,50 @@ def test_epoch_run_host_buffers_and_determinism(capi):
     assert r1.max_score == r2.max_score and r1.sum_score == r2.sum_score     # bit-reproducible
     assert abs(r3.max_score - r1.max_score) / r1.max_score < SCORE_RTOL
     assert ctx.launch_count() > 0
+
+
+# ---- velocity / clock-drift manifold ------------------------------------------
+@pytest.mark.parametrize("fs,prns", [(2.5e6, synth.PRNS_8), (10.0e6, synth.PRNS_12)])
+def test_velocity_manifold_matches_oracle(capi, fs, prns):
+    sc = H.scenario(fs, prns)
+    grid, tg = synth.uniform_grid(5, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(9, (0.5, 0.5, 0.5, 0.25))
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[4:] += (1.0, -0.5, 0.5, 0.3)                       # velocity / drift error of the prediction
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    C, S, Wd = len(prns), ep["S"], 64
+    bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"], want_carrier=True)
+    n_fft = bcs["n_fft"]
+    assert n_fft == 8 * (1 << int(np.ceil(np.log2(S))))
+    ref = orc.vel_meas_ml(bcs["carr_scores"], vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"], ep["time_dim"],
+                          ep["fi"], ep["doppler_sign"], ep["fs"], n_fft)
+    assert ref["valid"].all()
+    ctx = capi.Context(fs=fs, S=S, max_chan=C, G=grid.shape[0], time_dim=len(tg), lag_halfwidth=16,
+                       Gv=vgrid.shape[0], dopp_halfwidth=Wd)
+    ctx.grid_set(grid)
+    ctx.vel_grid_set(vgrid)
+    res = ctx.epoch_run(iq, ep, with_vel=1)
+    NBd = 2 * Wd + 2
+    carr = ctx.copy_out(capi.PTR_CARR_SCORES, np.float64, C * NBd * 2).reshape(C, NBd, 2)
+    got = carr[..., 0] + 1j * carr[..., 1]
+    want = bcs["carr_scores"][:, n_fft // 2 - Wd: n_fft // 2 - Wd + NBd]
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 2e-6
+    vs = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    assert np.max(np.abs(vs - ref["scores"]) / ref["scores"]) < SCORE_RTOL
+    assert res.vel_argmax == ref["argmax"] and res.vel_out_of_window == 0
+    assert np.max(np.abs(np.array(res.z[4:8]) - ref["z"])) < 1e-9
+    rval = ctx.copy_out(capi.PTR_RVAL, np.float64, 64).reshape(8, 8)
+    assert np.array_equal(rval, np.eye(8))
+    # the manifold pulls the velocity prediction back towards the (static) truth
+    truth = sc.rx_state(ep["rx_time"])
+    assert np.linalg.norm(np.array(res.z[4:7]) - truth[4:7]) < np.linalg.norm(center[4:7] - truth[4:7])
+    ctx.close()
+
+
+def test_velocity_needs_its_grid(capi):
+    ctx = _ctx(capi, 5000, 2, 16, 1, 2.5e6)
+    with pytest.raises(capi.DpeError) as e:
+        ctx.vel_grid_set(np.zeros((16, 4)))
+    assert e.value.code == capi.DPE_ESTATE

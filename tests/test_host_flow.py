@@ -184,6 +184,7 @@ def _drive(flowapi, files, n, extra=(), epochs=-1, xfile=None):
             'setparam rx BatchCorrManifold LoadPosGridFilename "%s"' % files["grid"],
             "setparam rx BatchCorrManifold LoadPosGrid true",
             "setparam rx BatchCorrManifold PosGridDimSize %d" % n,
+            "setparam rx BatchCorrManifold VelGridDimSize 5",
             'setparam rx XECEFLogger Filename "%s"' % xfile] + list(extra)
     for c in cmds:
         assert sh.exec(c) == 0, c
@@ -213,14 +214,18 @@ def test_dpe_flow_end_to_end_against_oracle_closed_loop(flowapi, tmp_path, brute
     x = h["X_ECEF"].copy()
     x[:4] += (6.0, -4.0, 3.0, 7.0)
     _, tg = synth.uniform_grid(n, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(5, 1.0)                  # VelGridDimSize 5, GridDimSpacing 1.0 (the default)
     ch = chm.chanmgr_start(nav, h, sc.cfg.T, x)
     for e in range(epochs):
         sat, R = chm.grid_prep(ch, x, tg)
         iq = sc.block(e)
-        bcs = orc.batch_corr_scores(iq, ch.prn, ch.rc_start, ch.ri_start, ch.fc, ch.fi, ch.cp_start, ch.cp_ref, sc.cfg.fs)
+        bcs = orc.batch_corr_scores(iq, ch.prn, ch.rc_start, ch.ri_start, ch.fc, ch.fi, ch.cp_start, ch.cp_ref,
+                                    sc.cfg.fs, want_carrier=True)
         r = orc.pos_meas_ml(bcs["code_scores"], grid, x, R, sat, len(tg), ch.fc, ch.rc_end, ch.cp_ref_tow, ch.cp_end,
                             ch.cp_ref, ch.rx_time, sc.cfg.fs, sc.S)
-        x = np.concatenate([r["z"], x[4:]])
+        v = orc.vel_meas_ml(bcs["carr_scores"], vgrid, x, R, sat, len(tg), ch.fi, 1, sc.cfg.fs, bcs["n_fft"])
+        x = np.concatenate([r["z"], v["z"]])
+        assert np.max(np.abs(rows[e, 4:] - x[4:])) < 1e-5, "velocity fix, epoch %d" % e
         # logged fix (6 decimals) vs oracle: position 0.1 m, clock 1 ns = 0.2998 m
         assert np.max(np.abs(rows[e, :3] - x[:3])) < 0.1, "epoch %d" % e
         assert abs(rows[e, 3] - x[3]) < 0.2998
@@ -248,4 +253,5 @@ def test_dpe_flow_reproduces_the_reference_epochs(flowapi, tmp_path):
     for e in range(epochs):
         ref = g["e%d_x_k1k1" % e]
         assert np.max(np.abs(rows[e, :3] - ref[:3])) < 0.1 and abs(rows[e, 3] - ref[3]) < 0.2998
+        assert np.max(np.abs(rows[e, 4:] - ref[4:])) < 1e-5        # velocity manifold arg-max (5^4 grid, 1 m/s)
     sh.close()
