@@ -36,6 +36,9 @@ WORKLOADS = {
                desc="synthetic L1 C/A 2.5 MHz, 12 PRNs, uniform 21^4 grid (194481 candidates)"),
     "c4": dict(fs=10.0e6, prns="12", grid=("uniform", 51, (2.0, 2.0, 2.0, 2.0)),
                desc="synthetic L1 C/A 10 MHz, 12 PRNs, uniform 51^4 grid (6765201 candidates)"),
+    "c5": dict(fs=2.5e6, prns="8", grid=("uniform", 21, (5.0, 5.0, 5.0, 6.0)), streams=256,
+               desc="256 independent synthetic receiver streams, 2.5 MHz, 8 PRNs, uniform 21^4 grid each "
+                    "(streams sharded over ranks, no collective: replicas)"),
     "tiny": dict(fs=2.5e6, prns="8", grid=("uniform", 9, (5.0, 5.0, 5.0, 6.0)),
                  desc="synthetic 2.5 MHz, 8 PRNs, 9^4 grid (CI-sized)"),
 }
@@ -127,8 +130,13 @@ def run_ours(args):
 
     sc, grid, tg = build_workload(args.workload)
     G_total, C, S, T = grid.shape[0], sc.C, sc.S, len(tg)
-    per = (G_total + world - 1) // world
-    lo, hi = min(rank * per, G_total), min((rank + 1) * per, G_total)
+    streams = WORKLOADS[args.workload].get("streams", 0)          # c5: independent receivers, sharded by stream
+    if streams:
+        lo, hi = 0, G_total
+        my_streams = len(range(rank, streams, world))
+    else:
+        per = (G_total + world - 1) // world
+        lo, hi = min(rank * per, G_total), min((rank + 1) * per, G_total)
     shard = np.ascontiguousarray(grid[lo:hi])
     score_mode = capi.SCORE_LOOKUP if args.path == "lookup" else capi.SCORE_BRUTE
     est_mode = capi.EST_WEIGHTED if args.estimate == "weighted" else capi.EST_ARGMAX
@@ -137,7 +145,7 @@ def run_ours(args):
     ctx = capi.Context(fs=sc.cfg.fs, S=S, max_chan=C, G=hi - lo, time_dim=T, lag_halfwidth=args.lag_halfwidth,
                        flags=capi.FLAG_BRUTE_TILES, device=local, grid_offset=lo, G_total=G_total)
     ctx.grid_set(shard)
-    n_blocks = 4
+    n_blocks = 8 if streams else 4
     blocks_host = [torch.from_numpy(sc.block(b).copy()).pin_memory() for b in range(n_blocks)]
     blocks_dev = [b.to(dev) for b in blocks_host]                 # resident inputs for `value`
     epochs = [epoch_for_block(sc, b, tg) for b in range(n_blocks)]
@@ -149,8 +157,22 @@ def run_ours(args):
     recv = torch.empty(2 * S, dtype=torch.int16, device=dev)
     recv_u8 = recv.view(torch.uint8)                               # NCCL has no int16: broadcast the bytes
 
+    def one_stream_epoch(b, host):
+        if host:
+            return ctx.epoch_run(blocks_host[b], ep_structs[b], sats[b], score_mode, est_mode, 0, stream)
+        ctx.block_stage(blocks_dev[b], stream)
+        ctx.epoch_set(ep_structs[b], sats[b], stream)
+        ctx.replica_prepare(stream)
+        ctx.correlogram(stream)
+        ctx.score_pos(score_mode, sat_mode, stream)
+        ctx.estimate(est_mode, None, 1, stream)
+
     def step_resident(i):
         b = i % n_blocks
+        if streams:                                                # one epoch of every stream this rank owns
+            for s_ in range(my_streams):
+                one_stream_epoch((i + s_) % n_blocks, False)
+            return
         if world > 1:
             if rank == 0:
                 recv.copy_(blocks_dev[b], non_blocking=True)
@@ -171,6 +193,11 @@ def run_ours(args):
 
     def step_e2e(i):
         b = i % n_blocks
+        if streams:
+            r_ = None
+            for s_ in range(my_streams):
+                r_ = one_stream_epoch((i + s_) % n_blocks, True)
+            return r_
         if world > 1:
             if rank == 0:
                 recv.copy_(blocks_host[b], non_blocking=True)     # H2D from pinned memory, then NVLink broadcast
@@ -211,7 +238,8 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), wall
 
-    pairs_per_step = G_total * C
+    pairs_per_step = G_total * C * (streams if streams else 1)
+    n_epochs_rank = my_streams if streams else 1
     # --- resident-input throughput (`value`) with per-stage device timing -----------------------
     sampler = ClockSampler(local) if rank == 0 else None
     ctx.profile_enable(True)
@@ -219,7 +247,7 @@ def run_ours(args):
     ms_total, wall = timed(step_resident, args.steps, args.warmup)
     stage_ms, stage_cnt = ctx.profile_read()
     clocks = sampler.stop() if sampler else None
-    launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup)
+    launches = (ctx.launch_count() - launches0) // ((args.steps + args.warmup) * n_epochs_rank)
     ctx.profile_enable(False)
     res = ctx.result_fetch(stream)
     valid_pairs = ctx.brute_pairs() if score_mode == capi.SCORE_BRUTE else (hi - lo) * C
@@ -230,8 +258,8 @@ def run_ours(args):
     e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
     e2e_ms /= args.steps
     e2e_value = pairs_per_step / (e2e_ms * 1e-3)
-    h2d = 4 * S + 8 * 8 * C * T + 2300                           # block + sat states + dpe_epoch (approx. struct size)
-    d2h = 16 * 8
+    h2d = (4 * S + 8 * 8 * C * T + 2300) * n_epochs_rank         # block + sat states + dpe_epoch per epoch
+    d2h = 16 * 8 * n_epochs_rank
 
     # --- the other path for context (lookup when the headline is brute and vice versa) ----------
     other = None
@@ -272,6 +300,13 @@ def run_ours(args):
                         kernel_ms=k_ms, kernel_share=stage_ms[capi.STAGE_BRUTE_CORR] / max(stage_ms.sum(), 1e-9))
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
         nominal = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        try:                                                       # DRAM traffic of one launch, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k_brute_traffic.json")))
+            if tr.get("workload") == args.workload and world == 1:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         roofline.update(peak_nominal=nominal, frac_nominal=achieved / nominal,
                         nominal_source="148 SM x 128 FP32 lanes x 2 FLOP x %.0f MHz (median SM clock under load)" % mhz)
     else:
@@ -289,6 +324,13 @@ def run_ours(args):
         ("prepare", "correlogram", "lookup", "brute_bins", "brute_corr", "brute_score", "estimate"))}
 
     cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, budget_s=args.cpu_budget)
+    flow = None
+    if world == 1 and args.flow_epochs > 0 and args.workload == "demo":
+        try:
+            ctx.close()
+            flow = [flow_realtime(args, "brute"), flow_realtime(args, "lookup")]
+        except Exception as exc:                                   # reported, never silently dropped
+            flow = dict(error=repr(exc))
 
     line = dict(metric="DPE candidate-PRN correlations/s (20 ms epochs, %s BCM)" % args.path, value=value,
                 unit="corr/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
@@ -296,17 +338,62 @@ def run_ours(args):
                 data="synthetic",
                 config=dict(workload="%s: %s" % (args.workload, WORKLOADS[args.workload]["desc"]),
                             S=S, prns=C, candidates=G_total, path=args.path, estimate=args.estimate,
-                            lag_halfwidth=args.lag_halfwidth, sharding="grid candidates, contiguous index ranges",
+                            lag_halfwidth=args.lag_halfwidth,
+                            sharding=("independent streams, %d per rank, no collective" % n_epochs_rank) if streams
+                            else "grid candidates, contiguous index ranges",
                             l2="flushed (256 MiB memset) between timed iterations"),
-                epochs_per_s=1e3 / ms_per_step, realtime_factor=(1e3 / ms_per_step) / 50.0,
+                epochs_per_s=1e3 * (streams if streams else 1) / ms_per_step,
+                realtime_factor=(1e3 / ms_per_step) / 50.0,
                 e2e=dict(value=e2e_value, unit="corr/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=e2e_ms, epochs_per_s=1e3 / e2e_ms),
-                gpu_launches=int(launches), stage_ms_per_step=stages, roofline=roofline, cpu_baseline=cpu,
-                clocks=clocks, other_path=other, wall_s=wall,
+                gpu_launches=int(launches) * args.steps * n_epochs_rank, gpu_launches_per_epoch=int(launches),
+                stage_ms_per_step=stages, roofline=roofline, cpu_baseline=cpu,
+                clocks=clocks, other_path=other, flow=flow, wall_s=wall,
                 fix=dict(z=[res.z[i] for i in range(4)], argmax=res.argmax, out_of_window=res.out_of_window))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def flow_realtime(args, path):
+    """BASELINE.json config 2: the same synthetic capture pushed through the rebuilt `newflow dpe /
+    loadflow / startflow` flow (file reader -> BCS -> BCM -> pass-through EKF -> host channel manager ->
+    CSV logger), 25^4 position + 25^4 velocity grids.  Returns the flow's own per-epoch statistics
+    (the reference's `[Flow] Average ... block duration`, flow.cu:172-191) and the real-time factor."""
+    import dpe_pkg
+    flowapi = dpe_pkg.submodule("flowapi")
+    synth = dpe_pkg.submodule("synth")
+    sc, grid, tg = build_workload("demo")
+    d = "/tmp/dpe_bench_flow"
+    n_epochs = args.flow_epochs
+    files = sc.write_files(d, n_epochs + 34, grid=grid, handoff_block=0)   # + the reader's 32-block read-ahead
+    sh = flowapi.Shell()
+    cmds = ["newflow dpe rx", "loadflow rx",
+            'setparam rx SampleBlock Filename "%s"' % files["dat"],
+            'setparam rx DPInit HandoffFilename "%s"' % files["handoff"],
+            'setparam rx DPInit RINEXFilename "%s"' % files["rinex"],
+            'setparam rx BatchCorrManifold LoadPosGridFilename "%s"' % files["grid"],
+            "setparam rx BatchCorrManifold LoadPosGrid true",
+            "setparam rx BatchCorrManifold PosGridDimSize 25", "setparam rx BatchCorrManifold VelGridDimSize 25",
+            "setparam rx BatchCorrManifold GridDimSpacing 0.5",
+            "setparam rx BatchCorrManifold LagHalfwidth %d" % args.lag_halfwidth,
+            "setparam rx BatchCorrManifold BruteForce %s" % ("true" if path == "brute" else "false"),
+            'setparam rx XECEFLogger Filename "%s/XFile.csv"' % d]
+    for c in cmds:
+        if sh.exec(c) != 0:
+            raise RuntimeError("console command failed: " + c)
+    if sh.run_blocking("rx", n_epochs) != 0:
+        raise RuntimeError("flow failed")
+    st = sh.stats("rx")
+    rows = np.loadtxt(os.path.join(d, "XFile.csv"), delimiter=",")
+    truth = sc.rx_state(sc.cfg.rx_time0 + n_epochs * sc.cfg.T)
+    err = float(np.linalg.norm(rows[-1, :3] - truth[:3]))
+    sh.close()
+    return dict(path=path, epochs=st["run_count"], avg_epoch_us=st["avg_us"], min_epoch_us=st["min_us"],
+                max_epoch_us=st["max_us"], epochs_per_s=1e6 / st["avg_us"], realtime_factor=20000.0 / st["avg_us"],
+                final_position_error_m=err,
+                note="dpe_console flow on a synthetic 2.5 MHz capture: 25^4 spread position grid + 25^4 velocity "
+                     "grid (0.5 m/s), 8 PRNs, host buffers, per-epoch D2H of the fix, CSV logging")
 
 
 def _as_tensor(torch, ptr, n, dev):
@@ -319,14 +406,27 @@ def _as_tensor(torch, ptr, n, dev):
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm: NumPy restatement of the reference's DPE epoch (oracle/), host cores.
 # ---------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_prepare(name, max_cand):
+    """Per-process cache of the epoch inputs (building the synthetic scenario is not part of the path)."""
+    key = (name, max_cand)
+    if key not in _CPU_CACHE:
+        sc, grid, tg = build_workload(name)
+        if max_cand and grid.shape[0] > max_cand:
+            grid = grid[:max_cand]
+        _CPU_CACHE[key] = (sc, grid, [(sc.block(b), epoch_for_block(sc, b, tg)) for b in range(2)])
+    return _CPU_CACHE[key]
+
+
 def _cpu_epoch(a):
+    """One epoch of the reference's CPU DPE path: FFT correlogram (BCS) + vectorised grid lookup and
+    arg-max (BCM), oracle/dpe_oracle.py.  Returns (seconds, candidate-PRN pairs, arg-max)."""
     name, b, max_cand = a
     from oracle import dpe_oracle as orc
-    sc, grid, tg = build_workload(name)
-    if max_cand and grid.shape[0] > max_cand:
-        grid = grid[:max_cand]
-    ep = epoch_for_block(sc, b, tg)
-    iq = sc.block(b)
+    sc, grid, eps = _cpu_prepare(name, max_cand)
+    iq, ep = eps[b % len(eps)]
     t0 = time.perf_counter()
     bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
                                 ep["cp_ref"], ep["fs"])
@@ -336,45 +436,44 @@ def _cpu_epoch(a):
     return time.perf_counter() - t0, grid.shape[0] * sc.C, int(r["argmax"])
 
 
-def cpu_baseline(name, budget_s=20.0, procs=1, max_cand=400000, epochs=None):
-    """Reference CPU path (FFT correlogram + vectorised grid lookup, one process per stream as
-    PyGNSS runs one thread per receiver).  Bounded: `epochs` epochs per process on at most
-    `max_cand` candidates."""
-    import multiprocessing as mp
+def cpu_baseline(name, budget_s=20.0, max_cand=400000):
+    """Single-process reference CPU path on a bounded sample (PyGNSS runs one thread per receiver)."""
+    _cpu_prepare(name, max_cand)
     t_first, pairs, _ = _cpu_epoch((name, 0, max_cand))
-    n = epochs if epochs else max(1, min(8, int(budget_s / max(t_first, 1e-3)) // max(procs, 1)))
-    jobs = [(name, b % 4, max_cand) for b in range(n * procs)]
+    n = max(1, min(8, int(budget_s / max(t_first, 1e-3))))
     t0 = time.perf_counter()
-    if procs > 1:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            out = pool.map(_cpu_epoch, jobs)
-    else:
-        out = [_cpu_epoch(j) for j in jobs]
+    out = [_cpu_epoch((name, b, max_cand)) for b in range(n)]
     wall = time.perf_counter() - t0
-    tot_pairs = sum(o[1] for o in out)
-    return dict(value=tot_pairs / wall, unit="corr/s", cores=procs, kind="port",
-                sample="%d epoch(s) x %d process(es) of workload %s, %d candidate-PRN pairs per epoch "
-                       "(NumPy FFT correlogram + grid lookup, oracle/dpe_oracle.py)" % (n, procs, name, out[0][1]),
-                epochs_per_s=len(out) / wall, s_per_epoch=wall / len(out) * procs)
+    return dict(value=sum(o[1] for o in out) / wall, unit="corr/s", cores=1, kind="port",
+                sample="%d epoch(s) of workload %s, %d candidate-PRN pairs per epoch (NumPy FFT correlogram + "
+                       "grid lookup, oracle/dpe_oracle.py), one process" % (n, name, pairs),
+                epochs_per_s=n / wall, s_per_epoch=wall / n)
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU DPE path on the host cores, one process per core over
+    independent epochs (the way PyGNSS scales: one receiver per process).  A step = one epoch per
+    process; inputs are built once per process outside the timed region."""
+    import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     procs = max(1, min(os.cpu_count() or 1, args.cpu_procs))
-    sc, grid, tg = build_workload(args.workload)
-    vals = []
-    for _ in range(args.warmup):
-        cpu_baseline(args.workload, procs=procs, epochs=1)
-    t0 = time.perf_counter()
-    last = None
-    for _ in range(args.steps):
-        last = cpu_baseline(args.workload, procs=procs, epochs=1)
-        vals.append(last["value"])
-    wall = time.perf_counter() - t0
-    v = float(np.mean(vals))
-    cpu = dict(last, value=v)
+    jobs = lambda i: [(args.workload, (i + k) % 2, 400000) for k in range(procs)]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_cpu_epoch, jobs(0))                      # builds the per-process caches
+        for i in range(args.warmup):
+            pool.map(_cpu_epoch, jobs(i))
+        t0 = time.perf_counter()
+        pairs = 0
+        for i in range(args.steps):
+            pairs += sum(o[1] for o in pool.map(_cpu_epoch, jobs(i)))
+        wall = time.perf_counter() - t0
+    v = pairs / wall
+    cpu = dict(value=v, unit="corr/s", cores=procs, kind="port",
+               sample="%d step(s) x %d process(es), one epoch of workload %s per process and step "
+                      "(NumPy FFT correlogram + grid lookup, oracle/dpe_oracle.py)" % (args.steps, procs, args.workload),
+               epochs_per_s=args.steps * procs / wall)
     line = dict(impl="reference", metric="DPE candidate-PRN correlations/s (20 ms epochs, %s BCM)" % args.path,
                 value=v, unit="corr/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -401,6 +500,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--cpu-procs", type=int, default=64)
+    ap.add_argument("--flow-epochs", type=int, default=100,
+                    help="epochs of the dpe_console flow run for the real-time factor (0 = skip; N=1, demo only)")
     args = ap.parse_args()
     if args.steps < 1 or args.warmup < 0:
         raise SystemExit("steps >= 1, warmup >= 0")
