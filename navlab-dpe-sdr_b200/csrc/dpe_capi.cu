@@ -168,6 +168,10 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->vpart, C * c->nchunk * c->NBd);
         DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
     }
+    c->sat_cap = C * c->T * 8;
+    DPE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->ep_pin), sizeof(EpochDev) * kPinSlots));
+    DPE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->sat_pin), sizeof(double) * c->sat_cap * kPinSlots));
+    for (int i = 0; i < kPinSlots; ++i) DPE_CUDA(cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
     if (rc) { dpe_ctx_destroy(c); return rc; }
@@ -191,6 +195,11 @@ int dpe_ctx_destroy(dpe_ctx* c) {
                     c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (c->ep_pin) {
+        cudaFreeHost(c->ep_pin);
+        cudaFreeHost(c->sat_pin);
+        for (int i = 0; i < kPinSlots; ++i) cudaEventDestroy(c->pin_ev[i]);
+    }
     if (c->prof_ev) {
         for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
@@ -272,11 +281,26 @@ int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states
         }
     }
     cudaStream_t s = (cudaStream_t)stream;
-    // ep_host is pageable: cudaMemcpyAsync stages it before returning, so it may be rewritten next call
-    DPE_CUDA(cudaMemcpyAsync(c->ep, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    if (parts & DPE_PART_GEOMETRY)
-        DPE_CUDA(cudaMemcpyAsync(c->sat, sat_states, sizeof(double) * 8 * (size_t)ep->C * c->T,
-                                 cudaMemcpyDefault, s));
+    // stage through a page-locked ring slot: truly asynchronous, and the caller may reuse its arrays at once
+    const int slot = c->pin_next;
+    c->pin_next = (slot + 1) % kPinSlots;
+    DPE_CUDA(cudaEventSynchronize(c->pin_ev[slot]));          // the copy issued kPinSlots calls ago has long finished
+    c->ep_pin[slot] = h;
+    DPE_CUDA(cudaMemcpyAsync(c->ep, &c->ep_pin[slot], sizeof(h), cudaMemcpyHostToDevice, s));
+    if (parts & DPE_PART_GEOMETRY) {
+        const size_t n = 8 * (size_t)ep->C * c->T;
+        cudaPointerAttributes at;
+        const bool dev = cudaPointerGetAttributes(&at, sat_states) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        if (!dev) cudaGetLastError();
+        if (dev) {
+            DPE_CUDA(cudaMemcpyAsync(c->sat, sat_states, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        } else {
+            double* stage = c->sat_pin + (size_t)slot * c->sat_cap;
+            memcpy(stage, sat_states, sizeof(double) * n);
+            DPE_CUDA(cudaMemcpyAsync(c->sat, stage, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        }
+    }
+    DPE_CUDA(cudaEventRecord(c->pin_ev[slot], s));
     c->epoch_C = ep->C;
     c->have_epoch |= (int)parts;
     if (parts & DPE_PART_CHANNELS) c->have_prepare = c->have_corr = 0;

@@ -36,6 +36,7 @@ constexpr int kLagTile = 8;            // lags per thread in the correlogram ker
 constexpr int kPartialLen = DPE_PARTIAL_LEN;
 constexpr int kReduceBlock = 256;
 constexpr int kProfMax = 8192;
+constexpr int kPinSlots = 8;
 
 // brute-force kernel geometry
 constexpr int kBfNC = 32;              // candidates per warp (one group)
@@ -106,6 +107,8 @@ struct dpe_ctx {
     int epoch_C;
     int64_t launches;
     dpe::EpochDev ep_host;
+    // page-locked staging ring for the per-epoch uploads (no implicit stream sync, safe reuse)
+    dpe::EpochDev* ep_pin; double* sat_pin; cudaEvent_t pin_ev[dpe::kPinSlots]; int pin_next; size_t sat_cap;
     // per-stage event brackets (dpe_profile_*)
     int prof_on; int prof_n;                 // brackets recorded since the last read
     cudaEvent_t* prof_ev;                    // [2 * kProfMax]

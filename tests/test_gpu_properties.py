@@ -1,0 +1,154 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes (where the oracle is
+too slow to be the checker) and at the edges: the two scoring formulations agree, sharding is
+exact, the path is linear in the samples, channel order does not matter, minimum sizes work."""
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import orc, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _demo_case():
+    sc = H.scenario()
+    grid = synth.spread_grid()                                   # 25^4 = 390625 candidates (demo config)
+    tg = 6.0 * synth.spread_axis()
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[:4] += (4.0, -3.0, 2.0, 5.0)
+    return sc, grid, tg, sc.epoch_inputs(0, center=center, time_grid=tg), sc.block(0)
+
+
+def _scores(capi, ctx, iq, ep, mode, G, est=0):
+    res = ctx.epoch_run(iq, ep, score_mode=mode, est_mode=est)
+    return res, ctx.copy_out(capi.PTR_POS_SCORES, np.float64, G)
+
+
+def test_full_demo_grid_brute_force_equals_lookup(capi):
+    sc, grid, tg, ep, iq = _demo_case()
+    G = grid.shape[0]
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=G, time_dim=len(tg), lag_halfwidth=16,
+                       flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    r_l, s_l = _scores(capi, ctx, iq, ep, capi.SCORE_LOOKUP, G)
+    r_b, s_b = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, G)
+    assert ctx.brute_pairs() == G * sc.C and r_b.out_of_window == 0
+    assert np.max(np.abs(s_b - s_l) / s_l) < RTOL
+    assert r_b.argmax == r_l.argmax == int(np.argmax(s_l))       # first maximum
+    assert np.array_equal(np.array(r_b.z[:4]), np.array(r_l.z[:4]))
+    # spot-check 2000 random candidates of the full grid against the oracle
+    idx = np.random.default_rng(7).choice(G, 2000, replace=False)
+    ref = H.oracle_pos(H.oracle_bcs(), grid[idx], ep)
+    assert np.max(np.abs(s_b[idx] - ref["scores"]) / ref["scores"]) < RTOL
+    # weighted estimate, per-time satellite state, both formulations
+    w_l, _ = _scores(capi, ctx, iq, ep, capi.SCORE_LOOKUP, G, est=capi.EST_WEIGHTED)
+    w_b, _ = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, G, est=capi.EST_WEIGHTED)
+    assert np.max(np.abs(np.array(w_b.z[:4]) - np.array(w_l.z[:4]))) < 1e-3
+    assert abs(w_b.sum_score - w_l.sum_score) / w_l.sum_score < 1e-6
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sharded_contexts_reproduce_the_single_context_result(capi, mode):
+    """3 contexts holding contiguous shards (what 3 ranks would hold) + dpe_estimate on the gathered
+    partials == one context holding the whole grid, bit for bit."""
+    import dpe_pkg
+    import torch
+    sharding = dpe_pkg.submodule("sharding")
+    sc, iq, grid, ep = H.epoch_case(n=9, center_offset=(6.0, -4.0, 3.0, 7.0))
+    G, C, T = grid.shape[0], sc.C, ep["time_dim"]
+    full = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=C, G=G, time_dim=T, lag_halfwidth=16, flags=capi.FLAG_BRUTE_TILES)
+    full.grid_set(grid)
+    for est in (capi.EST_ARGMAX, capi.EST_WEIGHTED):
+        rf = full.epoch_run(iq, ep, score_mode=mode, est_mode=est)
+        sf = full.copy_out(capi.PTR_POS_SCORES, np.float64, G)
+        parts, scores = [], []
+        world = 3
+        ctxs = []
+        for r in range(world):
+            lo, hi = sharding.shard_range(G, world, r)
+            c = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=C, G=hi - lo, time_dim=T, lag_halfwidth=16,
+                             flags=capi.FLAG_BRUTE_TILES, grid_offset=lo, G_total=G)
+            c.grid_set(grid[lo:hi])
+            c.epoch_run(iq, ep, score_mode=mode, est_mode=est)
+            parts.append(c.copy_out(capi.PTR_PARTIAL, np.float64, capi.DPE_PARTIAL_LEN))
+            scores.append(c.copy_out(capi.PTR_POS_SCORES, np.float64, hi - lo))
+            ctxs.append(c)
+        assert np.array_equal(np.concatenate(scores), sf)           # same kernels, same inputs: identical bits
+        gathered = torch.from_numpy(np.concatenate(parts)).cuda()
+        ctxs[0].estimate(est, gathered, world)
+        rs = ctxs[0].result_fetch()
+        assert rs.argmax == rf.argmax and rs.max_score == rf.max_score
+        assert np.max(np.abs(np.array(rs.z[:4]) - np.array(rf.z[:4]))) < 1e-6
+        host = sharding.combine_partials(np.stack(parts), est)       # host mirror of k_finalize
+        assert host["argmax"] == rf.argmax and np.max(np.abs(host["z"] - np.array(rf.z[:4]))) < 1e-6
+        for c in ctxs:
+            c.close()
+    full.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_linearity_in_the_samples(capi, mode):
+    """Doubling the int16 samples (no clipping) doubles every score exactly: all products and sums
+    scale by a power of two."""
+    sc, iq, grid, ep = H.epoch_case(n=7)
+    assert np.abs(iq).max() < 16000
+    G = grid.shape[0]
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=G, time_dim=ep["time_dim"], lag_halfwidth=16,
+                       flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    _, s1 = _scores(capi, ctx, iq, ep, mode, G)
+    _, s2 = _scores(capi, ctx, (2 * iq).astype(np.int16), ep, mode, G)
+    assert np.array_equal(s2, 2.0 * s1)
+    ctx.close()
+
+
+def test_channel_order_does_not_matter(capi):
+    sc, iq, grid, ep = H.epoch_case(n=7, center_offset=(3.0, 2.0, -1.0, 4.0))
+    G, C, T = grid.shape[0], sc.C, ep["time_dim"]
+    perm = np.array([5, 2, 7, 0, 3, 6, 1, 4])
+    ep2 = dict(ep)
+    for k in ("prn", "rc_start", "ri_start", "fc", "fi", "cp_start", "cp_ref", "rc_end", "cp_end", "cp_ref_tow"):
+        ep2[k] = np.asarray(ep[k])[perm]
+    ep2["sat_states"] = ep["sat_states"].reshape(C, T, 8)[perm].reshape(C * T, 8)
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=C, G=G, time_dim=T, lag_halfwidth=16, flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    for mode in (capi.SCORE_LOOKUP, capi.SCORE_BRUTE):
+        r1, s1 = _scores(capi, ctx, iq, ep, mode, G)
+        r2, s2 = _scores(capi, ctx, iq, ep2, mode, G)
+        assert np.max(np.abs(s1 - s2) / s1) < 1e-12 and r1.argmax == r2.argmax
+    ctx.close()
+
+
+def test_minimum_sizes_one_candidate_one_channel(capi):
+    sc, iq, grid, ep = H.epoch_case(n=3)
+    one = dict(ep)
+    for k in ("prn", "rc_start", "ri_start", "fc", "fi", "cp_start", "cp_ref", "rc_end", "cp_end", "cp_ref_tow"):
+        one[k] = np.asarray(ep[k])[:1]
+    T = ep["time_dim"]
+    one["sat_states"] = ep["sat_states"][:T]
+    g1 = grid[40:41]                                               # the centre candidate
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=1, G=1, time_dim=T, lag_halfwidth=1, flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(g1)
+    bcs = orc.batch_corr_scores(iq, one["prn"], one["rc_start"], one["ri_start"], one["fc"], one["fi"], one["cp_start"],
+                                one["cp_ref"], one["fs"])
+    ref = H.oracle_pos(bcs, g1, one)
+    for mode in (capi.SCORE_LOOKUP, capi.SCORE_BRUTE):
+        r, s = _scores(capi, ctx, iq, one, mode, 1)
+        assert r.argmax == 0 and abs(s[0] - ref["scores"][0]) / ref["scores"][0] < RTOL
+    ctx.close()
+
+
+def test_ten_megahertz_block_length_beyond_16_bits(capi):
+    """S = 200000 overflows the reference's unsigned short block length (sampleblock.h:81)."""
+    sc, iq, grid, ep = H.epoch_case(fs=10.0e6, prns=synth.PRNS_12, n=5, spacing=(2.0, 2.0, 2.0, 2.0))
+    assert ep["S"] == 200000
+    G = grid.shape[0]
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=12, G=G, time_dim=ep["time_dim"], lag_halfwidth=16,
+                       flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    r_l, s_l = _scores(capi, ctx, iq, ep, capi.SCORE_LOOKUP, G)
+    r_b, s_b = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, G)
+    assert np.max(np.abs(s_b - s_l) / s_l) < RTOL and r_b.argmax == r_l.argmax
+    ctx.close()
