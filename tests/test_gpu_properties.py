@@ -117,7 +117,10 @@ def test_channel_order_does_not_matter(capi):
     for mode in (capi.SCORE_LOOKUP, capi.SCORE_BRUTE):
         r1, s1 = _scores(capi, ctx, iq, ep, mode, G)
         r2, s2 = _scores(capi, ctx, iq, ep2, mode, G)
-        assert np.max(np.abs(s1 - s2) / s1) < 1e-12 and r1.argmax == r2.argmax
+        # not bit-identical: the reference adds the row offset S*chan BEFORE the floor (batchcorrmanifold.cu:1797),
+        # so the lerp fraction depends on the channel slot at the 1e-10 level
+        # (and, in the brute-force path, its FP32 rounding)
+        assert np.max(np.abs(s1 - s2) / s1) < 1e-7 and r1.argmax == r2.argmax
     ctx.close()
 
 
