@@ -139,6 +139,7 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_reduce_partials(dpe_ctx* c, cudaStream_t s);
 int launch_score_vel(dpe_ctx* c, cudaStream_t s);
+int launch_dc_sum(dpe_ctx* c, cudaStream_t s);
 size_t brute_smem_bytes(int H);
 int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, cudaStream_t s);
 int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStream_t s);

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256)
 k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
           const EpochDev* __restrict__ ep, double fs, int S, int S_pad,
           float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
-          int32_t* __restrict__ idx_next, float* __restrict__ bx, int64_t bx_stride) {
+          int32_t* __restrict__ idx_next, float* __restrict__ bx, int64_t bx_stride,
+          const long long* __restrict__ dc, float2* __restrict__ zw) {
     __shared__ int8_t code_s[1024];
     const int c = blockIdx.y;
     const EpochDev& e = *ep;
@@ -89,6 +90,9 @@ k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
             v[2 * q + 1] = in ? iq[2 * (size_t)(n0 + q) + 1] : (int16_t)0;
         }
     }
+    // DC mean for the carrier branch: sum / (float)S (ComplexDivide, batchcorrscores.cu:1065,1210-1216)
+    const double inv = 1.0 / (double)(float)S;
+    const double mr = dc ? (double)dc[0] * inv : 0.0, mi = dc ? (double)dc[1] * inv : 0.0;
     float xr[4], xi[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -108,6 +112,9 @@ k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
             rs[(size_t)c * S + n] = code_s[chip];
             if (chip_idx) chip_idx[(size_t)c * S + n] = (int16_t)chip;
             xw[(size_t)c * S + n] = make_float2(xr[q], xi[q]);
+            if (zw)   // (x - mean) * conj(carrier), BCS_SubtractDCOffset :470-485
+                zw[(size_t)c * S + n] = make_float2((float)((I - mr) * cs + (Q - mi) * sn),
+                                                    (float)((Q - mi) * cs - (I - mr) * sn));
         }
     }
     if (bx) {  // float4-skewed interleaved plane for the brute-force kernel (zero beyond S)
@@ -272,9 +279,11 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     const bool brute = (c->cfg.flags & DPE_FLAG_BRUTE_TILES) != 0;
     dim3 grid((S_pad / 4 + 255) / 256, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
+    if (c->Gv > 0) { int rc = launch_dc_sum(c, s); if (rc) return rc; }
     k_prepare<<<grid, 256, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, brute ? S_pad : ((S + 3) / 4) * 4,
                                    c->xw, c->rs, c->chip_idx, c->idx_next,
-                                   brute ? c->bx : nullptr, c->bx_stride);
+                                   brute ? c->bx : nullptr, c->bx_stride, c->Gv > 0 ? c->dc_sum : nullptr,
+                                   c->Gv > 0 ? c->bb : nullptr);
     prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());

@@ -33,54 +33,54 @@ __global__ void __launch_bounds__(256) k_dc_sum(const int16_t* __restrict__ iq, 
     }
 }
 
-// bb[n] = (x[n] - mean) * conj(carrier)[n] * chosen replica[n]     (FP64 like k_prepare, FP32 out)
-__global__ void __launch_bounds__(256)
-k_carrier_baseband(const int16_t* __restrict__ iq, const long long* __restrict__ dc, const int8_t* __restrict__ rs,
-                   const int32_t* __restrict__ idx_next, const int32_t* __restrict__ no_flip,
-                   const EpochDev* __restrict__ ep, double fs, int S, float2* __restrict__ bb) {
-    const int c = blockIdx.y;
-    const EpochDev& e = *ep;
-    if (c >= e.C) return;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= S) return;
-    const double inv = 1.0 / (double)(float)S;                  // ComplexDivide(..., (float) S), :1065-1066
-    const double mr = (double)dc[0] * inv, mi = (double)dc[1] * inv;
-    double t = (double)n / fs;
-    t = round(t * 1.0e9) / 1.0e9;
-    double sn, cs;
-    sincos(2 * K_PI * (e.fi[c] * t + e.ri_start[c]), &sn, &cs);
-    const short2 v = reinterpret_cast<const short2*>(iq)[n];
-    const double I = (double)v.x - mr, Q = (double)v.y - mi;
-    double r = (double)rs[(size_t)c * S + n];
-    if (!no_flip[c] && n >= idx_next[c]) r = -r;
-    bb[(size_t)c * S + n] = make_float2((float)((I * cs + Q * sn) * r), (float)((Q * cs - I * sn) * r));
-}
-
 // One CTA per (1024-sample chunk, channel); warp w owns bins w, w+8, ...; lanes stride the samples.
+// bb[n] = zw[n] * chosen replica[n]  with zw = (x - mean) * conj(carrier) from k_prepare
+// (BCS_SubtractDCOffset :470-485, BCS_ChoosyBatchMultiplyAndPad :422-452).
+// Twiddles: lane handles samples n0 + lane + 32 i; exp(-j 2 pi n m / N_c) is evaluated exactly
+// (integer n*m mod N_c -> sincospif) every 8th step and advanced by the exact 32-sample rotation in
+// between (7 complex multiplies: < 5e-7 relative drift).
 __global__ void __launch_bounds__(256)
-k_carr_partial(const float2* __restrict__ bb, const EpochDev* __restrict__ ep, int S, int Wd, int NBd, int n_fft,
-               int nchunk, double2* __restrict__ vpart) {
+k_carr_partial(const float2* __restrict__ zw, const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
+               const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
+               int n_fft, int nchunk, double2* __restrict__ vpart) {
     __shared__ float2 xs[kCorrChunk];
     const int c = blockIdx.y;
     if (c >= ep->C) return;
     const int chunk = blockIdx.x, n0 = chunk * kCorrChunk;
-    for (int i = threadIdx.x; i < kCorrChunk; i += blockDim.x)
-        xs[i] = (n0 + i < S) ? bb[(size_t)c * S + n0 + i] : make_float2(0.f, 0.f);
+    const bool flip = !no_flip[c];
+    const int edge = idx_next[c];
+    for (int i = threadIdx.x; i < kCorrChunk; i += blockDim.x) {
+        const int n = n0 + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (n < S) {
+            v = zw[(size_t)c * S + n];
+            float r = (float)rs[(size_t)c * S + n];
+            if (flip && n >= edge) r = -r;
+            v.x *= r; v.y *= r;
+        }
+        xs[i] = v;
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned mask = (unsigned)n_fft - 1u;                 // n_fft is a power of two
     const float scale = 2.0f / (float)n_fft;
     for (int l = warp; l < NBd; l += 8) {
         const int m = l - Wd;                                   // bin relative to 0 Hz
+        float stp_s, stp_c;                                     // rotation of 32 samples: exp(-j 2 pi 32 m / N_c)
+        sincospif((float)((32u * (unsigned)m) & mask) * scale, &stp_s, &stp_c);
         float ar = 0.f, ai = 0.f;
-#pragma unroll 4
-        for (int i = lane; i < kCorrChunk; i += 32) {
-            const unsigned k = ((unsigned)(n0 + i) * (unsigned)m) & mask;     // n*m mod N_c (two's complement ok)
+#pragma unroll 1
+        for (int i0 = lane; i0 < kCorrChunk; i0 += 32 * 8) {
             float sn, cs;
-            sincospif((float)k * scale, &sn, &cs);              // exp(-j 2 pi k / N_c) = cs - j sn
-            const float2 x = xs[i];
-            ar = fmaf(x.x, cs, fmaf(x.y, sn, ar));
-            ai = fmaf(x.y, cs, fmaf(-x.x, sn, ai));
+            sincospif((float)(((unsigned)(n0 + i0) * (unsigned)m) & mask) * scale, &sn, &cs);   // exact re-sync
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float2 x = xs[i0 + 32 * k];
+                ar = fmaf(x.x, cs, fmaf(x.y, sn, ar));          // x * (cs - j sn)
+                ai = fmaf(x.y, cs, fmaf(-x.x, sn, ai));
+                const float c2 = cs * stp_c - sn * stp_s, s2 = sn * stp_c + cs * stp_s;
+                cs = c2; sn = s2;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -112,8 +112,19 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
             const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
             double* __restrict__ vscores, double* __restrict__ blk_partial) {
     __shared__ EpochDev e;
+    __shared__ double los_s[DPE_MAX_CHAN][8];
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
+    __syncthreads();
+    // the line of sight goes to the grid CENTRE (batchcorrmanifold.cu:1917-1921): one per channel, not per candidate
+    if (threadIdx.x < e.C) {
+        const int c = threadIdx.x;
+        const double* s = sat + ((size_t)c * T + T / 2) * 8;
+        double los[3] = {s[0] - e.center[0], s[1] - e.center[1], s[2] - e.center[2]};
+        const double range = norm(3, los);
+        los_s[c][0] = los[0] / range; los_s[c][1] = los[1] / range; los_s[c][2] = los[2] / range;
+        los_s[c][3] = s[4]; los_s[c][4] = s[5]; los_s[c][5] = s[6]; los_s[c][6] = s[7];
+    }
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < Gv;
@@ -128,12 +139,9 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
         v.pt = g[3] + e.center[7];
         const double ex = v.px - K_OEDOT * e.center[1], ey = v.py + K_OEDOT * e.center[0], ez = v.pz;
         for (int c = 0; c < e.C; ++c) {
-            const double* s = sat + ((size_t)c * T + T / 2) * 8;
-            double los[3] = {s[0] - e.center[0], s[1] - e.center[1], s[2] - e.center[2]};
-            const double range = norm(3, los);
-            const double rate = ((los[0] / range) * (ex - s[4])) + ((los[1] / range) * (ey - s[5])) +
-                                ((los[2] / range) * (ez - s[6]));
-            const double bc_fi = K_F_L1 * ((rate - v.pt) / K_C + s[7]) / e.doppler_sign;
+            const double* u = los_s[c];                          // unit LOS to the centre + satellite velocity / drift
+            const double rate = (u[0] * (ex - u[3])) + (u[1] * (ey - u[4])) + (u[2] * (ez - u[5]));
+            const double bc_fi = K_F_L1 * ((rate - v.pt) / K_C + u[6]) / e.doppler_sign;
             const double fi0 = bc_fi - e.fi[c];
             const double idx_base = (n_fft / fs) * fi0 + n_fft / 2.0;
             const bool valid = (idx_base < n_fft) && (idx_base > 0);
@@ -190,21 +198,28 @@ k_vel_finalize(const double* __restrict__ blk, int n_blk, const double* __restri
     }
 }
 
+// DC sum of the block; runs before k_prepare when a velocity grid exists (k_prepare then also
+// emits zw = (x - mean) * conj(carrier))
+int launch_dc_sum(dpe_ctx* c, cudaStream_t s) {
+    DPE_CUDA(cudaMemsetAsync(c->dc_sum, 0, 2 * sizeof(long long), s));
+    k_dc_sum<<<32, 256, 0, s>>>(c->iq, (int)c->S, c->dc_sum);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
 int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S, C = c->epoch_C;
     prof_begin(c, DPE_STAGE_VELOCITY, s);
-    DPE_CUDA(cudaMemsetAsync(c->dc_sum, 0, 2 * sizeof(long long), s));
-    k_dc_sum<<<32, 256, 0, s>>>(c->iq, S, c->dc_sum);
-    dim3 g1((S + 255) / 256, C);
-    k_carrier_baseband<<<g1, 256, 0, s>>>(c->iq, c->dc_sum, c->rs, c->idx_next, c->no_flip, c->ep, c->cfg.fs, S, c->bb);
     dim3 g2(c->nchunk, C);
-    k_carr_partial<<<g2, 256, 0, s>>>(c->bb, c->ep, S, c->Wd, c->NBd, c->n_fft, c->nchunk, c->vpart);
+    k_carr_partial<<<g2, 256, 0, s>>>(c->bb, c->rs, c->idx_next, c->no_flip, c->ep, S, c->Wd, c->NBd, c->n_fft,
+                                      c->nchunk, c->vpart);
     k_carr_finalize<<<C, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->nchunk, c->carr);
     const int nblk = (int)((c->Gv + kReduceBlock - 1) / kReduceBlock);
     k_score_vel<<<nblk, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd,
                                               c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial);
     k_vel_finalize<<<1, kReduceBlock, 0, s>>>(c->vblk_partial, nblk, c->vgrid, c->ep, c->zval, c->rval, c->result);
-    c->launches += 6;
+    c->launches += 4;
     prof_end(c, s);
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;

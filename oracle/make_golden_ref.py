@@ -33,7 +33,7 @@ synth = dpe_pkg.submodule("synth")
 
 I32 = ("cp_ref", "cp_start", "cp_end", "cp_ref_tow")
 F64 = ("rx_time", "tx_time", "rc_start", "ri_start", "rc_end", "ri_end", "fc", "fi", "sat_states", "sat_raw",
-       "enu2ecef", "x_kk1", "x_k1k1", "code_scores_win", "pos_scores", "zval", "time_grid")
+       "enu2ecef", "x_kk1", "x_k1k1", "code_scores_win", "carr_scores_win", "pos_scores", "zval", "time_grid")
 
 
 def main():
@@ -79,7 +79,7 @@ def main():
 
     meta = dict(l.split() for l in open(os.path.join(dump, "meta.txt")))
     C, CT = int(meta["C"]), int(meta["CT"])
-    pack = dict(first_block=1, C=C, T=CT // C, S=sc.S, fs=sc.cfg.fs, W=a.W, n=a.n, epochs=a.epochs, grid=grid,
+    pack = dict(first_block=1, Wd=64, vel_dim=5, C=C, T=CT // C, S=sc.S, fs=sc.cfg.fs, W=a.W, n=a.n, epochs=a.epochs, grid=grid,
                 offset=np.array(a.offset), truth0=sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T))
     for e in range(a.epochs):
         def rd(name, dt):
@@ -89,6 +89,7 @@ def main():
         for k in I32:
             pack["e%d_%s" % (e, k)] = rd(k, np.int32)
         pack["e%d_prn" % e] = rd("prn", np.uint8)
+        pack["n_fft"] = int(rd("n_fft", np.int32)[0])
         pack["e%d_iq" % e] = rd("iq", np.int16)
     path = os.path.join(a.out, "ref_epochs_n%d.npz" % a.n)
     np.savez_compressed(path, **pack)

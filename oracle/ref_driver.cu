@@ -139,6 +139,17 @@ class RefHarness : public dsp::DPEFlow {
                        (const char*)cs->Data + ((size_t)c * S + S / 2 - W) * 2 * sizeof(double),
                        (size_t)NL * 2 * sizeof(double), cudaMemcpyDeviceToHost);
         dump_host(out, e, "code_scores_win", win.data(), win.size() * sizeof(double));
+        // CarrScores window: fft-shifted bins N_c/2-Wd .. N_c/2+Wd+1 of the zero-padded carrier spectrum
+        dsp::Port* cr = P("BatchCorrScores", "CarrScores");
+        const int Nc = *(int*)P("BatchCorrScores", "NumFFTPoints")->Data;
+        const int Wd = 64, NBd = 2 * Wd + 2;
+        std::vector<double> cw((size_t)C * NBd * 2);
+        for (int c = 0; c < C; ++c)
+            cudaMemcpy(&cw[(size_t)c * NBd * 2],
+                       (const char*)cr->Data + ((size_t)c * Nc + Nc / 2 - Wd) * 2 * sizeof(double),
+                       (size_t)NBd * 2 * sizeof(double), cudaMemcpyDeviceToHost);
+        dump_host(out, e, "carr_scores_win", cw.data(), cw.size() * sizeof(double));
+        dump_host(out, e, "n_fft", &Nc, sizeof(int));
         int G = 0;
         GetModParam("BatchCorrManifold", "PosGridDimSize", &G);
         const size_t Gtot = (size_t)G * G * G * G;

@@ -104,6 +104,28 @@ def test_oracle_manifold_matches_reference_scores_and_fix(gold):
         assert np.array_equal(gold.k(e, "x_k1k1")[:4], gold.k(e, "zval")[:4])
 
 
+def test_oracle_carrier_spectrum_matches_reference(gold):
+    """Velocity branch: DC removal, chosen replica, zero-padded 524288-point spectrum
+    (batchcorrscores.cu:1158-1180) -- the reference's CarrScores window around 0 Hz."""
+    g = gold.g
+    Wd, n_fft = int(g["Wd"]), int(g["n_fft"])
+    NBd = 2 * Wd + 2
+    assert n_fft == 8 * (1 << int(np.ceil(np.log2(gold.S))))
+    for e in range(gold.epochs):
+        ep = gold.epoch_dict(e)
+        bcs = orc.batch_corr_scores(gold.k(e, "iq"), ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"],
+                                    ep["cp_start"], ep["cp_ref"], gold.fs, want_carrier=True)
+        ref = gold.k(e, "carr_scores_win").reshape(gold.C, NBd, 2)
+        ref = ref[..., 0] + 1j * ref[..., 1]
+        mine = bcs["carr_scores"][:, n_fft // 2 - Wd: n_fft // 2 - Wd + NBd]
+        assert np.max(np.abs(mine - ref) / np.max(np.abs(ref), axis=1)[:, None]) < 1e-12
+        # velocity arg-max of the reference (5^4 grid, 1 m/s) from the oracle's scores
+        vgrid, _ = H.synth.uniform_grid(int(g["vel_dim"]), 1.0)
+        v = orc.vel_meas_ml(bcs["carr_scores"], vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"], gold.T,
+                            ep["fi"], 1, gold.fs, n_fft)
+        assert np.max(np.abs(v["z"] - gold.k(e, "zval")[4:8])) < 1e-9
+
+
 def test_channel_manager_oracle_reproduces_reference_epoch_inputs(gold):
     """oracle/chanmgr_oracle.py (cuChanMgr restatement) started from the same handoff must
     reproduce what the reference's cuChanMgr handed to BCS/BCM at epoch 0."""
@@ -174,3 +196,19 @@ def test_cuda_path_matches_reference_golden(gold, capi):
         with pytest.raises(capi.DpeError):
             ctx.score_pos(capi.SCORE_BRUTE)                            # foreign correlogram: lookup only
         ctx.close()
+
+        # velocity manifold against the reference's CarrScores window and velocity fix
+        Wd, n_fft, vd = int(gold.g["Wd"]), int(gold.g["n_fft"]), int(gold.g["vel_dim"])
+        vgrid, _ = H.synth.uniform_grid(vd, 1.0)
+        cv = capi.Context(fs=gold.fs, S=gold.S, max_chan=gold.C, G=gold.grid.shape[0], time_dim=gold.T,
+                          lag_halfwidth=gold.W, Gv=vgrid.shape[0], dopp_halfwidth=Wd)
+        cv.grid_set(gold.grid)
+        cv.vel_grid_set(vgrid)
+        rv = cv.epoch_run(gold.k(e, "iq"), ep, with_vel=1)
+        NBd = 2 * Wd + 2
+        carr = cv.copy_out(capi.PTR_CARR_SCORES, np.float64, gold.C * NBd * 2).reshape(gold.C, NBd, 2)
+        refc = gold.k(e, "carr_scores_win").reshape(gold.C, NBd, 2)
+        d = (carr[..., 0] - refc[..., 0]) + 1j * (carr[..., 1] - refc[..., 1])
+        assert np.max(np.abs(d)) / np.max(np.hypot(refc[..., 0], refc[..., 1])) < 5e-6
+        assert np.max(np.abs(np.array(rv.z[4:8]) - gold.k(e, "zval")[4:8])) < 1e-9
+        cv.close()

@@ -250,7 +250,7 @@ def test_velocity_manifold_matches_oracle(capi, fs, prns):
     carr = ctx.copy_out(capi.PTR_CARR_SCORES, np.float64, C * NBd * 2).reshape(C, NBd, 2)
     got = carr[..., 0] + 1j * carr[..., 1]
     want = bcs["carr_scores"][:, n_fft // 2 - Wd: n_fft // 2 - Wd + NBd]
-    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 2e-6
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 5e-6
     vs = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
     assert np.max(np.abs(vs - ref["scores"]) / ref["scores"]) < SCORE_RTOL
     assert res.vel_argmax == ref["argmax"] and res.vel_out_of_window == 0
