@@ -251,9 +251,12 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
         const int c = h.x, k = h.y - W, n_valid = h.z;
-        float al[kBfNC];                                    // FFMA2 takes alpha as a broadcast .F32 operand
+        // one coalesced load of the group's 32 alphas, then register broadcast (FFMA2 takes alpha as a
+        // scalar .F32 operand)
+        const float a_mine = (lane < n_valid) ? ent_a[(size_t)g * kBfNC + lane] : 0.f;
+        float al[kBfNC];
 #pragma unroll
-        for (int j = 0; j < kBfNC; ++j) al[j] = (j < n_valid) ? ent_a[(size_t)g * kBfNC + j] : 0.f;
+        for (int j = 0; j < kBfNC; ++j) al[j] = __shfl_sync(0xffffffffu, a_mine, j);
         float2 acc[kBfNC];                                  // (re, im) of this lane's samples
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -292,21 +295,24 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
             }
         }
 
-        // lane partials -> FP64 -> warp butterfly; lane j keeps candidate j
-        double outr = 0.0, outi = 0.0;
+        // lane partials -> one candidate per lane: halving butterfly (31 shuffles per component instead of
+        // 160): at step o the lanes with bit o set keep the upper half of the candidates, the others the
+        // lower half; after 5 steps lane l holds the full sum of candidate l.  FP32 here (32 addends of
+        // equal weight: ~1e-7), FP64 from pair_v on.
 #pragma unroll
-        for (int j = 0; j < kBfNC; ++j) {
-            double re = (double)acc[j].x, im = (double)acc[j].y;
+        for (int o = 16, n = kBfNC / 2; o > 0; o >>= 1, n >>= 1) {
+            const bool up = (lane & o) != 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                re += __shfl_xor_sync(0xffffffffu, re, o);
-                im += __shfl_xor_sync(0xffffffffu, im, o);
+            for (int j = 0; j < n; ++j) {
+                const float2 keep = up ? acc[j + n] : acc[j];
+                const float2 send = up ? acc[j] : acc[j + n];
+                acc[j].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, o);
+                acc[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, o);
             }
-            if (lane == j) { outr = re; outi = im; }
         }
         if (lane < n_valid) {
             const int64_t j = ent_j[(size_t)g * kBfNC + lane];
-            pair_v[(size_t)c * G + j] = make_double2(outr, outi);
+            pair_v[(size_t)c * G + j] = make_double2((double)acc[0].x, (double)acc[0].y);
         }
     }
 }
