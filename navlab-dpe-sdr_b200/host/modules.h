@@ -122,7 +122,10 @@ class BatchCorrManifold : public Module {
     dpe_result last;
 };
 
-/** EKF disabled in the DPE flow: measurement copied into the state (cuekf.cu:147-159,577-592). */
+/** 8-state filter between the manifold and the channel manager.  The DPE flow runs it disabled
+ *  (EnableEKF=false, dpeflow.cpp:90): the measurement is copied into the state (EKF_PassMeas,
+ *  cuekf.cu:147-159,577-592).  Enabled: linear KF with H = I, random-walk F, speed-adaptive Q
+ *  (cuekf.cu:42-81,625-742), on the host -- 8x8 FP64 matrices. */
 class cuEKF : public Module {
   public:
     cuEKF();
@@ -133,7 +136,12 @@ class cuEKF : public Module {
   private:
     double SampleLength = 0.02;
     bool EnableEKF = false, Started = false;
-    double xkk1[8], xk1k1[8], Pkk1[64];
+    double xkk1[8], xk1k1[8], Pkk1[64], Pk1k1[64], F[64], Q[64];
+    double lpfVals[20], lpfAvg = 0;
+    int lpfIdx = 0;
+    long measIdx = 0, prevMeasIdx = 0;
+    int StepUpdate(const double* z, const double* R);
+    void StepPredict();
 };
 
 /** Channel manager + satellite states on the host (cuchanmgr.cu:240-923 runs them on the GPU). */

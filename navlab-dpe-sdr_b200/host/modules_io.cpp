@@ -1,5 +1,6 @@
 // modules_io.cpp -- DPInit, SampleBlock, cuEKF (pass-through), DataLogger: the host modules
 // either side of the hot path.
+#include <algorithm>
 #include <cerrno>
 #include <cmath>
 #include <cstring>
@@ -206,21 +207,106 @@ cuEKF::cuEKF() {
     InsertParam("EnableEKF", &EnableEKF, BOOL_t, sizeof(bool), sizeof(bool));
 }
 
+// 8x8 row-major helpers
+static void mat_mul(const double* A, const double* B, double* C, bool transB) {
+    for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 8; ++c) {
+            double s = 0;
+            for (int k = 0; k < 8; ++k) s += A[r * 8 + k] * (transB ? B[c * 8 + k] : B[k * 8 + c]);
+            C[r * 8 + c] = s;
+        }
+}
+
+static bool mat_inv(const double* A, double* inv) {            // Gauss-Jordan, partial pivoting
+    double a[8][16];
+    for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 8; ++c) { a[r][c] = A[r * 8 + c]; a[r][8 + c] = (r == c) ? 1.0 : 0.0; }
+    for (int p = 0; p < 8; ++p) {
+        int best = p;
+        for (int r = p + 1; r < 8; ++r)
+            if (std::fabs(a[r][p]) > std::fabs(a[best][p])) best = r;
+        if (a[best][p] == 0.0) return false;
+        if (best != p)
+            for (int c = 0; c < 16; ++c) std::swap(a[p][c], a[best][c]);
+        const double d = a[p][p];
+        for (int c = 0; c < 16; ++c) a[p][c] /= d;
+        for (int r = 0; r < 8; ++r)
+            if (r != p && a[r][p] != 0.0) {
+                const double f = a[r][p];
+                for (int c = 0; c < 16; ++c) a[r][c] -= f * a[p][c];
+            }
+    }
+    for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 8; ++c) inv[r * 8 + c] = a[r][8 + c];
+    return true;
+}
+
 int cuEKF::Start(void*) {
     if (Started) return 0;
     if (!InputsConnected()) return -1;
-    if (EnableEKF) {
-        std::cerr << "[cuEKF] the 8-state filter is out of scope (SURVEY.md section 8 f-4); EnableEKF must be false"
-                  << std::endl;
-        return -1;
-    }
     for (int i = 0; i < 8; ++i) xkk1[i] = xk1k1[i] = In<double>(0)[i];      // cuekf.cu:338-344
-    for (int i = 0; i < 64; ++i) Pkk1[i] = In<double>(1)[i];
+    for (int i = 0; i < 64; ++i) {
+        Pk1k1[i] = In<double>(1)[i];                                         // InitP
+        Pkk1[i] = Q[i] = F[i] = (i % 9 == 0) ? 1.0 : 0.0;                    // EKF_MakeIMatrix (:392-400)
+    }
+    for (int i = 0; i < 4; ++i) F[i * 8 + 4 + i] = SampleLength;            // EKF_MakeDPERandomWalkFMatrix (:107-135)
+    for (int i = 0; i < 20; ++i) lpfVals[i] = 0;
+    lpfAvg = 0; lpfIdx = 0; measIdx = 0; prevMeasIdx = -1;      // cuekf.cu:446-447: one predict per update
+    if (EnableEKF) StepPredict();   // "the initial value is a k-1|k-1 measurement; predict the next state" (:487-491)
     Started = true;
     return 0;
 }
 
+// y = z - H x_kk1, S = H P H' + R, K = P H' S^-1, x = x_kk1 + K y, P = (I - K H) P_kk1 with H = I
+// (cuEKF::StepUpdate, cuekf.cu:660-715)
+int cuEKF::StepUpdate(const double* z, const double* R) {
+    double S[64], Sinv[64], K[64], IKH[64], y[8];
+    for (int i = 0; i < 8; ++i) y[i] = z[i] - xkk1[i];
+    for (int i = 0; i < 64; ++i) S[i] = Pkk1[i] + R[i];
+    if (!mat_inv(S, Sinv)) { std::cerr << "[" << ModuleName << "] Error: StepUpdate() S inversion failed" << std::endl; return -1; }
+    mat_mul(Pkk1, Sinv, K, false);
+    for (int r = 0; r < 8; ++r) {
+        double s = xkk1[r];
+        for (int c = 0; c < 8; ++c) s += K[r * 8 + c] * y[c];
+        xk1k1[r] = s;
+    }
+    for (int i = 0; i < 64; ++i) IKH[i] = ((i % 9 == 0) ? 1.0 : 0.0) - K[i];
+    mat_mul(IKH, Pkk1, Pk1k1, false);
+    return 0;
+}
+
+// Q from the 20-tap mean speed (EKF_Update_Q, cuekf.cu:42-81; Q = F Qd F', GetQVal :733-742), then
+// x_kk1 = F x_k1k1, P_kk1 = F P_k1k1 F' + Q (StepPredict :636-655)
+void cuEKF::StepPredict() {
+    const double v = std::sqrt(xk1k1[4] * xk1k1[4] + xk1k1[5] * xk1k1[5] + xk1k1[6] * xk1k1[6]);
+    lpfAvg = lpfAvg - lpfVals[lpfIdx] + (v / 20.0);
+    lpfVals[lpfIdx] = v / 20.0;
+    if (++lpfIdx >= 20) lpfIdx = 0;
+    const double vval = 1.0 + 250.0 / std::fmin(std::fmax(lpfAvg * lpfAvg, 50.0), 125.0);
+    double Qd[64], T1[64];
+    for (int i = 0; i < 64; ++i) Qd[i] = 0;
+    Qd[4 * 8 + 4] = Qd[5 * 8 + 5] = Qd[6 * 8 + 6] = vval;
+    Qd[63] = (2.5e-10) * (2.5e-10) * 299792458.0 * 299792458.0;            // Q_CLOCK_DRIFT, cuekf.h:28
+    mat_mul(F, Qd, T1, false);
+    mat_mul(T1, F, Q, true);
+    for (int r = 0; r < 8; ++r) {
+        double s = 0;
+        for (int c = 0; c < 8; ++c) s += F[r * 8 + c] * xk1k1[c];
+        xkk1[r] = s;
+    }
+    mat_mul(F, Pk1k1, T1, false);
+    mat_mul(T1, F, Pkk1, true);
+    for (int i = 0; i < 64; ++i) Pkk1[i] += Q[i];
+}
+
 int cuEKF::Update(void*) {
+    if (!Started) return -1;
+    if (EnableEKF) {                                   // cuEKF::Update, cuekf.cu:577-589
+        if (StepUpdate(In<double>(3), In<double>(4))) return -1;
+        while (prevMeasIdx < measIdx) { StepPredict(); ++prevMeasIdx; }
+        ++measIdx;
+        return 0;
+    }
     // exactly 8 values (the reference copies 16, reading past zVal)
     for (int i = 0; i < 8; ++i) xk1k1[i] = xkk1[i] = In<double>(3)[i];
     return 0;

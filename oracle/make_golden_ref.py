@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--n", type=int, default=9)
     ap.add_argument("--W", type=int, default=32)
+    ap.add_argument("--ekf", action="store_true", help="enable the reference's 8-state KF (cuEKF EnableEKF=true); "
+                    "writes only the per-epoch states (ref_ekf_n<N>.npz)")
     ap.add_argument("--offset", type=float, nargs=4, default=[7.0, -4.0, 3.0, 8.0],
                     help="ECEF x,y,z and clock (m) offset of the handed-off state from the truth")
     a = ap.parse_args()
@@ -69,7 +71,7 @@ def main():
 
     dump = os.path.join(a.work, "dump")
     cmd = [exe, files["dat"], files["handoff"], files["rinex"], files["grid"], str(a.n), "5", str(a.epochs), dump,
-           str(a.W), repr(sc.cfg.fs), "1"]
+           str(a.W), repr(sc.cfg.fs), "1", "1" if a.ekf else "0"]
     print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     open(os.path.join(a.out, "ref_run.log"), "w").write(r.stdout)
@@ -91,7 +93,13 @@ def main():
         pack["e%d_prn" % e] = rd("prn", np.uint8)
         pack["n_fft"] = int(rd("n_fft", np.int32)[0])
         pack["e%d_iq" % e] = rd("iq", np.int16)
-    path = os.path.join(a.out, "ref_epochs_n%d.npz" % a.n)
+    if a.ekf:
+        keep = ("x_kk1", "x_k1k1", "zval", "rx_time")
+        import re
+        pack = {k: v for k, v in pack.items()
+                if not re.match(r"^e\d+_", k) or re.sub(r"^e\d+_", "", k) in keep}
+        pack["ekf"] = 1
+    path = os.path.join(a.out, ("ref_ekf_n%d.npz" if a.ekf else "ref_epochs_n%d.npz") % a.n)
     np.savez_compressed(path, **pack)
     print("wrote", path, os.path.getsize(path), "bytes")
     if os.path.exists(os.path.join(dump, "XFile.csv")):

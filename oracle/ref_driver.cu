@@ -170,6 +170,7 @@ int main(int argc, char** argv) {
     const int W = argc > 9 ? atoi(argv[9]) : 32;
     const double fs = argc > 10 ? atof(argv[10]) : 2.5e6;
     const bool dump = argc > 11 ? atoi(argv[11]) != 0 : true;
+    const bool ekf = argc > 12 ? atoi(argv[12]) != 0 : false;      // run the reference with its 8-state KF enabled
     mkdir(out.c_str(), 0755);
     if (!getenv("HOME")) setenv("HOME", "/tmp", 1);
 
@@ -195,6 +196,7 @@ int main(int argc, char** argv) {
     rc |= flow.SetModParam("BatchCorrManifold", "VelGridDimSize", vel_dim);
     rc |= flow.SetModParam("BatchCorrManifold", "GridLogFileName", (out + "/grid_log.csv").c_str());
     rc |= flow.SetModParam("XECEFLogger", "Filename", (out + "/XFile.csv").c_str());
+    if (ekf) rc |= flow.SetModParam("cuEKF", "EnableEKF", true);
     if (rc) { fprintf(stderr, "SetModParam failed\n"); return 1; }
     const int done = flow.Run(epochs, out, W, dump);
     fflush(stdout);

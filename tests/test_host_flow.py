@@ -255,3 +255,29 @@ def test_dpe_flow_reproduces_the_reference_epochs(flowapi, tmp_path):
         assert np.max(np.abs(rows[e, :3] - ref[:3])) < 0.1 and abs(rows[e, 3] - ref[3]) < 0.2998
         assert np.max(np.abs(rows[e, 4:] - ref[4:])) < 1e-5        # velocity manifold arg-max (5^4 grid, 1 m/s)
     sh.close()
+
+
+@pytest.mark.gpu
+def test_dpe_flow_with_the_kalman_filter_enabled_matches_the_reference(flowapi, tmp_path):
+    """`setparam <flow> cuEKF EnableEKF true` (the reference's 8-state KF: H = I, random-walk F,
+    speed-adaptive Q, cuekf.cu:42-81,625-742) against the UNMODIFIED reference run with the same switch
+    (tests/golden/ref_ekf_n9.npz, oracle/make_golden_ref.py --ekf)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_ekf_n9.npz"))
+    n, epochs, first = int(g["n"]), int(g["epochs"]), int(g["first_block"])
+    sc, grid, files = _write_scenario(tmp_path, n, epochs + first, first_block=first)
+    off = g["offset"]
+    extra = ["setparam rx DPInit InitDeltaX %r" % float(off[0]), "setparam rx DPInit InitDeltaY %r" % float(off[1]),
+             "setparam rx DPInit InitDeltaZ %r" % float(off[2]), "setparam rx DPInit InitDeltaT %r" % float(off[3]),
+             "setparam rx cuEKF EnableEKF true"]
+    xfile = str(tmp_path / "XFile.csv")
+    sh = _drive(flowapi, files, n, extra, epochs, xfile)
+    rows = np.loadtxt(xfile, delimiter=",")
+    assert rows.shape == (epochs, 8)
+    for e in range(epochs):
+        ref = g["e%d_x_k1k1" % e]
+        assert np.max(np.abs(rows[e, :3] - ref[:3])) < 1e-3 and abs(rows[e, 3] - ref[3]) < 1e-3, "epoch %d" % e
+        assert np.max(np.abs(rows[e, 4:] - ref[4:])) < 1e-5
+    # the prediction handed to the next epoch's grid (x_{k|k-1}) moved with the clock drift
+    xkk1 = sh.read_port("rx", "cuEKF", "xCurrkk1")
+    assert abs((xkk1[3] - g["e0_x_kk1"][3]) - epochs * 0.02 * g["e0_x_kk1"][7]) < 1e-3
+    sh.close()
