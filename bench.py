@@ -78,7 +78,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -355,6 +355,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_FLOW_FILES = {}
+
+
 def flow_realtime(args, path):
     """BASELINE.json config 2: the same synthetic capture pushed through the rebuilt `newflow dpe /
     loadflow / startflow` flow (file reader -> BCS -> BCM -> pass-through EKF -> host channel manager ->
@@ -366,7 +369,11 @@ def flow_realtime(args, path):
     sc, grid, tg = build_workload("demo")
     d = "/tmp/dpe_bench_flow"
     n_epochs = args.flow_epochs
-    files = sc.write_files(d, n_epochs + 34, grid=grid, handoff_block=0)   # + the reader's 32-block read-ahead
+    need = 4 * sc.S * (n_epochs + 34)                                    # + the reader's 32-block read-ahead
+    files = _FLOW_FILES.get("files")
+    if not files or os.path.getsize(files["dat"]) < need:
+        files = sc.write_files(d, n_epochs + 34, grid=grid, handoff_block=0)
+        _FLOW_FILES["files"] = files
     sh = flowapi.Shell()
     cmds = ["newflow dpe rx", "loadflow rx",
             'setparam rx SampleBlock Filename "%s"' % files["dat"],
