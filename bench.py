@@ -383,7 +383,6 @@ def flow_realtime(args, path):
             "setparam rx BatchCorrManifold LoadPosGrid true",
             "setparam rx BatchCorrManifold PosGridDimSize 25", "setparam rx BatchCorrManifold VelGridDimSize 25",
             "setparam rx BatchCorrManifold GridDimSpacing 0.5",
-            "setparam rx BatchCorrManifold LagHalfwidth %d" % args.lag_halfwidth,
             "setparam rx BatchCorrManifold BruteForce %s" % ("true" if path == "brute" else "false"),
             'setparam rx XECEFLogger Filename "%s/XFile.csv"' % d]
     for c in cmds:

@@ -273,10 +273,10 @@ int dpe_device_count(void);
 enum {
     DPE_STAGE_PREPARE = 0,       /* k_prepare                                        */
     DPE_STAGE_CORRELOGRAM = 1,   /* k_corr_partial + k_corr_finalize (+ replica plane)*/
-    DPE_STAGE_LOOKUP = 2,        /* k_score_lookup + k_reduce_partials               */
+    DPE_STAGE_LOOKUP = 2,        /* k_score_lookup (grid reduction fused, last CTA)  */
     DPE_STAGE_BRUTE_BINS = 3,    /* k_pair_bins + k_bucket_scan + k_scatter          */
     DPE_STAGE_BRUTE_CORR = 4,    /* k_brute (the north-star kernel) alone            */
-    DPE_STAGE_BRUTE_SCORE = 5,   /* k_score_pairs + k_reduce_partials                */
+    DPE_STAGE_BRUTE_SCORE = 5,   /* k_score_pairs (grid reduction fused, last CTA)   */
     DPE_STAGE_ESTIMATE = 6,      /* k_finalize                                       */
     DPE_STAGE_VELOCITY = 7,      /* velocity manifold: DC, baseband, windowed DFT, scoring */
     DPE_N_STAGES = 8

@@ -321,7 +321,8 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
 __global__ void __launch_bounds__(kReduceBlock)
 k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
               const int16_t* __restrict__ pair_k, const double2* __restrict__ pair_v, int lpower,
-              int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial) {
+              int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
+              unsigned int* __restrict__ ticket, double* __restrict__ partial) {
     const EpochDev& e = *ep;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < G;
@@ -341,6 +342,7 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         scores[j] = score;
     }
     block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
+    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
 }
 
 size_t brute_smem_bytes(int H) {
@@ -399,13 +401,12 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     prof_begin(c, DPE_STAGE_BRUTE_SCORE, s);
     const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
     k_score_pairs<<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_k, c->pair_v, c->cfg.lpower, c->G,
-                                                c->cfg.grid_offset, c->scores, c->blk_partial);
+                                                c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
-    rc = launch_reduce_partials(c, s);
     prof_end(c, s);
-    return rc;
+    return DPE_OK;
 }
 
 }  // namespace dpe

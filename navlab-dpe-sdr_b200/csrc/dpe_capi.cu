@@ -126,6 +126,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_ALLOC(c->scores, G);
     DPE_ALLOC(c->blk_partial, ((G + kReduceBlock - 1) / kReduceBlock) * 8);
     DPE_ALLOC(c->partial, kPartialLen);
+    DPE_ALLOC(c->ticket, 4);
     DPE_ALLOC(c->zval, 16);     // the reference's EKF_PassMeas reads 16; keep the slack
     DPE_ALLOC(c->rval, 64);
     DPE_ALLOC(c->result, 16);
@@ -190,7 +191,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     cudaSetDevice(c->cfg.device);
     void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
                     c->cpart, c->cs, c->bx, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
-                    c->zval, c->rval, c->result, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
+                    c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
                     c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial};
     for (void* p : ptrs)

@@ -102,4 +102,75 @@ __device__ __forceinline__ void block_reduce_store(double score, int64_t gidx, c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Grid-level reduction without a second launch: the CTA that takes the last ticket reduces all
+// block partials in a fixed order (so the result does not depend on which CTA happens to be last)
+// and resets the ticket counter for the next launch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool take_last_ticket(unsigned int* counter) {
+    __shared__ bool s_last;
+    __threadfence();                                   // this CTA's partial is visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *counter = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+// all kReduceBlock threads of one CTA: r[0..4] sums, r[5]/r[6] max / arg-max (lowest index on ties), r[7] sum;
+// valid in thread 0 on return
+__device__ __forceinline__ void reduce_all_partials(const double* __restrict__ blk, int n_blk, double (&r)[8]) {
+    __shared__ double shr[kReduceBlock][8];
+    r[0] = r[1] = r[2] = r[3] = r[4] = 0.0; r[5] = -1.0; r[6] = 9.0e18; r[7] = 0.0;
+    for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
+        const double* q = blk + (size_t)b * 8;
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcg(q + k);          // written by other CTAs: bypass L1
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] += v[k];
+        r[7] += v[7];
+        if (v[5] > r[5] || (v[5] == r[5] && v[6] < r[6])) { r[5] = v[5]; r[6] = v[6]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) shr[threadIdx.x][k] = r[k];
+    __syncthreads();
+    for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            double* a = shr[threadIdx.x];
+            const double* b = shr[threadIdx.x + s];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a[k] += b[k];
+            a[7] += b[7];
+            if (b[5] > a[5] || (b[5] == a[5] && b[6] < a[6])) { a[5] = b[5]; a[6] = b[6]; }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = shr[0][k];
+}
+
+// per-rank partial of the position manifold: sums, max / arg-max, and the arg-max candidate's state
+// (BCM_MakePosMeas, batchcorrmanifold.cu:1990-2000)
+__device__ __forceinline__ void finish_position_partial(const double* __restrict__ blk, int n_blk,
+                                                        const double* __restrict__ grid, const EpochDev& e,
+                                                        int64_t grid_offset, double* __restrict__ partial) {
+    double r[8];
+    reduce_all_partials(blk, n_blk, r);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) partial[k] = r[k];
+        for (int k = 8; k < kPartialLen; ++k) partial[k] = 0.0;
+        if (r[5] >= 0.0) {
+            const Cand p = cand_ecef(e, grid + 4 * ((int64_t)r[6] - grid_offset));
+            partial[8] = p.px; partial[9] = p.py; partial[10] = p.pz; partial[11] = p.pt;
+        }
+    }
+}
+
 }  // namespace dpe

@@ -87,6 +87,7 @@ struct dpe_ctx {
     int64_t bx_stride, br_stride;      // per-channel plane strides (floats)
     double* grid; double* scores;
     double* blk_partial; int32_t n_blk_partial;
+    unsigned int* ticket;              // last-CTA ticket counter of the scoring kernels (self-resetting)
     double* partial; double* zval; double* rval; double* result;  // result: device mirror of dpe_result
     // brute-force work lists
     int16_t* pair_k; float* pair_a; double2* pair_v;   // [C][G]
@@ -137,7 +138,6 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s);
 int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
-int launch_reduce_partials(dpe_ctx* c, cudaStream_t s);
 int launch_score_vel(dpe_ctx* c, cudaStream_t s);
 int launch_dc_sum(dpe_ctx* c, cudaStream_t s);
 size_t brute_smem_bytes(int H);

@@ -223,32 +223,44 @@ k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
 // k_corr_finalize: fixed-order FP64 sum of the chunk partials, flip / no-flip
 // choice on lag 0 (BCS_ChooseCodeCorr, batchcorrscores.cu:499-543), fft-shifted
 // window out (BCS_cufftBatchShift, :554-584: cs[l] <-> shifted bin l - W + S/2).
-__global__ void k_corr_finalize(const double2* __restrict__ cpart, const int32_t* __restrict__ idx_next,
-                                const EpochDev* __restrict__ ep, int S, int W, int NL, int NLp,
-                                int nchunk, double2* __restrict__ cs, int32_t* __restrict__ no_flip) {
-    __shared__ int s_noflip;
+// One warp per lag (lanes stride the chunks, xor-tree: a fixed summation order); every warp also
+// sums lag 0 so the decision needs no cross-CTA exchange.
+__device__ __forceinline__ void sum_chunks(const double2* __restrict__ cpart, int c, int l, int NLp, int nchunk,
+                                           int lane, double (&r)[4]) {
+    r[0] = r[1] = r[2] = r[3] = 0.0;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+        const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + l;
+        r[0] += p[0].x; r[1] += p[0].y; r[2] += p[NLp].x; r[3] += p[NLp].y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+}
+
+__global__ void __launch_bounds__(256)
+k_corr_finalize(const double2* __restrict__ cpart, const int32_t* __restrict__ idx_next,
+                const EpochDev* __restrict__ ep, int S, int W, int NL, int NLp,
+                int nchunk, double2* __restrict__ cs, int32_t* __restrict__ no_flip) {
     const int c = blockIdx.x;
     if (c >= ep->C) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.y * 8 + warp;
     const int edge_raw = idx_next[c];
     const bool edge = (edge_raw > 0) && (edge_raw < S);
-    double2 nf = make_double2(0, 0), fl = make_double2(0, 0);
-    const int l = threadIdx.x;
-    if (l < NL) {
-        double ax = 0, ay = 0, bx = 0, by = 0;
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + l;
-            ax += p[0].x; ay += p[0].y; bx += p[NLp].x; by += p[NLp].y;
-        }
-        nf = make_double2(ax + bx, ay + by);
-        if (edge) fl = make_double2(ax - bx, ay - by);     // else all-zero flipped replica (:364-367)
+    double z[4];
+    sum_chunks(cpart, c, W, NLp, nchunk, lane, z);                // lag 0
+    const bool keep = !edge || (hypot(z[0] + z[2], z[1] + z[3]) > hypot(z[0] - z[2], z[1] - z[3]));
+    if (blockIdx.y == 0 && threadIdx.x == 0) no_flip[c] = keep ? 1 : 0;
+    if (l >= NL) return;
+    double r[4];
+    sum_chunks(cpart, c, l, NLp, nchunk, lane, r);
+    if (lane == 0) {
+        double2 v;
+        if (keep) v = make_double2(r[0] + r[2], r[1] + r[3]);     // no-flip = A + B
+        else v = make_double2(r[0] - r[2], r[1] - r[3]);          // flipped = A - B (only chosen when an edge exists)
+        cs[(size_t)c * NL + l] = v;
     }
-    if (l == W) {   // lag 0
-        const bool keep = !edge || (hypot(nf.x, nf.y) > hypot(fl.x, fl.y));
-        s_noflip = keep ? 1 : 0;
-        no_flip[c] = s_noflip;
-    }
-    __syncthreads();
-    if (l < NL) cs[(size_t)c * NL + l] = s_noflip ? nf : fl;
 }
 
 // k_replica_plane: chosen replica (flip applied) as FP32 +-1 with a circular halo
@@ -301,9 +313,9 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
                                            c->nchunk, c->cpart);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    int threads = ((c->NL + 31) / 32) * 32;
-    k_corr_finalize<<<c->epoch_C, threads, 0, s>>>(c->cpart, c->idx_next, c->ep, S, c->W, c->NL,
-                                                   c->NLp, c->nchunk, c->cs, c->no_flip);
+    dim3 gf(c->epoch_C, (c->NL + 7) / 8);
+    k_corr_finalize<<<gf, 256, 0, s>>>(c->cpart, c->idx_next, c->ep, S, c->W, c->NL, c->NLp, c->nchunk, c->cs,
+                                       c->no_flip);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     if (c->cfg.flags & DPE_FLAG_BRUTE_TILES) {

@@ -22,7 +22,8 @@ template <int SAT_MODE>
 __global__ void __launch_bounds__(kReduceBlock)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
-               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial) {
+               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
+               unsigned int* __restrict__ ticket, double* __restrict__ partial) {
     __shared__ EpochDev e;
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
@@ -50,6 +51,7 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         scores[j] = score;
     }
     block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
+    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
 }
 
 // Bins only (parity tests: "code-phase bins bit-exact").
@@ -73,48 +75,9 @@ __global__ void k_debug_bins(const double* __restrict__ grid, const EpochDev* __
 }
 
 // ---------------------------------------------------------------------------
-// Estimate: level-2 reduction of the block partials (one CTA, fixed order) and
-// the final zVal / RVal.  partial[0..7] as block partials, [8..11] = ECEF / clock
-// of this rank's arg-max candidate.
+// Estimate.  partial[0..7] as block partials, [8..11] = ECEF / clock of this rank's arg-max candidate
+// (written by the last CTA of the scoring kernel, dpe_geom.cuh).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kReduceBlock)
-k_reduce_partials(const double* __restrict__ blk, int n_blk, const double* __restrict__ grid,
-                  const EpochDev* __restrict__ ep, int64_t grid_offset, double* __restrict__ partial) {
-    __shared__ double sh[kReduceBlock][8];
-    double r[8] = {0, 0, 0, 0, 0, -1.0, 9.0e18, 0};
-    for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
-        const double* q = blk + (size_t)b * 8;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) r[k] += q[k];
-        r[7] += q[7];
-        if (q[5] > r[5] || (q[5] == r[5] && q[6] < r[6])) { r[5] = q[5]; r[6] = q[6]; }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = r[k];
-    __syncthreads();
-    for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            double* a = sh[threadIdx.x];
-            const double* b = sh[threadIdx.x + s];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) a[k] += b[k];
-            a[7] += b[7];
-            if (b[5] > a[5] || (b[5] == a[5] && b[6] < a[6])) { a[5] = b[5]; a[6] = b[6]; }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) partial[k] = sh[0][k];
-        for (int k = 8; k < kPartialLen; ++k) partial[k] = 0.0;
-        if (sh[0][5] >= 0.0) {
-            const int64_t j = (int64_t)sh[0][6] - grid_offset;
-            const Cand p = cand_ecef(*ep, grid + 4 * j);         // BCM_MakePosMeas :1990-2000
-            partial[8] = p.px; partial[9] = p.py; partial[10] = p.pz; partial[11] = p.pt;
-        }
-    }
-}
-
 // One thread: combine the per-rank partials (rank order = ascending grid offset,
 // so "first maximum" = lowest global index, like thrust::max_element / np.argmax).
 // result layout mirrors dpe_result (doubles; indices exact below 2^53).
@@ -149,24 +112,15 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     if (sat_mode == DPE_SAT_PER_TIME)
         k_score_lookup<DPE_SAT_PER_TIME><<<nblk, kReduceBlock, 0, s>>>(
             c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
-            c->cfg.grid_offset, c->scores, c->blk_partial);
+            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
     else
         k_score_lookup<DPE_SAT_MIDDLE><<<nblk, kReduceBlock, 0, s>>>(
             c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
-            c->cfg.grid_offset, c->scores, c->blk_partial);
+            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
-    const int rc = launch_reduce_partials(c, s);
     prof_end(c, s);
-    return rc;
-}
-
-int launch_reduce_partials(dpe_ctx* c, cudaStream_t s) {
-    k_reduce_partials<<<1, kReduceBlock, 0, s>>>(c->blk_partial, c->n_blk_partial, c->grid, c->ep,
-                                                 c->cfg.grid_offset, c->partial);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
     return DPE_OK;
 }
 

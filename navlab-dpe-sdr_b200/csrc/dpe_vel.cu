@@ -91,18 +91,26 @@ k_carr_partial(const float2* __restrict__ zw, const int8_t* __restrict__ rs, con
     }
 }
 
-__global__ void k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ ep, int NBd,
-                                int nchunk, double2* __restrict__ carr) {
+// one warp per bin, lanes stride the chunks, xor-tree (fixed order)
+__global__ void __launch_bounds__(256)
+k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ ep, int NBd,
+                int nchunk, double2* __restrict__ carr) {
     const int c = blockIdx.x;
     if (c >= ep->C) return;
-    for (int l = threadIdx.x; l < NBd; l += blockDim.x) {
-        double re = 0, im = 0;
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const double2 p = vpart[((size_t)c * nchunk + ch) * NBd + l];
-            re += p.x; im += p.y;
-        }
-        carr[(size_t)c * NBd + l] = make_double2(re, im);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.y * 8 + warp;
+    if (l >= NBd) return;
+    double re = 0, im = 0;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+        const double2 p = vpart[((size_t)c * nchunk + ch) * NBd + l];
+        re += p.x; im += p.y;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if (lane == 0) carr[(size_t)c * NBd + l] = make_double2(re, im);
 }
 
 // BCM_VelMeasML with the arg-max fused (batchcorrmanifold.cu:1896-1962); partial layout as the
@@ -110,7 +118,9 @@ __global__ void k_carr_finalize(const double2* __restrict__ vpart, const EpochDe
 __global__ void __launch_bounds__(kReduceBlock)
 k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
-            double* __restrict__ vscores, double* __restrict__ blk_partial) {
+            double* __restrict__ vscores, double* __restrict__ blk_partial, unsigned int* __restrict__ ticket,
+            const double* __restrict__ vgrid_all, double* __restrict__ zval, double* __restrict__ rval,
+            double* __restrict__ res) {
     __shared__ EpochDev e;
     __shared__ double los_s[DPE_MAX_CHAN][8];
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
@@ -159,42 +169,21 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
         vscores[j] = score;
     }
     block_reduce_store(score, j, v, active, oow, blk_partial);
-}
-
-// level-2 reduction + BCM_MakeVelMeas: zVal[4:8], RVal rows 4-7, result slots
-__global__ void __launch_bounds__(kReduceBlock)
-k_vel_finalize(const double* __restrict__ blk, int n_blk, const double* __restrict__ vgrid,
-               const EpochDev* __restrict__ ep, double* __restrict__ zval, double* __restrict__ rval,
-               double* __restrict__ res) {
-    __shared__ double sh[kReduceBlock][3];
-    double mx = -1.0, mi = 9.0e18, oo = 0;
-    for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
-        const double* q = blk + (size_t)b * 8;
-        oo += q[7];
-        if (q[5] > mx || (q[5] == mx && q[6] < mi)) { mx = q[5]; mi = q[6]; }
-    }
-    sh[threadIdx.x][0] = mx; sh[threadIdx.x][1] = mi; sh[threadIdx.x][2] = oo;
-    __syncthreads();
-    for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            double* a = sh[threadIdx.x];
-            const double* b = sh[threadIdx.x + s];
-            a[2] += b[2];
-            if (b[0] > a[0] || (b[0] == a[0] && b[1] < a[1])) { a[0] = b[0]; a[1] = b[1]; }
+    // last CTA: arg-max over all candidates + BCM_MakeVelMeas (zVal[4:8], RVal rows 4-7, batchcorrmanifold.cu:2030-2068)
+    if (take_last_ticket(ticket)) {
+        double r[8];
+        reduce_all_partials(blk_partial, gridDim.x, r);
+        if (threadIdx.x == 0) {
+            const int64_t jm = (int64_t)r[6];
+            const double* g = vgrid_all + 4 * jm;
+            const double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
+                                 e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
+                                 e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
+            for (int k = 0; k < 4; ++k) { zval[4 + k] = z[k]; res[4 + k] = z[k]; }
+            for (int rr = 4; rr < 8; ++rr)
+                for (int k = 0; k < 8; ++k) rval[rr * 8 + k] = (rr == k) ? 1.0 : 0.0;
+            res[12] = r[5]; res[13] = (double)jm; res[14] = r[7];
         }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const EpochDev& e = *ep;
-        const int64_t j = (int64_t)sh[0][1];
-        const double* g = vgrid + 4 * j;
-        const double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
-                             e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
-                             e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
-        for (int k = 0; k < 4; ++k) { zval[4 + k] = z[k]; res[4 + k] = z[k]; }
-        for (int r = 4; r < 8; ++r)
-            for (int k = 0; k < 8; ++k) rval[r * 8 + k] = (r == k) ? 1.0 : 0.0;
-        res[12] = sh[0][0]; res[13] = (double)j; res[14] = sh[0][2];
     }
 }
 
@@ -214,12 +203,13 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     dim3 g2(c->nchunk, C);
     k_carr_partial<<<g2, 256, 0, s>>>(c->bb, c->rs, c->idx_next, c->no_flip, c->ep, S, c->Wd, c->NBd, c->n_fft,
                                       c->nchunk, c->vpart);
-    k_carr_finalize<<<C, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->nchunk, c->carr);
+    dim3 g3(C, (c->NBd + 7) / 8);
+    k_carr_finalize<<<g3, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->nchunk, c->carr);
     const int nblk = (int)((c->Gv + kReduceBlock - 1) / kReduceBlock);
     k_score_vel<<<nblk, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd,
-                                              c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial);
-    k_vel_finalize<<<1, kReduceBlock, 0, s>>>(c->vblk_partial, nblk, c->vgrid, c->ep, c->zval, c->rval, c->result);
-    c->launches += 4;
+                                              c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial, c->ticket,
+                                              c->vgrid, c->zval, c->rval, c->result);
+    c->launches += 3;
     prof_end(c, s);
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;

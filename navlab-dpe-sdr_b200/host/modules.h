@@ -114,7 +114,7 @@ class BatchCorrManifold : public Module {
     char Filename[kNameCap] = "", loadPosGridFilename[kNameCap] = "";
     // extensions (not in the reference): scoring path, estimator, lag window
     bool bruteForce = false, weightedMean = false;
-    int lagHalfwidth = 32, doppHalfwidth = 64;
+    int lagHalfwidth = 0, doppHalfwidth = 0;       // 0 = sized from the extent of the grids
     bool Started = false, haveVel = false;
     void* flowStream = nullptr;
     std::vector<double> grid, timeGrid;

@@ -1,6 +1,7 @@
 // modules_dpe.cpp -- BatchCorrScores and BatchCorrManifold: the two hot-path modules.  Their
 // Update() bodies gather the same input ports as the reference's modules and make C-ABI calls;
 // no device code, no CUDA runtime here.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <iostream>
@@ -176,7 +177,17 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
     cfg.time_dim = posGridDimSize;
     cfg.G = cfg.G_total = (int64_t)grid.size() / 4;
     cfg.lpower = LPower;
-    cfg.lag_halfwidth = lagHalfwidth;
+    // lag window: a candidate at ENU offset p and clock offset t moves the code phase by at most
+    // (|p| + |t|) / c seconds = (|p| + |t|) fs / c samples (+3 for the lerp neighbour and tracking residuals)
+    int W = lagHalfwidth;
+    if (W <= 0) {
+        double ext = 0;
+        for (size_t i = 0; i + 3 < grid.size(); i += 4)
+            ext = std::max(ext, std::sqrt(grid[i] * grid[i] + grid[i + 1] * grid[i + 1] + grid[i + 2] * grid[i + 2]) +
+                                    std::fabs(grid[i + 3]));
+        W = std::min(160, std::max(4, (int)std::ceil(ext * fs / gnss::kC) + 3));
+    }
+    cfg.lag_halfwidth = W;
     cfg.flags = bruteForce ? DPE_FLAG_BRUTE_TILES : 0;
     // velocity / drift manifold: BCM_InitVelGrid (batchcorrmanifold.cu:265-316) is uniform for every grid type
     std::vector<double> vgrid;
@@ -184,7 +195,20 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
         const int vd[4] = {velGridDimSize, velGridDimSize, velGridDimSize, velGridDimSize};
         gnss::MakeGrid(vd, sp, 0, &vgrid, nullptr);
         cfg.Gv = (int64_t)vgrid.size() / 4;
-        cfg.dopp_halfwidth = doppHalfwidth;
+        // Doppler window: velocity v and drift d move the carrier by at most (|v| + |d|) F_L1 / c Hz;
+        // bins of the zero-padded spectrum are fs / N_c wide (+3 bins for the lerp neighbour and residuals)
+        int Wd = doppHalfwidth;
+        if (Wd <= 0) {
+            double ext = 0;
+            for (size_t i = 0; i + 3 < vgrid.size(); i += 4)
+                ext = std::max(ext, std::sqrt(vgrid[i] * vgrid[i] + vgrid[i + 1] * vgrid[i + 1] + vgrid[i + 2] * vgrid[i + 2]) +
+                                        std::fabs(vgrid[i + 3]));
+            int64_t nfft = 1;
+            while (nfft < (int64_t)(fs * T + 0.5)) nfft <<= 1;
+            nfft *= 8;
+            Wd = std::min(4096, std::max(4, (int)std::ceil(ext * gnss::kFL1 / gnss::kC * (double)nfft / fs) + 3));
+        }
+        cfg.dopp_halfwidth = Wd;
     }
     SharedCtx* sh = SharedFor(cuFlowStream);
     if (sh->ctx) { dpe_ctx_destroy(sh->ctx); sh->ctx = nullptr; }
