@@ -25,13 +25,15 @@
 namespace dpe {
 
 // ---------------------------------------------------------------------------
-// pass 1: bins of every pair + (PRN, lag) histogram
+// pass 1: bins of every pair + per-block (PRN, lag) histograms.  The sort below is a stable
+// counting sort (position in the bucket = rank by candidate index), so the composition of every
+// group -- and with it the summation order of the split tail slots -- is the same on every run.
 // ---------------------------------------------------------------------------
 template <int SAT_MODE>
 __global__ void __launch_bounds__(256)
 k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             double fs, int S, int W, int T, int64_t G, int64_t grid_offset, int16_t* __restrict__ pair_k,
-            float* __restrict__ pair_a, int32_t* __restrict__ hist) {
+            float* __restrict__ pair_a, int32_t* __restrict__ blk_hist) {
     extern __shared__ int32_t hs[];
     const EpochDev& e = *ep;
     const int NB = 2 * W + 1;
@@ -52,7 +54,39 @@ k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, co
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbuck; i += blockDim.x)
-        if (hs[i]) atomicAdd(&hist[i], hs[i]);
+        blk_hist[(size_t)i * gridDim.x + blockIdx.x] = hs[i];    // bucket-major: the scan below is coalesced
+}
+
+// pass 1b: exclusive scan of every bucket's per-block counts (in place) + bucket totals.
+// One CTA per bucket, 256 blocks per step.
+__global__ void __launch_bounds__(256)
+k_block_scan(int32_t* __restrict__ blk_hist, int nblk, int32_t* __restrict__ hist) {
+    __shared__ int32_t wsum[8];
+    __shared__ int32_t s_carry;
+    int32_t* row = blk_hist + (size_t)blockIdx.x * nblk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblk; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        const int32_t v = (b < nblk) ? row[b] : 0;
+        int32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int32_t woff = 0;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        const int32_t carry = s_carry;
+        if (b < nblk) row[b] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) hist[blockIdx.x] = s_carry;
 }
 
 // ---------------------------------------------------------------------------
@@ -115,24 +149,28 @@ k_group_headers(const int32_t* __restrict__ hist, const int32_t* __restrict__ gr
     hdr[g] = make_int4(lo / NB, lo % NB, n, 0);
 }
 
-// pass 3: scatter the pairs into their bucket.  Neighbouring candidates mostly share the
-// lag, so the slot counter is bumped once per (warp, bucket) and the lanes take ranks.
+// pass 3: scatter the pairs into their bucket, in candidate order: bucket base + pairs of earlier
+// blocks (k_block_scan) + pairs of earlier warps of this block + rank among the warp's lanes.
 __global__ void __launch_bounds__(256)
 k_scatter(const int16_t* __restrict__ pair_k, const float* __restrict__ pair_a, int64_t G, int W,
-          const int64_t* __restrict__ bucket_base, int32_t* __restrict__ cursor,
+          const int64_t* __restrict__ bucket_base, const int32_t* __restrict__ blk_base,
           int32_t* __restrict__ ent_j, float* __restrict__ ent_a) {
+    extern __shared__ int32_t wcnt[];                      // [8 warps][NB]
+    const int NB = 2 * W + 1;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * NB; i += blockDim.x) wcnt[i] = 0;
+    __syncthreads();
     const int k = (j < G) ? (int)pair_k[(size_t)c * G + j] : -1;
-    const int key = (k >= 0) ? c * (2 * W + 1) + k : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader && key >= 0) base = atomicAdd(&cursor[key], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (key < 0) return;
-    const int64_t pos = bucket_base[key] + base + __popc(peers & ((1u << lane) - 1u));
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    if (k >= 0 && lane == __ffs(peers) - 1) wcnt[warp * NB + k] = __popc(peers);
+    __syncthreads();
+    if (k < 0) return;
+    int before = __popc(peers & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) before += wcnt[w * NB + k];
+    const int key = c * NB + k;
+    const int64_t pos = bucket_base[key] + blk_base[(size_t)key * gridDim.x + blockIdx.x] + before;
     ent_j[pos] = (int32_t)j;
     ent_a[pos] = pair_a[(size_t)c * G + j];
 }
@@ -207,9 +245,10 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
         int64_t bx_stride, int64_t br_stride, const int4* __restrict__ hdr,
         const int32_t* __restrict__ ent_j, const float* __restrict__ ent_a,
         const int32_t* __restrict__ n_groups, double2* __restrict__ pair_v, int64_t G, int S_pad,
-        int H, int W) {
+        int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kBfStages], empty_bar[kBfStages];
+    __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr_len = (int)skewR(kBfTile + 2 * H);        // floats, multiple of 4
     const int stage_f = kXTileF + rr_len;                  // floats per stage
@@ -221,10 +260,24 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
     }
     __syncthreads();
 
+    // Work decomposition.  Whole rounds of gridDim.x slots run one slot per CTA.  The R < gridDim.x
+    // slots left over would cost a full wave for a fraction of the SMs (8 GPUs, demo: 10.3 waves
+    // -> 11), so each of them is split over P = gridDim.x / R CTAs by sample range; the CTA that
+    // takes the slot's last ticket adds the P partial sums in part order (deterministic).
     const int n_slots = *n_groups / kBfWarps;
     const int ntiles = S_pad / kBfTile;
-    const int my_slots = (blockIdx.x < n_slots) ? (n_slots - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t my_tiles = (uint32_t)my_slots * ntiles;  // tiles this CTA streams, numbered 0..my_tiles-1
+    const int rounds = n_slots / (int)gridDim.x;
+    const int n_full = rounds * (int)gridDim.x;
+    const int R = n_slots - n_full;
+    int P = R ? (int)gridDim.x / R : 0;
+    if (P > kBfMaxParts) P = kBfMaxParts;
+    if (P > ntiles) P = ntiles;
+    const bool has_tail = (int)blockIdx.x < R * P;
+    const int tail_idx = has_tail ? (int)blockIdx.x / P : 0, part = has_tail ? (int)blockIdx.x % P : 0;
+    const int tail_t0 = has_tail ? part * ntiles / P : 0, tail_t1 = has_tail ? (part + 1) * ntiles / P : 0;
+    const uint32_t full_tiles = (uint32_t)rounds * ntiles;
+    const uint32_t my_tiles = full_tiles + (uint32_t)(tail_t1 - tail_t0);   // tiles this CTA streams, 0..my_tiles-1
+    const int n_items = rounds + (has_tail ? 1 : 0);
     uint32_t it = 0;                                       // running tile counter (same on all warps)
 
     // TMA producer duty (one elected lane): stream tile `jt` of this CTA's sequence into stage jt % stages.
@@ -232,8 +285,9 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
     // 168 registers per thread (16K registers per SM sub-partition); the duty rotates over the 8 warps.
     auto issue_tile = [&](uint32_t jt) {
         if (jt >= my_tiles) return;
-        const int slot = blockIdx.x + (int)(jt / ntiles) * gridDim.x;
-        const int t = (int)(jt % ntiles);
+        const bool tail = jt >= full_tiles;
+        const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + (int)(jt / ntiles) * (int)gridDim.x;
+        const int t = tail ? tail_t0 + (int)(jt - full_tiles) : (int)(jt % ntiles);
         const int c = hdr[(size_t)slot * kBfWarps].x;
         const int s = jt % kBfStages;
         const uint32_t bytes_x = kXTileF * 4, bytes_r = (uint32_t)rr_len * 4;
@@ -247,7 +301,10 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
 
     // ===== consumer warps =====
     const int lane_f4 = 5 * lane;                          // float4 index of this lane's run (skewX)
-    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+    for (int item = 0; item < n_items; ++item) {
+        const bool tail = item == rounds;
+        const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + item * (int)gridDim.x;
+        const int t_begin = tail ? tail_t0 : 0, t_end = tail ? tail_t1 : ntiles;
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
         const int c = h.x, k = h.y - W, n_valid = h.z;
@@ -267,7 +324,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
 #pragma unroll
         for (int i = 0; i <= kBfNS; ++i) off[i] = (int)skewR(Lu + i) + 9 * lane;
 
-        for (int t = 0; t < ntiles; ++t, ++it) {
+        for (int t = t_begin; t < t_end; ++t, ++it) {
             const int s = it % kBfStages;
             mbar_wait(&full_bar[s], (it / kBfStages) & 1);
             const float* st = stage0 + (size_t)s * stage_f;
@@ -310,9 +367,37 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
                 acc[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, o);
             }
         }
-        if (lane < n_valid) {
+        if (tail && P > 1) {
+            tail_part[((size_t)tail_idx * P + part) * (kBfWarps * kBfNC) + threadIdx.x] = acc[0];
+        } else if (lane < n_valid) {
             const int64_t j = ent_j[(size_t)g * kBfNC + lane];
             pair_v[(size_t)c * G + j] = make_double2((double)acc[0].x, (double)acc[0].y);
+        }
+    }
+
+    // split tail slot: the last of its P CTAs combines the parts
+    if (has_tail && P > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int tk = atomicAdd(&tail_ticket[tail_idx], 1u);
+            s_last = (tk == (unsigned int)P - 1u);
+            if (s_last) tail_ticket[tail_idx] = 0u;            // self-resetting for the next launch
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int g = (n_full + tail_idx) * kBfWarps + warp;
+            const int4 h = hdr[g];
+            if (lane < h.z) {
+                float2 v = __ldcg(&tail_part[(size_t)tail_idx * P * (kBfWarps * kBfNC) + threadIdx.x]);
+                for (int q = 1; q < P; ++q) {
+                    const float2 u = __ldcg(&tail_part[((size_t)tail_idx * P + q) * (kBfWarps * kBfNC) + threadIdx.x]);
+                    v.x += u.x; v.y += u.y;
+                }
+                const int64_t j = ent_j[(size_t)g * kBfNC + lane];
+                pair_v[(size_t)h.x * G + j] = make_double2((double)v.x, (double)v.y);
+            }
         }
     }
 }
@@ -352,16 +437,17 @@ size_t brute_smem_bytes(int H) {
 int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int C = c->epoch_C, NB = 2 * c->W + 1, nbuck = C * NB;
     prof_begin(c, DPE_STAGE_BRUTE_BINS, s);
-    DPE_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * nbuck, s));
-    DPE_CUDA(cudaMemsetAsync(c->cursor, 0, sizeof(int32_t) * nbuck, s));
     const int nblk = (int)((c->G + 255) / 256);
     const size_t hs_bytes = sizeof(int32_t) * nbuck;
     if (sat_mode == DPE_SAT_PER_TIME)
         k_pair_bins<DPE_SAT_PER_TIME><<<nblk, 256, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
-            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->hist);
+            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->blk_hist);
     else
         k_pair_bins<DPE_SAT_MIDDLE><<<nblk, 256, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
-            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->hist);
+            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->blk_hist);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    k_block_scan<<<nbuck, 256, 0, s>>>(c->blk_hist, nblk, c->hist);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     k_bucket_scan<<<1, 256, sizeof(int32_t) * (2 * nbuck + 1), s>>>(c->hist, c->ep, c->W, c->group_base,
@@ -373,8 +459,8 @@ int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     dim3 gs(nblk, C);
-    k_scatter<<<gs, 256, 0, s>>>(c->pair_k, c->pair_a, c->G, c->W, c->bucket_base, c->cursor,
-                                 reinterpret_cast<int32_t*>(c->ent_j), c->ent_a);
+    k_scatter<<<gs, 256, sizeof(int32_t) * 8 * NB, s>>>(c->pair_k, c->pair_a, c->G, c->W, c->bucket_base, c->blk_hist,
+                                                        reinterpret_cast<int32_t*>(c->ent_j), c->ent_a);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     prof_end(c, s);
@@ -394,7 +480,7 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     k_brute<<<c->sm_count, kBfWarps * 32, smem, s>>>(
         c->bx, c->brr, c->bx_stride, c->br_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
-        c->H, c->W);
+        c->H, c->W, c->tail_part, c->tail_ticket);
     prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());

@@ -143,13 +143,15 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->pair_a, C * G);
         DPE_ALLOC(c->pair_v, C * G);
         DPE_ALLOC(c->hist, C * NB);
-        DPE_ALLOC(c->cursor, C * NB);
+        DPE_ALLOC(c->blk_hist, C * NB * ((G + 255) / 256));
         DPE_ALLOC(c->bucket_base, C * NB);
         DPE_ALLOC(c->group_base, C * NB + 1);
         DPE_ALLOC(c->hdr, c->max_groups * 4);
         DPE_ALLOC(c->ent_j, c->max_groups * kBfNC);
         DPE_ALLOC(c->ent_a, c->max_groups * kBfNC);
         DPE_ALLOC(c->n_groups, 1);
+        DPE_ALLOC(c->tail_part, (size_t)c->sm_count * kBfWarps * kBfNC);
+        DPE_ALLOC(c->tail_ticket, c->sm_count);
     }
     if (cfg->Gv > 0) {
         DPE_REQUIRE(cfg->Gv < (1ll << 31), DPE_EINVAL, "Gv out of range");
@@ -191,8 +193,8 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     cudaSetDevice(c->cfg.device);
     void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
                     c->cpart, c->cs, c->bx, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
-                    c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->cursor,
-                    c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->dbg_f, c->dbg_alpha,
+                    c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
+                    c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
                     c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial};
     for (void* p : ptrs)
         if (p) cudaFree(p);

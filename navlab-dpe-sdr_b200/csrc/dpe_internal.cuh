@@ -45,6 +45,7 @@ constexpr int kBfChunk = 32 * kBfNS;   // samples per warp-chunk (256)
 constexpr int kBfTile = 1024;          // samples per TMA stage
 constexpr int kBfWarps = 8;            // consumer warps per CTA
 constexpr int kBfStages = 4;
+constexpr int kBfMaxParts = 8;          // sample-range parts a left-over slot is split into
 
 // Device copy of the per-epoch parameters (+ values derived on the device).
 struct EpochDev {
@@ -92,11 +93,14 @@ struct dpe_ctx {
     // brute-force work lists
     int16_t* pair_k; float* pair_a; double2* pair_v;   // [C][G]
     int32_t* hist;                     // [C][NB] counts, NB = 2W+1
-    int32_t* cursor; int64_t* bucket_base; int32_t* group_base;
+    int32_t* blk_hist;                 // [C*NB][ceil(G/256)] per-block counts, then exclusive block prefixes
+    int64_t* bucket_base; int32_t* group_base;
     int32_t* hdr;                      // group headers {c, krel, n, pad}
     int32_t* ent_j; float* ent_a;      // bucketed entries
     int32_t* n_groups;                 // device scalar: total groups (multiple of kBfWarps)
     int64_t max_groups;
+    float2* tail_part;                 // [sm_count][kBfWarps * kBfNC] partial sums of split tail slots
+    unsigned int* tail_ticket;         // [sm_count] arrivals per split slot (self-resetting)
     // debug
     int64_t* dbg_f; double* dbg_alpha;
     // velocity (section 8 f-1)

@@ -52,7 +52,9 @@ def test_full_demo_grid_brute_force_equals_lookup(capi):
 @pytest.mark.parametrize("mode", [0, 1])
 def test_sharded_contexts_reproduce_the_single_context_result(capi, mode):
     """3 contexts holding contiguous shards (what 3 ranks would hold) + dpe_estimate on the gathered
-    partials == one context holding the whole grid, bit for bit."""
+    partials == one context holding the whole grid: bit for bit on the lookup path; on the
+    brute-force path to FP32 summation order (the slots left over after whole waves are split by
+    sample range, and which pairs they hold depends on the shard), with the same arg-max."""
     import dpe_pkg
     import torch
     sharding = dpe_pkg.submodule("sharding")
@@ -75,11 +77,14 @@ def test_sharded_contexts_reproduce_the_single_context_result(capi, mode):
             parts.append(c.copy_out(capi.PTR_PARTIAL, np.float64, capi.DPE_PARTIAL_LEN))
             scores.append(c.copy_out(capi.PTR_POS_SCORES, np.float64, hi - lo))
             ctxs.append(c)
-        assert np.array_equal(np.concatenate(scores), sf)           # same kernels, same inputs: identical bits
+        if mode == 0:
+            assert np.array_equal(np.concatenate(scores), sf)       # same kernels, same inputs: identical bits
+        else:
+            assert np.max(np.abs(np.concatenate(scores) - sf) / sf) < 2e-6
         gathered = torch.from_numpy(np.concatenate(parts)).cuda()
         ctxs[0].estimate(est, gathered, world)
         rs = ctxs[0].result_fetch()
-        assert rs.argmax == rf.argmax and rs.max_score == rf.max_score
+        assert rs.argmax == rf.argmax and abs(rs.max_score - rf.max_score) <= (0 if mode == 0 else 2e-6 * rf.max_score)
         assert np.max(np.abs(np.array(rs.z[:4]) - np.array(rf.z[:4]))) < 1e-6
         host = sharding.combine_partials(np.stack(parts), est)       # host mirror of k_finalize
         assert host["argmax"] == rf.argmax and np.max(np.abs(host["z"] - np.array(rf.z[:4]))) < 1e-6
@@ -119,8 +124,29 @@ def test_channel_order_does_not_matter(capi):
         r2, s2 = _scores(capi, ctx, iq, ep2, mode, G)
         # not bit-identical: the reference adds the row offset S*chan BEFORE the floor (batchcorrmanifold.cu:1797),
         # so the lerp fraction depends on the channel slot at the 1e-10 level
-        # (and, in the brute-force path, its FP32 rounding)
-        assert np.max(np.abs(s1 - s2) / s1) < 1e-7 and r1.argmax == r2.argmax
+        # (and, in the brute-force path, its FP32 rounding and summation order)
+        assert np.max(np.abs(s1 - s2) / s1) < (1e-7 if mode == capi.SCORE_LOOKUP else 2e-6) and r1.argmax == r2.argmax
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_cand", [4700, 5100, 6000, 6561])
+def test_brute_force_split_tail_slots(capi, n_cand):
+    """Slots left over after whole waves of 148 are split over several CTAs by sample range
+    (k_brute, 2 to 8 parts depending on how many are left): same scores as the lookup path and as
+    the oracle, identical bits from run to run (the parts are added in a fixed order)."""
+    sc, iq, grid, ep = H.epoch_case(n=9, center_offset=(6.0, -4.0, 3.0, 7.0))
+    g = np.ascontiguousarray(grid[:n_cand])
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=n_cand, time_dim=ep["time_dim"], lag_halfwidth=16,
+                       flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(g)
+    r_l, s_l = _scores(capi, ctx, iq, ep, capi.SCORE_LOOKUP, n_cand)
+    r_b, s_b = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, n_cand)
+    r_b2, s_b2 = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, n_cand)
+    assert np.array_equal(s_b, s_b2) and r_b.argmax == r_b2.argmax
+    assert np.max(np.abs(s_b - s_l) / s_l) < RTOL and r_b.argmax == r_l.argmax
+    idx = np.random.default_rng(11).choice(n_cand, 500, replace=False)
+    ref = H.oracle_pos(H.oracle_bcs(), g[idx], ep)
+    assert np.max(np.abs(s_b[idx] - ref["scores"]) / ref["scores"]) < RTOL
     ctx.close()
 
 
