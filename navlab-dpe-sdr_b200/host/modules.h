@@ -54,7 +54,8 @@ class DPInit : public Module {
     std::vector<gnss::EphSet> initEph;
 };
 
-/** File reader thread -> ring of page-locked 20 ms blocks (sampleblock.cu:312-515). */
+/** Reader thread (capture file or TCP stream) -> ring of page-locked 20 ms blocks
+ *  (sampleblock.cu:102-156,312-515). */
 class SampleBlock : public Module {
   public:
     SampleBlock();
@@ -73,7 +74,8 @@ class SampleBlock : public Module {
     char InputSourceType = 0;
     int64_t BlockLength = 0;                       // samples per block (64-bit: 10 MHz works)
     std::vector<int16_t*> Blocks;                  // pinned host ring
-    FILE* fp = nullptr;
+    int fd = -1;                                   // capture file or connected TCP socket
+    int OpenSource();
     std::thread reader;
     std::mutex mu;
     std::condition_variable cv;

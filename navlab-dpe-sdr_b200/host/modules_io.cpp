@@ -1,5 +1,11 @@
 // modules_io.cpp -- DPInit, SampleBlock, cuEKF (pass-through), DataLogger: the host modules
 // either side of the hot path.
+#include <fcntl.h>
+#include <netdb.h>
+#include <sys/socket.h>
+#include <sys/types.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cerrno>
 #include <cmath>
@@ -105,20 +111,56 @@ SampleBlock::SampleBlock() {
 
 SampleBlock::~SampleBlock() { Stop(); }
 
+// SampleBlock::Open (sampleblock.cu:102-156): a capture file positioned at StartByte, or a TCP
+// client socket to Hostname:PortNo streaming the same interleaved int16 I/Q.
+int SampleBlock::OpenSource() {
+    if (InputSourceType == 0) {                                    // SAMPLE_INPUT_SOURCE_FILE
+        fd = ::open(Filename, O_RDONLY);
+        if (fd < 0) { std::cerr << "[SampleBlock] Unable to open file: " << Filename << std::endl; return -1; }
+        const long long start = *In<long long>(0);
+        // the reference rejects StartByte 0 (lseek()==0 is read as a failure, sampleblock.cu:123-128); accepted here
+        if (start < 0 || lseek(fd, (off_t)start, SEEK_SET) != (off_t)start) {
+            std::cerr << "[SampleBlock] Failed to skip ahead in file: " << Filename << std::endl;
+            ::close(fd); fd = -1;
+            return -1;
+        }
+        std::clog << "[" << ModuleName << "] Starting reading at byte " << start << " in file " << Filename << std::endl;
+        return 0;
+    }
+    if (InputSourceType == 1) {                                    // SAMPLE_INPUT_SOURCE_SOCKET
+        struct addrinfo hints, *res = nullptr;
+        std::memset(&hints, 0, sizeof(hints));
+        hints.ai_family = AF_INET;
+        hints.ai_socktype = SOCK_STREAM;
+        char port[16];
+        std::snprintf(port, sizeof(port), "%d", PortNo);
+        if (getaddrinfo(Hostname, port, &hints, &res) || !res) {
+            std::cerr << "[" << ModuleName << "] Open: Invalid hostname." << std::endl;
+            return -1;
+        }
+        fd = ::socket(res->ai_family, res->ai_socktype, res->ai_protocol);
+        if (fd < 0) {
+            std::cerr << "[" << ModuleName << "] Open: Unable to open socket." << std::endl;
+            freeaddrinfo(res);
+            return -1;
+        }
+        if (::connect(fd, res->ai_addr, res->ai_addrlen) < 0) {
+            std::cerr << "[" << ModuleName << "] Open: Failed to connect." << std::endl;
+            freeaddrinfo(res);
+            ::close(fd); fd = -1;
+            return -1;
+        }
+        freeaddrinfo(res);
+        return 0;
+    }
+    std::cerr << "[" << ModuleName << "] Open: Invalid input source type." << std::endl;
+    return -1;
+}
+
 int SampleBlock::Start(void*) {
     if (Started) return 0;
     if (!InputsConnected()) return -1;
-    if (InputSourceType != 0) { std::cerr << "[SampleBlock] only the file source is built" << std::endl; return -1; }
-    fp = std::fopen(Filename, "rb");
-    if (!fp) { std::cerr << "[SampleBlock] Unable to open file: " << Filename << std::endl; return -1; }
-    const long long start = *In<long long>(0);
-    // the reference rejects StartByte 0 (lseek()==0 is read as a failure, sampleblock.cu:123-128); accepted here
-    if (start < 0 || fseeko(fp, (off_t)start, SEEK_SET)) {
-        std::cerr << "[SampleBlock] Failed to skip ahead in file: " << Filename << std::endl;
-        std::fclose(fp); fp = nullptr;
-        return -1;
-    }
-    std::clog << "[" << ModuleName << "] Starting reading at byte " << start << " in file " << Filename << std::endl;
+    if (OpenSource()) return -1;
     BlockLength = (int64_t)(SamplingFrequency * SampleLength + 0.5);
     Blocks.assign(kNumBlocks, nullptr);
     for (int i = 0; i < kNumBlocks; ++i)
@@ -143,8 +185,16 @@ void SampleBlock::ReaderThread() {
             cv.wait(lk, [&] { return freeSlots > 0 || !KeepRunning; });
             if (!KeepRunning) break;
         }
-        const size_t got = std::fread(Blocks[loadIdx], 1, bytes, fp);
-        if (got != bytes) {                       // partial block at EOF is dropped like the reference does
+        size_t got = 0;                           // read() until the whole block is in (sampleblock.cu:353-373)
+        bool failed = false;
+        while (got < bytes) {
+            const ssize_t n = ::read(fd, reinterpret_cast<char*>(Blocks[loadIdx]) + got, bytes - got);
+            if (n < 0 && errno == EINTR) continue;
+            if (n < 0) { failed = true; std::perror("[SampleBlock] Read Error"); break; }
+            if (n == 0) break;
+            got += (size_t)n;
+        }
+        if (failed || got != bytes) {             // partial block at EOF is dropped like the reference does
             std::lock_guard<std::mutex> lk(mu);
             eof = true;
             cv.notify_all();
@@ -155,6 +205,8 @@ void SampleBlock::ReaderThread() {
         loadIdx = (loadIdx + 1) % kNumBlocks;
         std::lock_guard<std::mutex> lk(mu);
         --freeSlots; ++filled;
+        // live capture with every buffer full: the next samples will be lost (sampleblock.cu:419-421)
+        if (RunLive && freeSlots == 0) std::clog << "[SampleBlock] Fail real-time." << std::endl;
         cv.notify_all();
     }
 }
@@ -183,7 +235,7 @@ int SampleBlock::Stop() {
     if (reader.joinable()) reader.join();
     for (size_t i = 0; i < Blocks.size(); ++i) dpe_host_free(Blocks[i]);
     Blocks.clear();
-    if (fp) { std::fclose(fp); fp = nullptr; }
+    if (fd >= 0) { ::close(fd); fd = -1; }
     Started = false;
     return 0;
 }

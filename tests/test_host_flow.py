@@ -238,6 +238,45 @@ def test_dpe_flow_end_to_end_against_oracle_closed_loop(flowapi, tmp_path, brute
 
 
 @pytest.mark.gpu
+def test_dpe_flow_fed_over_tcp_equals_the_file_source(flowapi, tmp_path):
+    """SampleBlock's socket source (`InputSourceType` 1, `Hostname`, `PortNo`; sampleblock.cu:134-156):
+    the same capture streamed by a TCP server in ragged chunks gives the same fixes as the file."""
+    import socket
+    import threading
+    n, epochs = 5, 5
+    sc, grid, files = _write_scenario(tmp_path, n, epochs, first_block=0)
+    x_file, x_sock = str(tmp_path / "XFile_file.csv"), str(tmp_path / "XFile_sock.csv")
+    _drive(flowapi, files, n, (), epochs, x_file).close()
+
+    srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    port = srv.getsockname()[1]
+
+    def serve():
+        conn, _ = srv.accept()
+        data = open(files["dat"], "rb").read()
+        try:
+            for lo in range(0, len(data), 70001):                  # not a multiple of the 200000-byte block
+                conn.sendall(data[lo:lo + 70001])
+        except OSError:
+            pass                                                   # the flow stopped after `epochs` blocks
+        finally:
+            conn.close()
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    extra = ["setparam rx SampleBlock InputSourceType \\x01", 'setparam rx SampleBlock Hostname "127.0.0.1"',
+             "setparam rx SampleBlock PortNo %d" % port]
+    _drive(flowapi, files, n, extra, epochs, x_sock).close()
+    th.join(timeout=10)
+    srv.close()
+    a, b = np.loadtxt(x_file, delimiter=","), np.loadtxt(x_sock, delimiter=",")
+    assert a.shape == (epochs, 8) and np.array_equal(a, b)
+
+
+@pytest.mark.gpu
 def test_dpe_flow_reproduces_the_reference_epochs(flowapi, tmp_path):
     """Same files, same offset as oracle/make_golden_ref.py fed to the UNMODIFIED reference: the
     fixes and the channel parameters handed to BCS / BCM must agree epoch by epoch."""
