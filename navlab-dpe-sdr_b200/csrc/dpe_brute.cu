@@ -471,10 +471,9 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     int rc = launch_brute_passes(c, sat_mode, s);
     if (rc) return rc;
     const size_t smem = brute_smem_bytes(c->H);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->brute_attr_set) {          // per context: the attribute belongs to the device the context lives on
         DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        c->brute_attr_set = 1;
     }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
     k_brute<<<c->sm_count, kBfWarps * 32, smem, s>>>(

@@ -110,6 +110,7 @@ struct dpe_ctx {
     // state
     int have_block, have_epoch, have_prepare, have_corr, have_scores;
     int epoch_C;
+    int brute_attr_set;
     int64_t launches;
     dpe::EpochDev ep_host;
     // page-locked staging ring for the per-epoch uploads (no implicit stream sync, safe reuse)
