@@ -2,24 +2,28 @@
 // whole 20 ms block against its own blended C/A replica (SURVEY.md section 8 a').
 //
 //   v(j,c) = sum_m xw_c[m] * ( (1-a) r_c[(m-k) mod S] + a r_c[(m-k-1) mod S] )
+//          = sum_p xw_c[(p+k) mod S] * ( r_c[p] + a d_c[p] ),   d_c[p] = r_c[p-1] - r_c[p]
 //
 // with integer lag k and fraction a from the candidate's FP64 geometry
 // (batchcorrmanifold.cu:1779-1800).  By linearity this equals the reference's
 // lerp of two correlogram bins (:1806-1812) to rounding.
 //
-// Mapping (B200, FP32-pipe bound; the block and the replica live in SMEM / L2):
-//   * pairs are bucketed by (PRN, k) so that the 16 pairs of a warp ("group")
-//     share the replica window; lanes own runs of 8 contiguous samples, the 16
-//     candidates live in registers: per pair of consecutive samples 1 FFMA2 (blend,
-//     alpha as broadcast operand) + 2 FFMA2 (re / im accumulate) -- scalar FFMA tops out
-//     at 49.7 TFLOP/s on B200, FFMA2 at 67.9 (dpe_microbench_fp32);
-//   * sample / replica tiles of 1024 samples are staged by 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier full/empty pairs, 4 stages);
-//     the planes are stored pre-skewed in HBM so the staged tiles are read with
-//     conflict-free LDS.128 (samples) and lane-stride-9 LDS.32 (replica);
+// Mapping (B200; the kernel is bound by FFMA2 issue -- one per 2 cycles per sub-partition, and
+// nothing co-issues with it -- so the design minimises every other instruction):
+//   * pairs are bucketed by (PRN, k); a warp ("group") holds 32 pairs of one bucket in
+//     registers, a CTA slot = 8 groups of ONE bucket, so the whole CTA shares the lag;
+//   * the kernel walks the replica position p.  The replica is staged as (d, d, r, r) position
+//     pairs, the samples from the copy of the sample plane that is shifted by k (dpe_prepare.cu:
+//     k_sample_planes), so both tiles are aligned on p for every lag: a lane's 8 positions are
+//     4 + 4 conflict-free LDS.128 at immediate offsets, and there is no address arithmetic and
+//     no subtraction in the loop;
+//   * per pair of positions and candidate: 1 FFMA2 (blend, alpha as broadcast operand) +
+//     2 FFMA2 (re / im accumulate);
+//   * tiles of 1024 positions are staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//     full/empty pairs, 4 stages); the planes are stored pre-skewed in HBM;
 //   * persistent CTAs (one per SM), 8 warps (2 per scheduler, up to 255 registers); the TMA
 //     refill duty rotates over the warps instead of living in a 9th producer warp;
-//   * lane partials are combined with warp shuffles in FP64.
+//   * lane partials are combined with warp shuffles.
 #include "dpe_geom.cuh"
 
 namespace dpe {
@@ -90,8 +94,8 @@ k_block_scan(int32_t* __restrict__ blk_hist, int nblk, int32_t* __restrict__ his
 }
 
 // ---------------------------------------------------------------------------
-// pass 2: bucket -> group layout.  Every bucket is padded to whole groups of
-// kBfNC pairs, every channel to whole CTAs of kBfWarps groups.
+// pass 2: bucket -> group layout.  Every non-empty bucket is padded to whole groups of
+// kBfNC pairs and to whole CTA slots of kBfWarps groups (a slot has one PRN and one lag).
 //   k_bucket_scan    (1 CTA)  group base of every bucket, total group count
 //   k_group_headers  (many)   {channel, lag, valid pairs} of every group
 // ---------------------------------------------------------------------------
@@ -113,8 +117,8 @@ k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep,
             for (int b = 0; b < NB; ++b) {
                 gb[c * NB + b] = g;
                 g += (cnt[c * NB + b] + kBfNC - 1) / kBfNC;
+                g = ((g + kBfWarps - 1) / kBfWarps) * kBfWarps;
             }
-            g = ((g + kBfWarps - 1) / kBfWarps) * kBfWarps;
         }
         gb[nbuck] = g;
         *n_groups = (g <= max_groups) ? g : 0;
@@ -201,35 +205,31 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(s2u(dst)), "l"(src), "r"(bytes), "r"(s2u(bar)) : "memory");
 }
 
-constexpr int kXTileF = (int)skewX(kBfTile);               // 2560 floats: float4-skewed (re,im) tile of 1024 samples
-constexpr int kRTileStep = kBfTile + kBfTile / 8;          // 1152: word-skewed replica plane advance per tile
+constexpr int kXTileF = (int)skewX(kBfTile);               // 2560 floats: float4-skewed tile of 1024 elements
 
-// Register image of one warp-chunk (256 samples): per lane 8 contiguous samples as (re,im) pairs
-// and the 9 replica values r[m-k-1 .. m-k+7] its blend needs.
+// Register image of one warp-chunk (256 positions): per lane 8 contiguous positions as 4 sample
+// float4 (re,im,re,im) and 4 replica float4 (d,d,r,r).
 struct BruteChunk {
-    float4 x[4];
-    float rr[kBfNS + 1];
-    __device__ __forceinline__ void load(const float4* __restrict__ px, const float* __restrict__ prr,
-                                         const int (&off)[kBfNS + 1], int ch) {
+    float4 x[4], rd[4];
+    __device__ __forceinline__ void load(const float4* __restrict__ px, int ch) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = px[ch * 160 + i];
 #pragma unroll
-        for (int i = 0; i <= kBfNS; ++i) rr[i] = prr[off[i] + ch * 288];
+        for (int i = 0; i < 4; ++i) rd[i] = px[kXTileF / 4 + ch * 160 + i];
     }
     // FFMA2 operand economy (B200: an FFMA2 with three uncached 64-bit sources needs a third
-    // register-file cycle): the blend takes alpha as a scalar .F32 operand and (r1-r0, r0) pairs
+    // register-file cycle): the blend takes alpha as a scalar .F32 operand and (d, r) pairs
     // shared by all candidates; the accumulate takes the blended chip as a scalar .F32 operand
-    // and the (re,im) sample pair shared by all candidates.  Per 2 samples and candidate:
+    // and the (re,im) sample pair shared by all candidates.  Per 2 positions and candidate:
     // 1 FFMA2 blend + 2 FFMA2 accumulate = 12 FLOP.
     __device__ __forceinline__ void accumulate(const float (&al)[kBfNC], float2 (&acc)[kBfNC]) const {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 dp = make_float2(rr[2 * q] - rr[2 * q + 1], rr[2 * q + 1] - rr[2 * q + 2]);
-            const float2 r0 = make_float2(rr[2 * q + 1], rr[2 * q + 2]);
+            const float2 dp = make_float2(rd[q].x, rd[q].y), r0 = make_float2(rd[q].z, rd[q].w);
             const float2 xa = make_float2(x[q].x, x[q].y), xb = make_float2(x[q].z, x[q].w);
 #pragma unroll
             for (int j = 0; j < kBfNC; ++j) {
-                const float2 bp = __ffma2_rn(make_float2(al[j], al[j]), dp, r0);   // r0 + alpha (r1 - r0)
+                const float2 bp = __ffma2_rn(make_float2(al[j], al[j]), dp, r0);   // r + alpha d
                 acc[j] = __ffma2_rn(make_float2(bp.x, bp.x), xa, acc[j]);
                 acc[j] = __ffma2_rn(make_float2(bp.y, bp.y), xb, acc[j]);
             }
@@ -241,8 +241,8 @@ struct BruteChunk {
 // k_brute: persistent; CTA slot = kBfWarps groups of one channel.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBfWarps * 32, 1)
-k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
-        int64_t bx_stride, int64_t br_stride, const int4* __restrict__ hdr,
+k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
+        int64_t bx_stride, int64_t brd_stride, const int4* __restrict__ hdr,
         const int32_t* __restrict__ ent_j, const float* __restrict__ ent_a,
         const int32_t* __restrict__ n_groups, double2* __restrict__ pair_v, int64_t G, int S_pad,
         int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket) {
@@ -250,8 +250,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
     __shared__ __align__(8) uint64_t full_bar[kBfStages], empty_bar[kBfStages];
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rr_len = (int)skewR(kBfTile + 2 * H);        // floats, multiple of 4
-    const int stage_f = kXTileF + rr_len;                  // floats per stage
+    constexpr int stage_f = 2 * kXTileF;                   // floats per stage: sample tile, replica tile
     float* const stage0 = reinterpret_cast<float*>(smem);
 
     if (threadIdx.x == 0) {
@@ -288,16 +287,19 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
         const bool tail = jt >= full_tiles;
         const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + (int)(jt / ntiles) * (int)gridDim.x;
         const int t = tail ? tail_t0 + (int)(jt - full_tiles) : (int)(jt % ntiles);
-        const int c = hdr[(size_t)slot * kBfWarps].x;
+        const int4 h = hdr[(size_t)slot * kBfWarps];         // one PRN and one lag per slot
+        const int c = h.x, k = h.y - W;
+        const int ks = k & 7, kq = (k - ks) / 8;             // k = 8 kq + ks, ks in 0..7
         const int s = jt % kBfStages;
-        const uint32_t bytes_x = kXTileF * 4, bytes_r = (uint32_t)rr_len * 4;
+        constexpr uint32_t bytes = kXTileF * 4;
         float* dst = stage0 + (size_t)s * stage_f;
-        mbar_expect_tx(&full_bar[s], bytes_x + bytes_r);
-        tma_load_1d(dst, bx + c * bx_stride + (size_t)t * kXTileF, bytes_x, &full_bar[s]);
-        tma_load_1d(dst + kXTileF, brr + c * br_stride + (size_t)t * kRTileStep, bytes_r, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], 2 * bytes);
+        tma_load_1d(dst, bx + ((size_t)c * 8 + ks) * bx_stride + skewX((int64_t)t * kBfTile + 8 * kq + H), bytes,
+                    &full_bar[s]);
+        tma_load_1d(dst + kXTileF, brd + c * brd_stride + (size_t)t * kXTileF, bytes, &full_bar[s]);
     };
     if (threadIdx.x == 0)
-        for (uint32_t jt = 0; jt + 1 < kBfStages; ++jt) issue_tile(jt);       // prologue: stages-1 tiles in flight
+        for (uint32_t jt = 0; jt < kBfStages - kBfLag; ++jt) issue_tile(jt);  // prologue: stages - lag tiles in flight
 
     // ===== consumer warps =====
     const int lane_f4 = 5 * lane;                          // float4 index of this lane's run (skewX)
@@ -307,7 +309,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
         const int t_begin = tail ? tail_t0 : 0, t_end = tail ? tail_t1 : ntiles;
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
-        const int c = h.x, k = h.y - W, n_valid = h.z;
+        const int c = h.x, n_valid = h.z;
         // one coalesced load of the group's 32 alphas, then register broadcast (FFMA2 takes alpha as a
         // scalar .F32 operand)
         const float a_mine = (lane < n_valid) ? ent_a[(size_t)g * kBfNC + lane] : 0.f;
@@ -317,37 +319,28 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brr,
         float2 acc[kBfNC];                                  // (re, im) of this lane's samples
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) acc[j] = make_float2(0.f, 0.f);
-        // replica window: lane run starts at local x' = Lu + chunk*256 + lane*8, Lu = H - k - 1;
-        // word offsets of its 9 replica values in the skewed tile (constant over the whole block)
-        const int Lu = H - k - 1;
-        int off[kBfNS + 1];
-#pragma unroll
-        for (int i = 0; i <= kBfNS; ++i) off[i] = (int)skewR(Lu + i) + 9 * lane;
-
         for (int t = t_begin; t < t_end; ++t, ++it) {
             const int s = it % kBfStages;
             mbar_wait(&full_bar[s], (it / kBfStages) & 1);
-            const float* st = stage0 + (size_t)s * stage_f;
-            const float4* px = reinterpret_cast<const float4*>(st) + lane_f4;
-            const float* prr = st + kXTileF;
+            const float4* px = reinterpret_cast<const float4*>(stage0 + (size_t)s * stage_f) + lane_f4;
             // software pipeline over the 4 chunks of the tile: the shared-memory operands of chunk
             // ch+1 are in flight while chunk ch is computed (2 warps per scheduler are not enough to
             // hide the LDS latency otherwise: they run in lock step)
             BruteChunk cur, nxt;
-            cur.load(px, prr, off, 0);
+            cur.load(px, 0);
 #pragma unroll
             for (int ch = 0; ch < kBfTile / kBfChunk; ++ch) {
-                if (ch + 1 < kBfTile / kBfChunk) nxt.load(px, prr, off, ch + 1);
+                if (ch + 1 < kBfTile / kBfChunk) nxt.load(px, ch + 1);
                 cur.accumulate(al, acc);
                 cur = nxt;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            // refill duty of tile `it`: reload the stage tile it-1 used (everyone released it about a
-            // tile ago, so the wait is normally already satisfied) with tile it+stages-1
+            // refill duty of tile `it`: reload the stage tile it-lag used (everyone released it about a
+            // tile ago) with tile it+stages-lag
             if (warp == (int)(it % kBfWarps)) {
-                if (it >= 1) mbar_wait(&empty_bar[(it - 1) % kBfStages], ((it - 1) / kBfStages) & 1);
-                if (lane == 0) issue_tile(it + kBfStages - 1);
+                if (it >= kBfLag) mbar_wait(&empty_bar[(it - kBfLag) % kBfStages], ((it - kBfLag) / kBfStages) & 1);
+                if (lane == 0) issue_tile(it + kBfStages - kBfLag);
                 __syncwarp();
             }
         }
@@ -430,8 +423,8 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
 }
 
-size_t brute_smem_bytes(int H) {
-    return (size_t)kBfStages * (kXTileF + skewR(kBfTile + 2 * H)) * sizeof(float);
+size_t brute_smem_bytes(int) {
+    return (size_t)kBfStages * 2 * kXTileF * sizeof(float);
 }
 
 int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
@@ -477,7 +470,7 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
     k_brute<<<c->sm_count, kBfWarps * 32, smem, s>>>(
-        c->bx, c->brr, c->bx_stride, c->br_stride, reinterpret_cast<const int4*>(c->hdr),
+        c->bx, c->brd, c->bx_stride, c->brd_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
         c->H, c->W, c->tail_part, c->tail_ticket);
     prof_end(c, s);

@@ -131,14 +131,14 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_ALLOC(c->rval, 64);
     DPE_ALLOC(c->result, 16);
     if (brute) {
-        c->bx_stride = skewX(c->S_pad);
-        c->br_stride = skewR(c->S_pad + 2 * c->H);
-        DPE_ALLOC(c->bx, C * c->bx_stride);
-        DPE_ALLOC(c->brr, C * c->br_stride);
+        c->bx_stride = skewX(c->S_pad + 2 * c->H);
+        c->brd_stride = skewX(c->S_pad);
+        DPE_ALLOC(c->bx, C * 8 * c->bx_stride);
+        DPE_ALLOC(c->brd, C * c->brd_stride);
         const size_t NB = 2 * c->W + 1;
         DPE_REQUIRE(sizeof(int32_t) * (2 * C * NB + 1) <= 48 * 1024, DPE_EINVAL,
                     "max_chan * (2W+1) too large for the bucket scan");
-        c->max_groups = (int64_t)(C * ((G + kBfNC - 1) / kBfNC + NB) + C * kBfWarps);
+        c->max_groups = (int64_t)(C * ((G + kBfNC - 1) / kBfNC + NB * kBfWarps));   // every bucket padded to whole slots
         DPE_ALLOC(c->pair_k, C * G);
         DPE_ALLOC(c->pair_a, C * G);
         DPE_ALLOC(c->pair_v, C * G);
@@ -192,7 +192,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     if (!c) return DPE_OK;
     cudaSetDevice(c->cfg.device);
     void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
-                    c->cpart, c->cs, c->bx, c->brr, c->grid, c->scores, c->blk_partial, c->partial,
+                    c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
                     c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial};

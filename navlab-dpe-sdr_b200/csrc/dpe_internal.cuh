@@ -5,10 +5,14 @@
 //   ca        int8   [37][1024]         C/A chips, +/-1  (BCS chipsCACode_d)
 //   xw        float2 [C][S]             wiped samples x[n]*conj(carrier)      (natural order)
 //   rs        int8   [C][S]             no-flip replica sign r[n]
-//   bx        float2 [C][skewX(S_pad)/2] wiped samples (re,im interleaved), float4-skewed for the
-//                                       brute-force kernel's conflict-free LDS.128
-//   brr       float  [C][skewR(S_pad+2H)] chosen replica (flip applied) with circular halo,
-//                                       word-skewed for conflict-free lane-strided LDS.32
+//   bx        float  [C][8][skewX(S_pad+2H)] wiped samples for the brute-force kernel: copy s holds
+//                                       x[(p + s) mod S] at element p + H (circular halo H), (re,im)
+//                                       interleaved, float4-skewed (conflict-free LDS.128).  Lag
+//                                       k = 8 q + s reads copy s at element offset 8 q: every tile
+//                                       a slot streams is aligned on the replica position p
+//   brd       float  [C][skewX(S_pad)]  chosen replica (flip applied) by position pair:
+//                                       (d[p], d[p+1], r[p], r[p+1]), d[p] = r[p-1] - r[p] (circular),
+//                                       zero beyond S; same float4 skew
 //   cpart     double2[C][NCHUNK][2][NLp] per-chunk partial correlograms (A: n<idxNext, B: rest)
 //   cs        double2[C][NL]            fft-shifted "CodeScores" window, lag k = l - W
 //   grid      double [G][4]             candidates (ENU metres + clock metres)
@@ -44,7 +48,8 @@ constexpr int kBfNS = 8;               // contiguous samples per lane per chunk
 constexpr int kBfChunk = 32 * kBfNS;   // samples per warp-chunk (256)
 constexpr int kBfTile = 1024;          // samples per TMA stage
 constexpr int kBfWarps = 8;            // consumer warps per CTA
-constexpr int kBfStages = 4;
+constexpr int kBfStages = 4;            // TMA stages of 20 KB (sample tile + replica tile)
+constexpr int kBfLag = 1;               // a stage is refilled this many tiles after its release (8 / 4: no gain)
 constexpr int kBfMaxParts = 8;          // sample-range parts a left-over slot is split into
 
 // Device copy of the per-epoch parameters (+ values derived on the device).
@@ -60,11 +65,9 @@ struct EpochDev {
     int32_t cp_end[DPE_MAX_CHAN], cp_ref_tow[DPE_MAX_CHAN];
 };
 
-// word-skew for the replica plane: lanes stride 8 words -> stride 9 (conflict-free LDS.32)
-__host__ __device__ constexpr inline int64_t skewR(int64_t x) { return x + (x >> 3); }
-// float4-skew of the interleaved (re,im) sample plane: float offset of sample n.  One float4 holds
-// two samples; one pad float4 after every 4 (lane l reads float4 4l..4l+3 -> physical 5l..5l+3,
-// conflict-free LDS.128 because 5 is odd).
+// float4-skew of the brute-force planes: float offset of element n (a sample (re,im) or half of a
+// replica position pair).  One float4 holds two elements; one pad float4 after every 4 (lane l
+// reads float4 4l..4l+3 -> physical 5l..5l+3, conflict-free LDS.128 because 5 is odd).
 __host__ __device__ constexpr inline int64_t skewX(int64_t n) { return 4 * ((n >> 1) + (n >> 3)) + 2 * (n & 1); }
 
 }  // namespace dpe
@@ -84,8 +87,8 @@ struct dpe_ctx {
     float2* xw; int8_t* rs; int16_t* chip_idx;
     int32_t* idx_next; int32_t* no_flip;
     double2* cpart; double2* cs;
-    float *bx, *brr;
-    int64_t bx_stride, br_stride;      // per-channel plane strides (floats)
+    float *bx, *brd;
+    int64_t bx_stride, brd_stride;     // floats per sample-plane copy (8 copies per channel) / per replica plane
     double* grid; double* scores;
     double* blk_partial; int32_t n_blk_partial;
     unsigned int* ticket;              // last-CTA ticket counter of the scoring kernels (self-resetting)

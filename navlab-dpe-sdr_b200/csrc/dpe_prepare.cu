@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(256)
 k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
           const EpochDev* __restrict__ ep, double fs, int S, int S_pad,
           float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
-          int32_t* __restrict__ idx_next, float* __restrict__ bx, int64_t bx_stride,
-          const long long* __restrict__ dc, float2* __restrict__ zw) {
+          int32_t* __restrict__ idx_next, const long long* __restrict__ dc, float2* __restrict__ zw) {
     __shared__ int8_t code_s[1024];
     const int c = blockIdx.y;
     const EpochDev& e = *ep;
@@ -117,11 +116,27 @@ k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
                                                     (float)((Q - mi) * cs - (I - mr) * sn));
         }
     }
-    if (bx) {  // float4-skewed interleaved plane for the brute-force kernel (zero beyond S)
-        float4* p = reinterpret_cast<float4*>(bx + c * bx_stride + skewX(n0));   // n0 % 4 == 0: two adjacent float4
-        p[0] = make_float4(xr[0], xi[0], xr[1], xi[1]);
-        p[1] = make_float4(xr[2], xi[2], xr[3], xi[3]);
-    }
+}
+
+// ---------------------------------------------------------------------------
+// Planes of the brute-force kernel (dpe_brute.cu).  The kernel walks the replica
+// position p; a pair with lag k multiplies replica position p with sample
+// (p + k) mod S.  k_sample_planes writes the wiped samples 8 times, copy s shifted
+// by s samples, each with a circular halo of H elements, so that lag k = 8 q + s is
+// copy s read at element offset 8 q: 16-byte aligned for the TMA bulk copy and in
+// phase with the float4 skew for every lag.  One thread per element pair.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sample_planes(const float2* __restrict__ xw, const EpochDev* __restrict__ ep, int S, int n_elem, int H,
+                float* __restrict__ bx, int64_t bx_stride) {
+    const int c = blockIdx.y, s = blockIdx.z;
+    if (c >= ep->C) return;
+    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // element = p + H
+    if (e >= n_elem) return;
+    int n0 = (e - H + s) % S; if (n0 < 0) n0 += S;
+    int n1 = n0 + 1; if (n1 == S) n1 = 0;
+    const float2 a = xw[(size_t)c * S + n0], b = xw[(size_t)c * S + n1];
+    *reinterpret_cast<float4*>(bx + ((size_t)c * 8 + s) * bx_stride + skewX(e)) = make_float4(a.x, a.y, b.x, b.y);
 }
 
 // ---------------------------------------------------------------------------
@@ -263,19 +278,33 @@ k_corr_finalize(const double2* __restrict__ cpart, const int32_t* __restrict__ i
     }
 }
 
-// k_replica_plane: chosen replica (flip applied) as FP32 +-1 with a circular halo
-// of H samples each side, word-skewed, for the brute-force kernel.
-__global__ void k_replica_plane(const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
-                                const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep,
-                                int S, int S_pad, int H, float* __restrict__ brr, int64_t br_stride) {
+// k_replica_rd: chosen replica (flip applied) by position pair for the brute-force kernel:
+// (d[p], d[p+1], r[p], r[p+1]) with d[p] = r[(p-1) mod S] - r[p], so that the blended chip of a
+// candidate is r + alpha d; zero beyond S (the padded tail of the last tile contributes nothing).
+__global__ void __launch_bounds__(256)
+k_replica_rd(const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
+             const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep,
+             int S, int S_pad, float* __restrict__ brd, int64_t brd_stride) {
     const int c = blockIdx.y;
     if (c >= ep->C) return;
-    const int xp = blockIdx.x * blockDim.x + threadIdx.x;       // x' = x + H
-    if (xp >= S_pad + 2 * H) return;
-    int n = (xp - H) % S; if (n < 0) n += S;
-    float r = (float)rs[(size_t)c * S + n];
-    if (!no_flip[c] && n >= idx_next[c]) r = -r;
-    brr[c * br_stride + skewR(xp)] = r;
+    const int p = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (p >= S_pad) return;
+    const bool flip = !no_flip[c];
+    const int edge = idx_next[c];
+    auto rep = [&](int n) -> float {                      // n in [0, S)
+        const float r = (float)rs[(size_t)c * S + n];
+        return (flip && n >= edge) ? -r : r;
+    };
+    float r[2] = {0.f, 0.f}, d[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int n = p + q;
+        if (n < S) {
+            r[q] = rep(n);
+            d[q] = rep(n == 0 ? S - 1 : n - 1) - r[q];
+        }
+    }
+    *reinterpret_cast<float4*>(brd + c * brd_stride + skewX(p)) = make_float4(d[0], d[1], r[0], r[1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -289,16 +318,22 @@ int launch_gen_ca(dpe_ctx* c, cudaStream_t s) {
 int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S, S_pad = (int)c->S_pad;
     const bool brute = (c->cfg.flags & DPE_FLAG_BRUTE_TILES) != 0;
-    dim3 grid((S_pad / 4 + 255) / 256, c->epoch_C);
+    const int S4 = ((S + 3) / 4) * 4;
+    dim3 grid((S4 / 4 + 255) / 256, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
     if (c->Gv > 0) { int rc = launch_dc_sum(c, s); if (rc) return rc; }
-    k_prepare<<<grid, 256, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, brute ? S_pad : ((S + 3) / 4) * 4,
-                                   c->xw, c->rs, c->chip_idx, c->idx_next,
-                                   brute ? c->bx : nullptr, c->bx_stride, c->Gv > 0 ? c->dc_sum : nullptr,
-                                   c->Gv > 0 ? c->bb : nullptr);
-    prof_end(c, s);
+    k_prepare<<<grid, 256, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, S4, c->xw, c->rs, c->chip_idx, c->idx_next,
+                                   c->Gv > 0 ? c->dc_sum : nullptr, c->Gv > 0 ? c->bb : nullptr);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
+    if (brute) {
+        const int n_elem = S_pad + 2 * c->H;
+        dim3 g2((n_elem / 2 + 255) / 256, c->epoch_C, 8);
+        k_sample_planes<<<g2, 256, 0, s>>>(c->xw, c->ep, S, n_elem, c->H, c->bx, c->bx_stride);
+        c->launches++;
+        DPE_CUDA(cudaGetLastError());
+    }
+    prof_end(c, s);
     return DPE_OK;
 }
 
@@ -319,10 +354,9 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     if (c->cfg.flags & DPE_FLAG_BRUTE_TILES) {
-        const int n = (int)c->S_pad + 2 * c->H;
-        dim3 g2((n + 255) / 256, c->epoch_C);
-        k_replica_plane<<<g2, 256, 0, s>>>(c->rs, c->idx_next, c->no_flip, c->ep, S, (int)c->S_pad,
-                                           c->H, c->brr, c->br_stride);
+        dim3 g2(((int)c->S_pad / 2 + 255) / 256, c->epoch_C);
+        k_replica_rd<<<g2, 256, 0, s>>>(c->rs, c->idx_next, c->no_flip, c->ep, S, (int)c->S_pad, c->brd,
+                                        c->brd_stride);
         c->launches++;
         DPE_CUDA(cudaGetLastError());
     }
