@@ -205,6 +205,26 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(s2u(dst)), "l"(src), "r"(bytes), "r"(s2u(bar)) : "memory");
 }
 
+// the same on 32-bit shared-window addresses (computed once per kernel: no address arithmetic per tile)
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u(uint32_t b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u(uint32_t b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d_u(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 constexpr int kXTileF = (int)skewX(kBfTile);               // 2560 floats: float4-skewed tile of 1024 elements
 
 // Register image of one warp-chunk (256 positions): per lane 8 contiguous positions as 4 sample
@@ -247,14 +267,15 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         const int32_t* __restrict__ n_groups, double2* __restrict__ pair_v, int64_t G, int S_pad,
         int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[kBfStages], empty_bar[kBfStages];
+    __shared__ __align__(8) uint64_t bars[2 * kBfStages];  // full[s] = bars[s], empty[s] = bars[stages + s]
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int stage_f = 2 * kXTileF;                   // floats per stage: sample tile, replica tile
-    float* const stage0 = reinterpret_cast<float*>(smem);
+    static_assert((kBfStages & (kBfStages - 1)) == 0 && (kBfWarps & (kBfWarps - 1)) == 0, "powers of two");
+    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[kBfStages]), smem0 = s2u(smem);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kBfStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kBfWarps); }
+        for (int s = 0; s < kBfStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[kBfStages + s], kBfWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -274,35 +295,40 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
     const bool has_tail = (int)blockIdx.x < R * P;
     const int tail_idx = has_tail ? (int)blockIdx.x / P : 0, part = has_tail ? (int)blockIdx.x % P : 0;
     const int tail_t0 = has_tail ? part * ntiles / P : 0, tail_t1 = has_tail ? (part + 1) * ntiles / P : 0;
-    const uint32_t full_tiles = (uint32_t)rounds * ntiles;
-    const uint32_t my_tiles = full_tiles + (uint32_t)(tail_t1 - tail_t0);   // tiles this CTA streams, 0..my_tiles-1
     const int n_items = rounds + (has_tail ? 1 : 0);
     uint32_t it = 0;                                       // running tile counter (same on all warps)
 
-    // TMA producer duty (one elected lane): stream tile `jt` of this CTA's sequence into stage jt % stages.
-    // There is no dedicated producer warp: 9 warps would put 3 on one scheduler and cap the kernel at
-    // 168 registers per thread (16K registers per SM sub-partition); the duty rotates over the 8 warps.
-    auto issue_tile = [&](uint32_t jt) {
-        if (jt >= my_tiles) return;
-        const bool tail = jt >= full_tiles;
-        const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + (int)(jt / ntiles) * (int)gridDim.x;
-        const int t = tail ? tail_t0 + (int)(jt - full_tiles) : (int)(jt % ntiles);
+    // TMA producer duty (one elected lane): stream the tile `ahead` tiles after tile (item, off) of this
+    // CTA's sequence into stage `stg`.  There is no dedicated producer warp: 9 warps would put 3 on one
+    // scheduler and cap the kernel at 168 registers per thread (16K registers per SM sub-partition);
+    // the duty rotates over the 8 warps.
+    auto issue_tile = [&](int item, int off, int ahead, uint32_t stg) {
+        off += ahead;
+        for (;;) {                                           // usually no iteration: same slot
+            if (item >= n_items) return;
+            const int len = (item == rounds) ? tail_t1 - tail_t0 : ntiles;
+            if (off < len) break;
+            off -= len; ++item;
+        }
+        const bool tail = item == rounds;
+        const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + item * (int)gridDim.x;
+        const int t = (tail ? tail_t0 : 0) + off;
         const int4 h = hdr[(size_t)slot * kBfWarps];         // one PRN and one lag per slot
         const int c = h.x, k = h.y - W;
         const int ks = k & 7, kq = (k - ks) / 8;             // k = 8 kq + ks, ks in 0..7
-        const int s = jt % kBfStages;
         constexpr uint32_t bytes = kXTileF * 4;
-        float* dst = stage0 + (size_t)s * stage_f;
-        mbar_expect_tx(&full_bar[s], 2 * bytes);
-        tma_load_1d(dst, bx + ((size_t)c * 8 + ks) * bx_stride + skewX((int64_t)t * kBfTile + 8 * kq + H), bytes,
-                    &full_bar[s]);
-        tma_load_1d(dst + kXTileF, brd + c * brd_stride + (size_t)t * kXTileF, bytes, &full_bar[s]);
+        const uint32_t dst = smem0 + stg * (stage_f * 4), bar = full0 + 8 * stg;
+        mbar_expect_tx_u(bar, 2 * bytes);
+        tma_load_1d_u(dst, bx + ((size_t)c * 8 + ks) * bx_stride + skewX((int64_t)t * kBfTile + 8 * kq + H), bytes, bar);
+        tma_load_1d_u(dst + bytes, brd + c * brd_stride + (size_t)t * kXTileF, bytes, bar);
     };
     if (threadIdx.x == 0)
-        for (uint32_t jt = 0; jt < kBfStages - kBfLag; ++jt) issue_tile(jt);  // prologue: stages - lag tiles in flight
+        for (int j = 0; j < kBfStages - kBfLag; ++j) issue_tile(0, 0, j, (uint32_t)j);   // prologue
 
     // ===== consumer warps =====
-    const int lane_f4 = 5 * lane;                          // float4 index of this lane's run (skewX)
+    const float4* const px0 = reinterpret_cast<const float4*>(smem) + 5 * lane;   // lane's run in stage 0 (skewX)
+    const float4* px = px0;
+    uint32_t stg = 0, par = 0;                             // stage and full-barrier parity of tile `it`
     for (int item = 0; item < n_items; ++item) {
         const bool tail = item == rounds;
         const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + item * (int)gridDim.x;
@@ -319,10 +345,8 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         float2 acc[kBfNC];                                  // (re, im) of this lane's samples
 #pragma unroll
         for (int j = 0; j < kBfNC; ++j) acc[j] = make_float2(0.f, 0.f);
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-            const int s = it % kBfStages;
-            mbar_wait(&full_bar[s], (it / kBfStages) & 1);
-            const float4* px = reinterpret_cast<const float4*>(stage0 + (size_t)s * stage_f) + lane_f4;
+        for (int t = t_begin; t < t_end; ++t) {
+            mbar_wait_u(full0 + 8 * stg, par);
             // software pipeline over the 4 chunks of the tile: the shared-memory operands of chunk
             // ch+1 are in flight while chunk ch is computed (2 warps per scheduler are not enough to
             // hide the LDS latency otherwise: they run in lock step)
@@ -335,14 +359,18 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
                 cur = nxt;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) mbar_arrive_u(empty0 + 8 * stg);
             // refill duty of tile `it`: reload the stage tile it-lag used (everyone released it about a
             // tile ago) with tile it+stages-lag
-            if (warp == (int)(it % kBfWarps)) {
-                if (it >= kBfLag) mbar_wait(&empty_bar[(it - kBfLag) % kBfStages], ((it - kBfLag) / kBfStages) & 1);
-                if (lane == 0) issue_tile(it + kBfStages - kBfLag);
+            if (warp == (int)(it & (kBfWarps - 1))) {
+                const uint32_t rs = (it - kBfLag) & (kBfStages - 1);
+                if (it >= kBfLag) mbar_wait_u(empty0 + 8 * rs, ((it - kBfLag) / kBfStages) & 1);
+                if (lane == 0) issue_tile(item, t - t_begin, kBfStages - kBfLag, rs);
                 __syncwarp();
             }
+            ++it;
+            px += stage_f / 4;
+            if (++stg == kBfStages) { stg = 0; par ^= 1; px = px0; }
         }
 
         // lane partials -> one candidate per lane: halving butterfly (31 shuffles per component instead of
