@@ -458,6 +458,11 @@ size_t brute_smem_bytes(int) {
 int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int C = c->epoch_C, NB = 2 * c->W + 1, nbuck = C * NB;
     prof_begin(c, DPE_STAGE_BRUTE_BINS, s);
+    if (!c->have_planes) {
+        int rc = launch_brute_planes(c, s);
+        if (rc) return rc;
+        c->have_planes = 1;
+    }
     const int nblk = (int)((c->G + 255) / 256);
     const size_t hs_bytes = sizeof(int32_t) * nbuck;
     if (sat_mode == DPE_SAT_PER_TIME)

@@ -323,6 +323,7 @@ int dpe_replica_prepare(dpe_ctx* c, void* stream) {
     int rc = launch_prepare(c, (cudaStream_t)stream);
     if (rc) return rc;
     c->have_prepare = 1;
+    c->have_planes = 0;
     c->have_corr = 0;
     return DPE_OK;
 }
@@ -333,6 +334,7 @@ int dpe_correlogram(dpe_ctx* c, void* stream) {
     int rc = launch_correlogram(c, (cudaStream_t)stream);
     if (rc) return rc;
     c->have_corr = 1;
+    c->have_planes = 0;
     return DPE_OK;
 }
 

@@ -114,6 +114,7 @@ struct dpe_ctx {
     int have_block, have_epoch, have_prepare, have_corr, have_scores;
     int epoch_C;
     int brute_attr_set;
+    int have_planes;                   // brute-force planes match the current prepare + correlogram
     int64_t launches;
     dpe::EpochDev ep_host;
     // page-locked staging ring for the per-epoch uploads (no implicit stream sync, safe reuse)
@@ -146,6 +147,7 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s);
 int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
+int launch_brute_planes(dpe_ctx* c, cudaStream_t s);
 int launch_score_vel(dpe_ctx* c, cudaStream_t s);
 int launch_dc_sum(dpe_ctx* c, cudaStream_t s);
 size_t brute_smem_bytes(int H);

@@ -316,8 +316,7 @@ int launch_gen_ca(dpe_ctx* c, cudaStream_t s) {
 }
 
 int launch_prepare(dpe_ctx* c, cudaStream_t s) {
-    const int S = (int)c->S, S_pad = (int)c->S_pad;
-    const bool brute = (c->cfg.flags & DPE_FLAG_BRUTE_TILES) != 0;
+    const int S = (int)c->S;
     const int S4 = ((S + 3) / 4) * 4;
     dim3 grid((S4 / 4 + 255) / 256, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
@@ -326,13 +325,6 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s) {
                                    c->Gv > 0 ? c->dc_sum : nullptr, c->Gv > 0 ? c->bb : nullptr);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    if (brute) {
-        const int n_elem = S_pad + 2 * c->H;
-        dim3 g2((n_elem / 2 + 255) / 256, c->epoch_C, 8);
-        k_sample_planes<<<g2, 256, 0, s>>>(c->xw, c->ep, S, n_elem, c->H, c->bx, c->bx_stride);
-        c->launches++;
-        DPE_CUDA(cudaGetLastError());
-    }
     prof_end(c, s);
     return DPE_OK;
 }
@@ -353,14 +345,23 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
                                        c->no_flip);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    if (c->cfg.flags & DPE_FLAG_BRUTE_TILES) {
-        dim3 g2(((int)c->S_pad / 2 + 255) / 256, c->epoch_C);
-        k_replica_rd<<<g2, 256, 0, s>>>(c->rs, c->idx_next, c->no_flip, c->ep, S, (int)c->S_pad, c->brd,
-                                        c->brd_stride);
-        c->launches++;
-        DPE_CUDA(cudaGetLastError());
-    }
     prof_end(c, s);
+    return DPE_OK;
+}
+
+// The planes k_brute streams (built on the first brute-force scoring of an epoch, so that a
+// context which only looks up pays nothing for them).
+int launch_brute_planes(dpe_ctx* c, cudaStream_t s) {
+    const int S = (int)c->S, S_pad = (int)c->S_pad;
+    const int n_elem = S_pad + 2 * c->H;
+    dim3 g1((n_elem / 2 + 255) / 256, c->epoch_C, 8);
+    k_sample_planes<<<g1, 256, 0, s>>>(c->xw, c->ep, S, n_elem, c->H, c->bx, c->bx_stride);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    dim3 g2((S_pad / 2 + 255) / 256, c->epoch_C);
+    k_replica_rd<<<g2, 256, 0, s>>>(c->rs, c->idx_next, c->no_flip, c->ep, S, S_pad, c->brd, c->brd_stride);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
     return DPE_OK;
 }
 
