@@ -294,7 +294,7 @@ def run_ours(args):
         achieved = flop / (k_ms * 1e-3) / 1e12
         roofline = dict(bound="fp32", kernel="k_brute", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
                         frac=achieved / fp32_peak, traffic=None,
-                        peak_source="FFMA2 micro-benchmark in this run (dpe_microbench_fp32); nominal "
+                        peak_source="FFMA2 issue-limit micro-benchmark in this run (dpe_microbench_fp32: scalar multiplier, shared pair); nominal "
                                     "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                         algorithmic="6 FLOP x S x valid (candidate,PRN) pairs per launch",
                         kernel_ms=k_ms, kernel_share=stage_ms[capi.STAGE_BRUTE_CORR] / max(stage_ms.sum(), 1e-9))
