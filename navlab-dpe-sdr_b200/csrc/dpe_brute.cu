@@ -268,7 +268,6 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * kBfStages];  // full[s] = bars[s], empty[s] = bars[stages + s]
-    __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int stage_f = 2 * kXTileF;                   // floats per stage: sample tile, replica tile
     static_assert((kBfStages & (kBfStages - 1)) == 0 && (kBfWarps & (kBfWarps - 1)) == 0, "powers of two");
@@ -280,39 +279,34 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
     }
     __syncthreads();
 
-    // Work decomposition.  Whole rounds of gridDim.x slots run one slot per CTA.  The R < gridDim.x
-    // slots left over would cost a full wave for a fraction of the SMs (8 GPUs, demo: 10.3 waves
-    // -> 11), so each of them is split over P = gridDim.x / R CTAs by sample range; the CTA that
-    // takes the slot's last ticket adds the P partial sums in part order (deterministic).
+    // Work decomposition: the CTA's share of the tile sequence of all slots (slot-major), cut at tile
+    // granularity so that every CTA streams the same number of tiles +-1 whatever the slot count
+    // (8 GPUs, demo: 10.3 waves of whole slots would cost 11).  A slot cut by a CTA boundary is summed in
+    // parts: every contributing warp stores its partial sums and takes a ticket, the last one adds the
+    // parts in CTA order (deterministic).
     const int n_slots = *n_groups / kBfWarps;
     const int ntiles = S_pad / kBfTile;
-    const int rounds = n_slots / (int)gridDim.x;
-    const int n_full = rounds * (int)gridDim.x;
-    const int R = n_slots - n_full;
-    int P = R ? (int)gridDim.x / R : 0;
-    if (P > kBfMaxParts) P = kBfMaxParts;
-    if (P > ntiles) P = ntiles;
-    const bool has_tail = (int)blockIdx.x < R * P;
-    const int tail_idx = has_tail ? (int)blockIdx.x / P : 0, part = has_tail ? (int)blockIdx.x % P : 0;
-    const int tail_t0 = has_tail ? part * ntiles / P : 0, tail_t1 = has_tail ? (part + 1) * ntiles / P : 0;
-    const int n_items = rounds + (has_tail ? 1 : 0);
+    const int64_t U = (int64_t)n_slots * ntiles;             // tiles of the whole launch
+    const int n_cta = (int)(U < (int64_t)gridDim.x ? U : (int64_t)gridDim.x);   // CTAs that get work
+    auto cta_begin = [&](int i) -> int64_t { return U * i / n_cta; };
+    auto cta_of = [&](int64_t u) -> int {                    // the CTA whose share holds tile u
+        int i = (int)(u * n_cta / U);
+        while (cta_begin(i + 1) <= u) ++i;
+        while (cta_begin(i) > u) --i;
+        return i;
+    };
+    const bool working = (int)blockIdx.x < n_cta;
+    const int64_t u0 = working ? cta_begin(blockIdx.x) : 0, u1 = working ? cta_begin(blockIdx.x + 1) : 0;
+    const uint32_t my_tiles = (uint32_t)(u1 - u0);            // tiles this CTA streams, 0..my_tiles-1
     uint32_t it = 0;                                       // running tile counter (same on all warps)
 
-    // TMA producer duty (one elected lane): stream the tile `ahead` tiles after tile (item, off) of this
-    // CTA's sequence into stage `stg`.  There is no dedicated producer warp: 9 warps would put 3 on one
-    // scheduler and cap the kernel at 168 registers per thread (16K registers per SM sub-partition);
-    // the duty rotates over the 8 warps.
-    auto issue_tile = [&](int item, int off, int ahead, uint32_t stg) {
-        off += ahead;
-        for (;;) {                                           // usually no iteration: same slot
-            if (item >= n_items) return;
-            const int len = (item == rounds) ? tail_t1 - tail_t0 : ntiles;
-            if (off < len) break;
-            off -= len; ++item;
-        }
-        const bool tail = item == rounds;
-        const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + item * (int)gridDim.x;
-        const int t = (tail ? tail_t0 : 0) + off;
+    // TMA producer duty (one elected lane): stream tile `jt` of this CTA's share into stage `stg`.
+    // There is no dedicated producer warp: 9 warps would put 3 on one scheduler and cap the kernel at
+    // 168 registers per thread (16K registers per SM sub-partition); the duty rotates over the 8 warps.
+    auto issue_tile = [&](uint32_t jt, uint32_t stg) {
+        if (jt >= my_tiles) return;
+        const int64_t u = u0 + jt;
+        const int slot = (int)(u / ntiles), t = (int)(u - (int64_t)slot * ntiles);
         const int4 h = hdr[(size_t)slot * kBfWarps];         // one PRN and one lag per slot
         const int c = h.x, k = h.y - W;
         const int ks = k & 7, kq = (k - ks) / 8;             // k = 8 kq + ks, ks in 0..7
@@ -323,16 +317,17 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         tma_load_1d_u(dst + bytes, brd + c * brd_stride + (size_t)t * kXTileF, bytes, bar);
     };
     if (threadIdx.x == 0)
-        for (int j = 0; j < kBfStages - kBfLag; ++j) issue_tile(0, 0, j, (uint32_t)j);   // prologue
+        for (uint32_t j = 0; j < kBfStages - kBfLag; ++j) issue_tile(j, j);   // prologue
 
     // ===== consumer warps =====
     const float4* const px0 = reinterpret_cast<const float4*>(smem) + 5 * lane;   // lane's run in stage 0 (skewX)
     const float4* px = px0;
     uint32_t stg = 0, par = 0;                             // stage and full-barrier parity of tile `it`
-    for (int item = 0; item < n_items; ++item) {
-        const bool tail = item == rounds;
-        const int slot = tail ? n_full + tail_idx : (int)blockIdx.x + item * (int)gridDim.x;
-        const int t_begin = tail ? tail_t0 : 0, t_end = tail ? tail_t1 : ntiles;
+    for (int64_t u = u0; u < u1;) {
+        const int slot = (int)(u / ntiles);
+        const int t_begin = (int)(u - (int64_t)slot * ntiles);
+        const int t_end = (u1 - u < (int64_t)(ntiles - t_begin)) ? t_begin + (int)(u1 - u) : ntiles;
+        u += t_end - t_begin;
         const int g = slot * kBfWarps + warp;
         const int4 h = hdr[g];
         const int c = h.x, n_valid = h.z;
@@ -365,7 +360,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
             if (warp == (int)(it & (kBfWarps - 1))) {
                 const uint32_t rs = (it - kBfLag) & (kBfStages - 1);
                 if (it >= kBfLag) mbar_wait_u(empty0 + 8 * rs, ((it - kBfLag) / kBfStages) & 1);
-                if (lane == 0) issue_tile(item, t - t_begin, kBfStages - kBfLag, rs);
+                if (lane == 0) issue_tile(it + kBfStages - kBfLag, rs);
                 __syncwarp();
             }
             ++it;
@@ -388,36 +383,39 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
                 acc[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, o);
             }
         }
-        if (tail && P > 1) {
-            tail_part[((size_t)tail_idx * P + part) * (kBfWarps * kBfNC) + threadIdx.x] = acc[0];
-        } else if (lane < n_valid) {
-            const int64_t j = ent_j[(size_t)g * kBfNC + lane];
-            pair_v[(size_t)c * G + j] = make_double2((double)acc[0].x, (double)acc[0].y);
-        }
-    }
-
-    // split tail slot: the last of its P CTAs combines the parts
-    if (has_tail && P > 1) {
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int tk = atomicAdd(&tail_ticket[tail_idx], 1u);
-            s_last = (tk == (unsigned int)P - 1u);
-            if (s_last) tail_ticket[tail_idx] = 0u;            // self-resetting for the next launch
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            const int g = (n_full + tail_idx) * kBfWarps + warp;
-            const int4 h = hdr[g];
-            if (lane < h.z) {
-                float2 v = __ldcg(&tail_part[(size_t)tail_idx * P * (kBfWarps * kBfNC) + threadIdx.x]);
-                for (int q = 1; q < P; ++q) {
-                    const float2 u = __ldcg(&tail_part[((size_t)tail_idx * P + q) * (kBfWarps * kBfNC) + threadIdx.x]);
-                    v.x += u.x; v.y += u.y;
-                }
+        if (t_begin == 0 && t_end == ntiles) {             // the whole slot was mine
+            if (lane < n_valid) {
                 const int64_t j = ent_j[(size_t)g * kBfNC + lane];
-                pair_v[(size_t)h.x * G + j] = make_double2((double)v.x, (double)v.y);
+                pair_v[(size_t)c * G + j] = make_double2((double)acc[0].x, (double)acc[0].y);
+            }
+        } else {
+            // part of a slot that a CTA boundary cuts.  Buffer 0 of a CTA holds the slot that began before
+            // its share, buffer 1 the slot that continues after it.
+            const int64_t s0 = (int64_t)slot * ntiles;
+            const int i_first = cta_of(s0), i_last = cta_of(s0 + ntiles - 1);
+            constexpr int kPart = kBfWarps * kBfNC;
+            tail_part[((size_t)blockIdx.x * 2 + (t_begin != 0 ? 0 : 1)) * kPart + threadIdx.x] = acc[0];
+            __threadfence();
+            __syncwarp();
+            unsigned int tk = 0;
+            if (lane == 0) {
+                unsigned int* ticket = &tail_ticket[i_first * kBfWarps + warp];
+                tk = atomicAdd(ticket, 1u);
+                if (tk == (unsigned int)(i_last - i_first)) *ticket = 0u;     // self-resetting for the next launch
+            }
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            if (tk == (unsigned int)(i_last - i_first)) {    // last part in: add all of them in CTA order
+                __threadfence();
+                float2 v = make_float2(0.f, 0.f);
+                for (int i = i_first; i <= i_last; ++i) {
+                    const int buf = (cta_begin(i) > s0) ? 0 : 1;
+                    const float2 w = __ldcg(&tail_part[((size_t)i * 2 + buf) * kPart + threadIdx.x]);
+                    v.x += w.x; v.y += w.y;
+                }
+                if (lane < n_valid) {
+                    const int64_t j = ent_j[(size_t)g * kBfNC + lane];
+                    pair_v[(size_t)c * G + j] = make_double2((double)v.x, (double)v.y);
+                }
             }
         }
     }

@@ -150,8 +150,8 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->ent_j, c->max_groups * kBfNC);
         DPE_ALLOC(c->ent_a, c->max_groups * kBfNC);
         DPE_ALLOC(c->n_groups, 1);
-        DPE_ALLOC(c->tail_part, (size_t)c->sm_count * kBfWarps * kBfNC);
-        DPE_ALLOC(c->tail_ticket, c->sm_count);
+        DPE_ALLOC(c->tail_part, (size_t)c->sm_count * 2 * kBfWarps * kBfNC);
+        DPE_ALLOC(c->tail_ticket, c->sm_count * kBfWarps);
     }
     if (cfg->Gv > 0) {
         DPE_REQUIRE(cfg->Gv < (1ll << 31), DPE_EINVAL, "Gv out of range");

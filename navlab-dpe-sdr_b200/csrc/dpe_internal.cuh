@@ -50,7 +50,6 @@ constexpr int kBfTile = 1024;          // samples per TMA stage
 constexpr int kBfWarps = 8;            // consumer warps per CTA
 constexpr int kBfStages = 4;            // TMA stages of 20 KB (sample tile + replica tile)
 constexpr int kBfLag = 1;               // a stage is refilled this many tiles after its release (8 / 4: no gain)
-constexpr int kBfMaxParts = 8;          // sample-range parts a left-over slot is split into
 
 // Device copy of the per-epoch parameters (+ values derived on the device).
 struct EpochDev {
@@ -102,8 +101,8 @@ struct dpe_ctx {
     int32_t* ent_j; float* ent_a;      // bucketed entries
     int32_t* n_groups;                 // device scalar: total groups (multiple of kBfWarps)
     int64_t max_groups;
-    float2* tail_part;                 // [sm_count][kBfWarps * kBfNC] partial sums of split tail slots
-    unsigned int* tail_ticket;         // [sm_count] arrivals per split slot (self-resetting)
+    float2* tail_part;                 // [sm_count][2][kBfWarps * kBfNC] partial sums of the slots a CTA boundary cuts
+    unsigned int* tail_ticket;         // [sm_count][kBfWarps] arrivals per cut slot and warp (self-resetting)
     // debug
     int64_t* dbg_f; double* dbg_alpha;
     // velocity (section 8 f-1)

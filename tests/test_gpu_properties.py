@@ -53,8 +53,8 @@ def test_full_demo_grid_brute_force_equals_lookup(capi):
 def test_sharded_contexts_reproduce_the_single_context_result(capi, mode):
     """3 contexts holding contiguous shards (what 3 ranks would hold) + dpe_estimate on the gathered
     partials == one context holding the whole grid: bit for bit on the lookup path; on the
-    brute-force path to FP32 summation order (the slots left over after whole waves are split by
-    sample range, and which pairs they hold depends on the shard), with the same arg-max."""
+    brute-force path to FP32 summation order (a slot that a CTA boundary of k_brute's tile-granular work
+    split cuts is summed in parts, and which pairs it holds depends on the shard), with the same arg-max."""
     import dpe_pkg
     import torch
     sharding = dpe_pkg.submodule("sharding")
@@ -129,11 +129,11 @@ def test_channel_order_does_not_matter(capi):
     ctx.close()
 
 
-@pytest.mark.parametrize("n_cand", [4700, 5100, 6000, 6561])
+@pytest.mark.parametrize("n_cand", [40, 700, 4700, 5100, 6000, 6561])
 def test_brute_force_split_tail_slots(capi, n_cand):
-    """Slots left over after whole waves of 148 are split over several CTAs by sample range
-    (k_brute, 2 to 8 parts depending on how many are left): same scores as the lookup path and as
-    the oracle, identical bits from run to run (the parts are added in a fixed order)."""
+    """k_brute cuts the tile sequence of all slots into equal shares per CTA, so slots straddling a CTA
+    boundary are summed in parts (more parts the fewer slots there are): same scores as the lookup path
+    and as the oracle, identical bits from run to run (the parts are added in a fixed order)."""
     sc, iq, grid, ep = H.epoch_case(n=9, center_offset=(6.0, -4.0, 3.0, 7.0))
     g = np.ascontiguousarray(grid[:n_cand])
     ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=n_cand, time_dim=ep["time_dim"], lag_halfwidth=16,
