@@ -103,29 +103,37 @@ __global__ void __launch_bounds__(256)
 k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep, int W,
               int32_t* __restrict__ group_base, int64_t* __restrict__ bucket_base,
               int32_t* __restrict__ n_groups, int64_t max_groups) {
-    extern __shared__ int32_t sm[];        // [nbuck] counts, then [nbuck+1] group bases
+    __shared__ int32_t wsum[8];
     const int NB = 2 * W + 1;
-    const int C = ep->C;
-    const int nbuck = C * NB;
-    int32_t* cnt = sm;
-    int32_t* gb = sm + nbuck;
-    for (int i = threadIdx.x; i < nbuck; i += blockDim.x) cnt[i] = hist[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int32_t g = 0;
-        for (int c = 0; c < C; ++c) {
-            for (int b = 0; b < NB; ++b) {
-                gb[c * NB + b] = g;
-                g += (cnt[c * NB + b] + kBfNC - 1) / kBfNC;
-                g = ((g + kBfWarps - 1) / kBfWarps) * kBfWarps;
-            }
-        }
-        gb[nbuck] = g;
-        *n_groups = (g <= max_groups) ? g : 0;
+    const int nbuck = ep->C * NB;
+    const int per = (nbuck + 255) / 256;                   // consecutive buckets per thread
+    const int b0 = threadIdx.x * per, b1 = min(b0 + per, nbuck);
+    auto groups_of = [&](int i) {                          // whole groups, rounded up to whole slots
+        const int g = (hist[i] + kBfNC - 1) / kBfNC;
+        return ((g + kBfWarps - 1) / kBfWarps) * kBfWarps;
+    };
+    int32_t mine = 0;
+    for (int i = b0; i < b1; ++i) mine += groups_of(i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
     }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    for (int i = threadIdx.x; i <= nbuck; i += blockDim.x) group_base[i] = gb[i];
-    for (int i = threadIdx.x; i < nbuck; i += blockDim.x) bucket_base[i] = (int64_t)gb[i] * kBfNC;
+    int32_t base = incl - mine;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    for (int i = b0; i < b1; ++i) {
+        group_base[i] = base;
+        bucket_base[i] = (int64_t)base * kBfNC;
+        base += groups_of(i);
+    }
+    if (threadIdx.x == 255) {                              // the last thread ends on the total
+        group_base[nbuck] = base;
+        *n_groups = (base <= max_groups) ? base : 0;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -474,8 +482,8 @@ int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     k_block_scan<<<nbuck, 256, 0, s>>>(c->blk_hist, nblk, c->hist);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    k_bucket_scan<<<1, 256, sizeof(int32_t) * (2 * nbuck + 1), s>>>(c->hist, c->ep, c->W, c->group_base,
-                                                                  c->bucket_base, c->n_groups, c->max_groups);
+    k_bucket_scan<<<1, 256, 0, s>>>(c->hist, c->ep, c->W, c->group_base, c->bucket_base, c->n_groups,
+                                    c->max_groups);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     k_group_headers<<<(int)((c->max_groups + 255) / 256), 256, sizeof(int32_t) * (nbuck + 1), s>>>(
