@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kBfWarps * 32, 1)
 k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         int64_t bx_stride, int64_t brd_stride, const int4* __restrict__ hdr,
         const int32_t* __restrict__ ent_j, const float* __restrict__ ent_a,
-        const int32_t* __restrict__ n_groups, double2* __restrict__ pair_v, int64_t G, int S_pad,
+        const int32_t* __restrict__ n_groups, float2* __restrict__ pair_v, int64_t G, int S_pad,
         int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * kBfStages];  // full[s] = bars[s], empty[s] = bars[stages + s]
@@ -379,7 +379,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         // lane partials -> one candidate per lane: halving butterfly (31 shuffles per component instead of
         // 160): at step o the lanes with bit o set keep the upper half of the candidates, the others the
         // lower half; after 5 steps lane l holds the full sum of candidate l.  FP32 here (32 addends of
-        // equal weight: ~1e-7), FP64 from pair_v on.
+        // equal weight: ~1e-7); the scores are formed in FP64 from these FP32 sums (k_score_pairs).
 #pragma unroll
         for (int o = 16, n = kBfNC / 2; o > 0; o >>= 1, n >>= 1) {
             const bool up = (lane & o) != 0;
@@ -394,7 +394,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         if (t_begin == 0 && t_end == ntiles) {             // the whole slot was mine
             if (lane < n_valid) {
                 const int64_t j = ent_j[(size_t)g * kBfNC + lane];
-                pair_v[(size_t)c * G + j] = make_double2((double)acc[0].x, (double)acc[0].y);
+                pair_v[(size_t)c * G + j] = acc[0];
             }
         } else {
             // part of a slot that a CTA boundary cuts.  Buffer 0 of a CTA holds the slot that began before
@@ -422,7 +422,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
                 }
                 if (lane < n_valid) {
                     const int64_t j = ent_j[(size_t)g * kBfNC + lane];
-                    pair_v[(size_t)c * G + j] = make_double2((double)v.x, (double)v.y);
+                    pair_v[(size_t)c * G + j] = v;
                 }
             }
         }
@@ -432,7 +432,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
 // pass 5: per-candidate score from the pair correlations + fused reductions
 __global__ void __launch_bounds__(kReduceBlock)
 k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
-              const int16_t* __restrict__ pair_k, const double2* __restrict__ pair_v, int lpower,
+              const int16_t* __restrict__ pair_k, const float2* __restrict__ pair_v, int lpower,
               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
               unsigned int* __restrict__ ticket, double* __restrict__ partial) {
     const EpochDev& e = *ep;
@@ -443,13 +443,12 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     Cand p = {0, 0, 0, 0};
     if (active) {
         p = cand_ecef(e, grid + 4 * j);
-        for (int c = 0; c < e.C; ++c) {
-            if (pair_k[(size_t)c * G + j] >= 0) {
-                const double2 v = pair_v[(size_t)c * G + j];
-                score += mag_pow(v.x, v.y, lpower);
-            } else {
-                ++oow;
-            }
+#pragma unroll 4
+        for (int c = 0; c < e.C; ++c) {                    // both loads unconditional: 2 x C independent requests in flight
+            const int k = pair_k[(size_t)c * G + j];
+            const float2 v = pair_v[(size_t)c * G + j];    // never written for an out-of-window pair: not used then
+            if (k >= 0) score += mag_pow((double)v.x, (double)v.y, lpower);
+            else ++oow;
         }
         scores[j] = score;
     }

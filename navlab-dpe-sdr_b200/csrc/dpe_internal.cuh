@@ -17,7 +17,7 @@
 //   cs        double2[C][NL]            fft-shifted "CodeScores" window, lag k = l - W
 //   grid      double [G][4]             candidates (ENU metres + clock metres)
 //   scores    double [G]                "PosScores"
-//   pair_*    per (channel, candidate) lag / alpha / v for the brute-force path
+//   pair_*    per (channel, candidate) lag (int16) / alpha (float) / correlation v (float2) for the brute-force path
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -93,7 +93,7 @@ struct dpe_ctx {
     unsigned int* ticket;              // last-CTA ticket counter of the scoring kernels (self-resetting)
     double* partial; double* zval; double* rval; double* result;  // result: device mirror of dpe_result
     // brute-force work lists
-    int16_t* pair_k; float* pair_a; double2* pair_v;   // [C][G]
+    int16_t* pair_k; float* pair_a; float2* pair_v;    // [C][G]
     int32_t* hist;                     // [C][NB] counts, NB = 2W+1
     int32_t* blk_hist;                 // [C*NB][ceil(G/256)] per-block counts, then exclusive block prefixes
     int64_t* bucket_base; int32_t* group_base;
