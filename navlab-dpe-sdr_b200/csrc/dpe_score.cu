@@ -19,7 +19,7 @@ namespace dpe {
 // state (:1773-1775) or per-time-index state (:865-873).
 // ---------------------------------------------------------------------------
 template <int SAT_MODE>
-__global__ void __launch_bounds__(kReduceBlock)
+__global__ void __launch_bounds__(kReduceBlock, 6)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
                int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
