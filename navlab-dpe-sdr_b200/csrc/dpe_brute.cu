@@ -31,7 +31,7 @@ namespace dpe {
 // ---------------------------------------------------------------------------
 // pass 1: bins of every pair + per-block (PRN, lag) histograms.  The sort below is a stable
 // counting sort (position in the bucket = rank by candidate index), so the composition of every
-// group -- and with it the summation order of the split tail slots -- is the same on every run.
+// group -- and with it the summation order of the slots that a CTA boundary cuts -- is the same on every run.
 // ---------------------------------------------------------------------------
 template <int SAT_MODE>
 __global__ void __launch_bounds__(256)
@@ -194,26 +194,8 @@ __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok) : "r"(s2u(b)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(s2u(dst)), "l"(src), "r"(bytes), "r"(s2u(bar)) : "memory");
-}
-
-// the same on 32-bit shared-window addresses (computed once per kernel: no address arithmetic per tile)
+// barrier and bulk-copy operations on 32-bit shared-window addresses (computed once per kernel: no address
+// arithmetic per tile)
 __device__ __forceinline__ void mbar_expect_tx_u(uint32_t b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
 }
