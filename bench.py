@@ -341,7 +341,10 @@ def run_ours(args):
                             lag_halfwidth=args.lag_halfwidth,
                             sharding=("independent streams, %d per rank, no collective" % n_epochs_rank) if streams
                             else "grid candidates, contiguous index ranges",
-                            l2="flushed (256 MiB memset) between timed iterations"),
+                            l2="flushed (256 MiB memset) between timed iterations",
+                            unit_of_work=("one candidate-PRN pair scored; brute = a full S-sample correlation per pair "
+                                          "(6*S FLOP, the north-star kernel); the reference arm and other_path=lookup "
+                                          "score a pair by interpolating a precomputed correlogram (same result)")),
                 epochs_per_s=1e3 * (streams if streams else 1) / ms_per_step,
                 realtime_factor=(1e3 / ms_per_step) / 50.0,
                 e2e=dict(value=e2e_value, unit="corr/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
