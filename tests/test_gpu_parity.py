@@ -101,7 +101,7 @@ def test_code_phase_bins_bit_exact(capi, sat_mode):
     assert np.max(np.abs(a - (idxo - f_ref))) < 1e-9
 
 
-@pytest.mark.parametrize("lpower", [1, 2])
+@pytest.mark.parametrize("lpower", [1, 2, 3])
 def test_lookup_scores_argmax_and_fix(capi, lpower):
     sc, iq, grid, ep = H.epoch_case(n=9, center_offset=(10.0, -5.0, 5.0, 12.0))
     G = grid.shape[0]
