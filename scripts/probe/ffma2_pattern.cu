@@ -16,10 +16,12 @@ __global__ void __launch_bounds__(256, 1) k_pat(const float* __restrict__ in, fl
     }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        const float eps = __ldcg(in + 4000 + (it & 7));     // 0 at run time, unknown at compile time
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            // make the shared operands loop-variant so nothing is hoisted (2 cheap ops per q)
-            rd[q].x += 1e-9f; x[q].x += 1e-9f;
+            // make every shared operand loop-variant so nothing is hoisted (8 cheap ops per q, all modes alike)
+            rd[q].x += eps; rd[q].y += eps; rd[q].z += eps; rd[q].w += eps;
+            x[q].x += eps; x[q].y += eps; x[q].z += eps; x[q].w += eps;
             const float2 dp = make_float2(rd[q].x, rd[q].y), r0 = make_float2(rd[q].z, rd[q].w);
             const float2 xa = make_float2(x[q].x, x[q].y), xb = make_float2(x[q].z, x[q].w);
             if (ORDER == 0) {                 // as compiled today: per candidate blend + 2 accumulates (compiler reorders)
@@ -28,6 +30,40 @@ __global__ void __launch_bounds__(256, 1) k_pat(const float* __restrict__ in, fl
                     const float2 bp = __ffma2_rn(make_float2(al[j], al[j]), dp, r0);
                     acc[j] = __ffma2_rn(make_float2(bp.x, bp.x), xa, acc[j]);
                     acc[j] = __ffma2_rn(make_float2(bp.y, bp.y), xb, acc[j]);
+                }
+            } else if (ORDER == 2) {          // 3 accumulates, scalar = half of a long-lived register pair
+#pragma unroll
+                for (int j = 0; j < NC; j += 2) {
+                    const float2 a2 = make_float2(al[j], al[j + 1]);
+                    acc[j] = __ffma2_rn(make_float2(a2.x, a2.x), xa, acc[j]);
+                    acc[j] = __ffma2_rn(make_float2(a2.y, a2.y), xb, acc[j]);
+                    acc[j] = __ffma2_rn(make_float2(a2.x, a2.x), dp, acc[j]);
+                    acc[j + 1] = __ffma2_rn(make_float2(a2.y, a2.y), xa, acc[j + 1]);
+                    acc[j + 1] = __ffma2_rn(make_float2(a2.x, a2.x), xb, acc[j + 1]);
+                    acc[j + 1] = __ffma2_rn(make_float2(a2.y, a2.y), dp, acc[j + 1]);
+                }
+            } else if (ORDER == 3) {          // halves of 16: blend 16, accumulate 32, twice
+#pragma unroll
+                for (int h = 0; h < NC; h += 16) {
+                    float2 bp[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) bp[j] = __ffma2_rn(make_float2(al[h + j], al[h + j]), dp, r0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        acc[h + j] = __ffma2_rn(make_float2(bp[j].x, bp[j].x), xa, acc[h + j]);
+                        acc[h + j] = __ffma2_rn(make_float2(bp[j].y, bp[j].y), xb, acc[h + j]);
+                    }
+                }
+            } else if (ORDER == 4) {          // blend by candidate pair: (b_j, b_j+1) for one position, alpha pair long-lived
+#pragma unroll
+                for (int j = 0; j < NC; j += 2) {
+                    const float2 a2 = make_float2(al[j], al[j + 1]);
+                    const float2 b0 = __ffma2_rn(a2, make_float2(dp.x, dp.x), make_float2(r0.x, r0.x));   // position p, candidates j, j+1
+                    const float2 b1 = __ffma2_rn(a2, make_float2(dp.y, dp.y), make_float2(r0.y, r0.y));   // position p+1
+                    acc[j] = __ffma2_rn(make_float2(b0.x, b0.x), xa, acc[j]);
+                    acc[j] = __ffma2_rn(make_float2(b1.x, b1.x), xb, acc[j]);
+                    acc[j + 1] = __ffma2_rn(make_float2(b0.y, b0.y), xa, acc[j + 1]);
+                    acc[j + 1] = __ffma2_rn(make_float2(b1.y, b1.y), xb, acc[j + 1]);
                 }
             } else {                          // accumulate only (the 2.03-cycle pattern), 3 per candidate
 #pragma unroll
@@ -64,10 +100,13 @@ void run(const char* name, const float* in, float* out) {
 
 int main() {
     float *in, *out; cudaMalloc(&in, 4096 * 4); cudaMalloc(&out, 64);
-    float h[4096]; for (int i = 0; i < 4096; ++i) h[i] = 0.5f + 1e-3f * i;
+    float h[4096]; for (int i = 0; i < 4096; ++i) h[i] = (i >= 4000) ? 0.f : 0.5f + 1e-3f * i;
     cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
     run<32, 0>("blend + 2 accumulates (k_brute pattern)", in, out);
     run<32, 1>("3 accumulates", in, out);
+    run<32, 2>("3 accumulates, scalar from a pair half", in, out);
+    run<32, 3>("blend 16 / accumulate 32, twice", in, out);
+    run<32, 4>("blend by candidate pair", in, out);
     run<16, 0>("blend + 2 accumulates", in, out);
     run<16, 1>("3 accumulates", in, out);
     run<24, 0>("blend + 2 accumulates", in, out);
