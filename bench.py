@@ -152,6 +152,7 @@ def run_ours(args):
     ep_structs = [capi.make_epoch(e) for e in epochs]
     sats = [np.ascontiguousarray(e["sat_states"]) for e in epochs]
     stream = torch.cuda.current_stream().cuda_stream
+    aux = torch.cuda.Stream(device=dev)                            # the pair sort runs beside the sample pre-pass
     gathered = torch.zeros(world * capi.DPE_PARTIAL_LEN, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     recv = torch.empty(2 * S, dtype=torch.int16, device=dev)
@@ -162,6 +163,8 @@ def run_ours(args):
             return ctx.epoch_run(blocks_host[b], ep_structs[b], sats[b], score_mode, est_mode, 0, stream)
         ctx.block_stage(blocks_dev[b], stream)
         ctx.epoch_set(ep_structs[b], sats[b], stream)
+        if score_mode == capi.SCORE_BRUTE:
+            ctx.brute_presort(sat_mode, aux.cuda_stream)
         ctx.replica_prepare(stream)
         ctx.correlogram(stream)
         ctx.score_pos(score_mode, sat_mode, stream)
@@ -181,6 +184,8 @@ def run_ours(args):
         else:
             ctx.block_stage(blocks_dev[b], stream)
         ctx.epoch_set(ep_structs[b], sats[b], stream)
+        if score_mode == capi.SCORE_BRUTE:
+            ctx.brute_presort(sat_mode, aux.cuda_stream)
         ctx.replica_prepare(stream)
         ctx.correlogram(stream)
         ctx.score_pos(score_mode, sat_mode, stream)
@@ -204,6 +209,8 @@ def run_ours(args):
             dist.broadcast(recv_u8, 0)
             ctx.block_stage(recv, stream)
             ctx.epoch_set(ep_structs[b], sats[b], stream)
+            if score_mode == capi.SCORE_BRUTE:
+                ctx.brute_presort(sat_mode, aux.cuda_stream)
             ctx.replica_prepare(stream)
             ctx.correlogram(stream)
             ctx.score_pos(score_mode, sat_mode, stream)

@@ -198,8 +198,8 @@ int dpe_replica_prepare(dpe_ctx* ctx, void* stream);
 /* dpe_correlogram: finish the circular code correlogram on lags -W..W+1, choose
  * flip / no-flip per channel, write the fft-shifted "CodeScores" rows.  Replaces
  * the cuFFT chain + BCS_ChooseCodeCorr + BCS_cufftBatchShift
- * (batchcorrscores.cu:1099-1153).  Also emits the brute-force replica tiles when
- * DPE_FLAG_BRUTE_TILES is set.                                                   */
+ * (batchcorrscores.cu:1099-1153).  (The planes the brute-force kernel streams are
+ * built by the first dpe_score_pos(DPE_SCORE_BRUTE) of the epoch.)                */
 int dpe_correlogram(dpe_ctx* ctx, void* stream);
 
 /* dpe_code_scores_set: use a correlogram produced elsewhere (e.g. the reference's own
@@ -217,6 +217,15 @@ int dpe_code_scores_set(dpe_ctx* ctx, const double* cs, int C, void* stream);
  *   partial[7] = out-of-window pair count
  *   partial[8..11] = ECEF x,y,z and clock (m) of this rank's arg-max candidate     */
 int dpe_score_pos(dpe_ctx* ctx, int score_mode, int sat_mode, void* stream);
+
+/* dpe_brute_presort (optional): bin and sort the (candidate, PRN) pairs of the current
+ * epoch for DPE_SCORE_BRUTE ahead of time -- typically on a second stream, while
+ * dpe_replica_prepare / dpe_correlogram run on the first: the sort needs dpe_epoch_set
+ * only, not the samples.  Ordering is handled inside: the sort waits for the epoch
+ * upload, dpe_score_pos(DPE_SCORE_BRUTE) with the same sat_mode waits for the sort and
+ * skips its own, and the next dpe_epoch_set waits for it before it overwrites the
+ * parameters.  dpe_epoch_run does this by itself on an internal stream.           */
+int dpe_brute_presort(dpe_ctx* ctx, int sat_mode, void* stream);
 
 /* dpe_estimate: turn partial(s) into zVal[0:4] / RVal rows 0-3.  `gathered` is
  * either NULL (single GPU: use this context's own partial) or a DEVICE pointer

@@ -34,7 +34,7 @@ EXPORTS = (
     "dpe_ctx_create", "dpe_ctx_destroy", "dpe_last_error", "dpe_abi_version", "dpe_grid_set",
     "dpe_vel_grid_set", "dpe_block_stage", "dpe_epoch_set", "dpe_epoch_set_part", "dpe_replica_prepare", "dpe_correlogram",
     "dpe_code_scores_set",
-    "dpe_score_pos", "dpe_estimate", "dpe_score_vel", "dpe_result_fetch", "dpe_epoch_run", "dpe_dev_ptr",
+    "dpe_score_pos", "dpe_brute_presort", "dpe_estimate", "dpe_score_vel", "dpe_result_fetch", "dpe_epoch_run", "dpe_dev_ptr",
     "dpe_debug_channel_flags", "dpe_debug_bins", "dpe_debug_read", "dpe_launch_count", "dpe_profile_enable", "dpe_profile_read",
     "dpe_brute_pairs", "dpe_stream_create", "dpe_stream_destroy", "dpe_stream_sync", "dpe_host_alloc",
     "dpe_host_free", "dpe_device_count", "dpe_microbench_fp32",
@@ -97,6 +97,7 @@ def load_library(path: str | None = None):
     lib.dpe_correlogram.argtypes = [vp, vp]
     lib.dpe_code_scores_set.argtypes = [vp, vp, i32, vp]
     lib.dpe_score_pos.argtypes = [vp, i32, i32, vp]
+    lib.dpe_brute_presort.argtypes = [vp, i32, vp]
     lib.dpe_estimate.argtypes = [vp, i32, vp, i32, vp]
     lib.dpe_score_vel.argtypes = [vp, vp]
     lib.dpe_result_fetch.argtypes = [vp, C.POINTER(DpeResult), vp]
@@ -238,6 +239,10 @@ class Context:
 
     def score_pos(self, score_mode=SCORE_LOOKUP, sat_mode=SAT_MIDDLE, stream=0):
         _check(self.lib, self.lib.dpe_score_pos(self.h, score_mode, sat_mode, C.c_void_p(stream)))
+
+    def brute_presort(self, sat_mode=SAT_MIDDLE, stream=0):
+        """Sort the pairs for SCORE_BRUTE ahead of time (e.g. on a second stream beside the pre-pass)."""
+        _check(self.lib, self.lib.dpe_brute_presort(self.h, sat_mode, C.c_void_p(stream)))
 
     def estimate(self, est_mode=EST_ARGMAX, gathered=None, nranks=1, stream=0):
         _check(self.lib, self.lib.dpe_estimate(self.h, est_mode, _ptr(gathered), nranks, C.c_void_p(stream)))

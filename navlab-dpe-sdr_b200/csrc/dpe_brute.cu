@@ -442,14 +442,11 @@ size_t brute_smem_bytes(int) {
     return (size_t)kBfStages * 2 * kXTileF * sizeof(float);
 }
 
-int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
+// bins + stable counting sort of the pairs into (PRN, lag) buckets / groups / slots; needs the epoch
+// parameters only (dpe_brute_presort may run it on another stream than the sample pre-pass)
+int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int C = c->epoch_C, NB = 2 * c->W + 1, nbuck = C * NB;
     prof_begin(c, DPE_STAGE_BRUTE_BINS, s);
-    if (!c->have_planes) {
-        int rc = launch_brute_planes(c, s);
-        if (rc) return rc;
-        c->have_planes = 1;
-    }
     const int nblk = (int)((c->G + 255) / 256);
     const size_t hs_bytes = sizeof(int32_t) * nbuck;
     if (sat_mode == DPE_SAT_PER_TIME)
@@ -481,8 +478,19 @@ int launch_brute_passes(dpe_ctx* c, int sat_mode, cudaStream_t s) {
 }
 
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
-    int rc = launch_brute_passes(c, sat_mode, s);
-    if (rc) return rc;
+    int rc;
+    if (!c->have_planes) {
+        if ((rc = launch_brute_planes(c, s))) return rc;
+        c->have_planes = 1;
+    }
+    if (c->sort_valid == 1 + sat_mode) {                   // presorted (maybe on another stream), or sorted earlier this epoch
+        if (c->sort_pending) DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
+        c->sort_pending = 0;
+    } else {
+        if (c->sort_pending) { DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0)); c->sort_pending = 0; }
+        if ((rc = launch_brute_sort(c, sat_mode, s))) return rc;
+        c->sort_valid = 1 + sat_mode;
+    }
     const size_t smem = brute_smem_bytes(c->H);
     if (!c->brute_attr_set) {          // per context: the attribute belongs to the device the context lives on
         DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -175,6 +175,8 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->ep_pin), sizeof(EpochDev) * kPinSlots));
     DPE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->sat_pin), sizeof(double) * c->sat_cap * kPinSlots));
     for (int i = 0; i < kPinSlots; ++i) DPE_CUDA(cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
+    DPE_CUDA(cudaEventCreateWithFlags(&c->ev_epoch, cudaEventDisableTiming));
+    DPE_CUDA(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
     if (rc) { dpe_ctx_destroy(c); return rc; }
@@ -203,6 +205,9 @@ int dpe_ctx_destroy(dpe_ctx* c) {
         cudaFreeHost(c->sat_pin);
         for (int i = 0; i < kPinSlots; ++i) cudaEventDestroy(c->pin_ev[i]);
     }
+    if (c->ev_epoch) cudaEventDestroy(c->ev_epoch);
+    if (c->ev_sort) cudaEventDestroy(c->ev_sort);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->prof_ev) {
         for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
@@ -284,6 +289,11 @@ int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states
         }
     }
     cudaStream_t s = (cudaStream_t)stream;
+    if (c->sort_pending) {                         // a presort on another stream still reads the old parameters
+        DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
+        c->sort_pending = 0;
+    }
+    c->sort_valid = 0;
     // stage through a page-locked ring slot: truly asynchronous, and the caller may reuse its arrays at once
     const int slot = c->pin_next;
     c->pin_next = (slot + 1) % kPinSlots;
@@ -304,6 +314,7 @@ int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states
         }
     }
     DPE_CUDA(cudaEventRecord(c->pin_ev[slot], s));
+    DPE_CUDA(cudaEventRecord(c->ev_epoch, s));
     c->epoch_C = ep->C;
     c->have_epoch |= (int)parts;
     if (parts & DPE_PART_CHANNELS) c->have_prepare = c->have_corr = 0;
@@ -372,6 +383,23 @@ int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
     return DPE_OK;
 }
 
+int dpe_brute_presort(dpe_ctx* c, int sat_mode, void* stream) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(c->cfg.flags & DPE_FLAG_BRUTE_TILES, DPE_ESTATE, "context created without DPE_FLAG_BRUTE_TILES");
+    DPE_REQUIRE((c->have_epoch & (DPE_PART_CHANNELS | DPE_PART_GEOMETRY)) == (DPE_PART_CHANNELS | DPE_PART_GEOMETRY),
+                DPE_ESTATE, "brute_presort before both parts of epoch_set");
+    DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
+    cudaStream_t s = (cudaStream_t)stream;
+    DPE_CUDA(cudaStreamWaitEvent(s, c->ev_epoch, 0));          // the parameters this epoch's upload put in place
+    if (c->sort_pending) DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
+    int rc = launch_brute_sort(c, sat_mode, s);
+    if (rc) return rc;
+    DPE_CUDA(cudaEventRecord(c->ev_sort, s));
+    c->sort_valid = 1 + sat_mode;
+    c->sort_pending = 1;
+    return DPE_OK;
+}
+
 int dpe_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
     DPE_REQUIRE(c->have_scores, DPE_ESTATE, "estimate before score_pos");
@@ -410,9 +438,14 @@ int dpe_epoch_run(dpe_ctx* c, const int16_t* iq_host, const dpe_epoch* ep, const
     int rc;
     if ((rc = dpe_block_stage(c, iq_host, c ? c->S : 0, stream))) return rc;
     if ((rc = dpe_epoch_set(c, ep, sat_states, stream))) return rc;
+    const int sat_mode = (est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
+    if (score_mode == DPE_SCORE_BRUTE && (c->cfg.flags & DPE_FLAG_BRUTE_TILES)) {
+        // the pair sort needs the parameters only: run it beside the sample pre-pass
+        if (!c->aux_stream) DPE_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        if ((rc = dpe_brute_presort(c, sat_mode, c->aux_stream))) return rc;
+    }
     if ((rc = dpe_replica_prepare(c, stream))) return rc;
     if ((rc = dpe_correlogram(c, stream))) return rc;
-    const int sat_mode = (est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
     if ((rc = dpe_score_pos(c, score_mode, sat_mode, stream))) return rc;
     if ((rc = dpe_estimate(c, est_mode, nullptr, 1, stream))) return rc;
     if (with_vel && (rc = dpe_score_vel(c, stream))) return rc;

@@ -114,6 +114,10 @@ struct dpe_ctx {
     int epoch_C;
     int brute_attr_set;
     int have_planes;                   // brute-force planes match the current prepare + correlogram
+    int sort_valid;                    // 0, or 1 + sat_mode the brute-force work lists were built for (this epoch)
+    int sort_pending;                  // a presort on another stream has not been waited for yet
+    cudaEvent_t ev_epoch, ev_sort;     // epoch upload done / presort done
+    cudaStream_t aux_stream;           // dpe_epoch_run's own presort stream (created on first use)
     int64_t launches;
     dpe::EpochDev ep_host;
     // page-locked staging ring for the per-epoch uploads (no implicit stream sync, safe reuse)
@@ -147,6 +151,7 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_brute_planes(dpe_ctx* c, cudaStream_t s);
+int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_vel(dpe_ctx* c, cudaStream_t s);
 int launch_dc_sum(dpe_ctx* c, cudaStream_t s);
 size_t brute_smem_bytes(int H);

@@ -182,6 +182,43 @@ def test_brute_force_ragged_groups_and_flipped_channels(capi):
     assert np.max(np.abs(scores - ref["scores"]) / ref["scores"]) < SCORE_RTOL
 
 
+def test_brute_presort_on_a_second_stream_changes_nothing(capi):
+    """dpe_brute_presort (the pair sort run ahead of time, beside the sample pre-pass): same bits as the
+    in-line sort; a new epoch_set invalidates it; a presort for the other sat_mode is not used."""
+    import torch
+    sc, iq, grid, ep = H.epoch_case(n=7, center_offset=(3.0, 2.0, -1.0, 4.0))
+    G = grid.shape[0]
+    ctx = _ctx(capi, ep["S"], sc.C, G, ep["time_dim"], ep["fs"], flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    aux = torch.cuda.Stream()
+
+    def run(presort_mode):
+        e = capi.make_epoch(ep)
+        ctx.block_stage(iq)
+        ctx.epoch_set(e, np.ascontiguousarray(ep["sat_states"]))
+        if presort_mode is not None:
+            ctx.brute_presort(presort_mode, aux.cuda_stream)
+        ctx.replica_prepare()
+        ctx.correlogram()
+        ctx.score_pos(capi.SCORE_BRUTE, capi.SAT_MIDDLE)
+        ctx.estimate(capi.EST_ARGMAX)
+        r = ctx.result_fetch()
+        return r, ctx.copy_out(capi.PTR_POS_SCORES, np.float64, G)
+
+    r0, s0 = run(None)
+    r1, s1 = run(capi.SAT_MIDDLE)
+    r2, s2 = run(capi.SAT_PER_TIME)            # wrong mode presorted: score_pos sorts again for SAT_MIDDLE
+    assert np.array_equal(s0, s1) and np.array_equal(s0, s2)
+    assert r0.argmax == r1.argmax == r2.argmax
+    with pytest.raises(capi.DpeError):
+        lookup_only = _ctx(capi, ep["S"], sc.C, G, ep["time_dim"], ep["fs"])
+        try:
+            lookup_only.brute_presort(capi.SAT_MIDDLE)
+        finally:
+            lookup_only.close()
+    ctx.close()
+
+
 def test_out_of_window_candidates_are_counted_not_scored(capi):
     sc, iq, grid, ep = H.epoch_case(n=3, spacing=(400.0, 400.0, 400.0, 400.0))
     G, C = grid.shape[0], 8
