@@ -45,6 +45,9 @@ def main():
     ap.add_argument("--W", type=int, default=32)
     ap.add_argument("--ekf", action="store_true", help="enable the reference's 8-state KF (cuEKF EnableEKF=true); "
                     "writes only the per-epoch states (ref_ekf_n<N>.npz)")
+    ap.add_argument("--gen-grid", type=int, default=-1, help="let the reference GENERATE its position grid "
+                    "(LoadPosGrid=false): ManifoldGridTypes value, 0 Uniform / 2 ArthurBasis; writes ref_grid_t<T>_n<N>.npz")
+    ap.add_argument("--spacing", type=float, default=2.0, help="GridDimSpacing for --gen-grid (all 8 dimensions)")
     ap.add_argument("--offset", type=float, nargs=4, default=[7.0, -4.0, 3.0, 8.0],
                     help="ECEF x,y,z and clock (m) offset of the handed-off state from the truth")
     a = ap.parse_args()
@@ -70,8 +73,10 @@ def main():
     open(files["handoff"], "w").write("\n".join(lines) + "\n")
 
     dump = os.path.join(a.work, "dump")
-    cmd = [exe, files["dat"], files["handoff"], files["rinex"], files["grid"], str(a.n), "5", str(a.epochs), dump,
-           str(a.W), repr(sc.cfg.fs), "1", "1" if a.ekf else "0"]
+    cmd = [exe, files["dat"], files["handoff"], files["rinex"], files["grid"] if a.gen_grid < 0 else "none", str(a.n), "5",
+           str(a.epochs), dump, str(a.W), repr(sc.cfg.fs), "1", "1" if a.ekf else "0"]
+    if a.gen_grid >= 0:
+        cmd += [str(a.gen_grid), repr(a.spacing)]
     print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     open(os.path.join(a.out, "ref_run.log"), "w").write(r.stdout)
@@ -99,7 +104,16 @@ def main():
         pack = {k: v for k, v in pack.items()
                 if not re.match(r"^e\d+_", k) or re.sub(r"^e\d+_", "", k) in keep}
         pack["ekf"] = 1
-    path = os.path.join(a.out, ("ref_ekf_n%d.npz" if a.ekf else "ref_epochs_n%d.npz") % a.n)
+    name = ("ref_ekf_n%d.npz" if a.ekf else "ref_epochs_n%d.npz") % a.n
+    if a.gen_grid >= 0:                                    # keep what pins the generator: axis values, scores, fixes
+        import re
+        keep = ("x_kk1", "x_k1k1", "zval", "rx_time", "time_grid", "pos_scores")
+        pack = {k: v for k, v in pack.items()
+                if not re.match(r"^e\d+_", k) or re.sub(r"^e\d+_", "", k) in keep}
+        del pack["grid"]
+        pack["grid_type"], pack["spacing"] = a.gen_grid, a.spacing
+        name = "ref_grid_t%d_n%d.npz" % (a.gen_grid, a.n)
+    path = os.path.join(a.out, name)
     np.savez_compressed(path, **pack)
     print("wrote", path, os.path.getsize(path), "bytes")
     if os.path.exists(os.path.join(dump, "XFile.csv")):

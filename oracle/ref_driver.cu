@@ -161,7 +161,8 @@ class RefHarness : public dsp::DPEFlow {
 
 int main(int argc, char** argv) {
     if (argc < 9) {
-        fprintf(stderr, "usage: %s samples.dat handoff.csv rinex grid.csv pos_dim vel_dim epochs out_dir [W] [fs] [dump]\n",
+        fprintf(stderr, "usage: %s samples.dat handoff.csv rinex grid.csv|none pos_dim vel_dim epochs out_dir [W] [fs] [dump] [ekf] "
+                        "[grid_type] [grid_spacing]\n",
                 argv[0]);
         return 2;
     }
@@ -171,6 +172,9 @@ int main(int argc, char** argv) {
     const double fs = argc > 10 ? atof(argv[10]) : 2.5e6;
     const bool dump = argc > 11 ? atoi(argv[11]) != 0 : true;
     const bool ekf = argc > 12 ? atoi(argv[12]) != 0 : false;      // run the reference with its 8-state KF enabled
+    // grid.csv == "none": let the reference generate its grid (BCM_InitPosGrid, batchcorrmanifold.cu:148-255)
+    const int grid_type = argc > 13 ? atoi(argv[13]) : 0;           // ManifoldGridTypes: 0 Uniform, 2 ArthurBasis
+    const float grid_spacing = argc > 14 ? (float)atof(argv[14]) : 1.0f;
     mkdir(out.c_str(), 0755);
     if (!getenv("HOME")) setenv("HOME", "/tmp", 1);
 
@@ -192,6 +196,8 @@ int main(int argc, char** argv) {
     rc |= flow.SetModParam("DPInit", "RINEXFilename", argv[3]);
     rc |= flow.SetModParam("BatchCorrManifold", "LoadPosGridFilename", argv[4]);
     rc |= flow.SetModParam("BatchCorrManifold", "LoadPosGrid", strcmp(argv[4], "none") != 0);
+    rc |= flow.SetModParam("BatchCorrManifold", "GridType", grid_type);
+    rc |= flow.SetModParam("BatchCorrManifold", "GridDimSpacing", grid_spacing);
     rc |= flow.SetModParam("BatchCorrManifold", "PosGridDimSize", pos_dim);
     rc |= flow.SetModParam("BatchCorrManifold", "VelGridDimSize", vel_dim);
     rc |= flow.SetModParam("BatchCorrManifold", "GridLogFileName", (out + "/grid_log.csv").c_str());

@@ -296,6 +296,51 @@ def test_dpe_flow_reproduces_the_reference_epochs(flowapi, tmp_path):
     sh.close()
 
 
+@pytest.mark.parametrize("grid_type", [0, 2])
+def test_host_grid_axes_match_the_reference_generator(flowapi, grid_type):
+    """BCM_InitPosGrid (batchcorrmanifold.cu:148-255), Uniform and ArthurBasis: the axis values the UNMODIFIED
+    reference generated for a 9^4 grid with GridDimSpacing 2.5 (its TimeGrid port, tests/golden/ref_grid_t*_n9.npz,
+    oracle/make_golden_ref.py --gen-grid) against the host generator, all four axes, t fastest."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_grid_t%d_n9.npz" % grid_type))
+    n, sp = int(g["n"]), float(g["spacing"])
+    ref_axis = g["e0_time_grid"]
+    grid = flowapi.make_grid([n] * 4, [sp] * 4, grid_type).reshape(n, n, n, n, 4)
+    assert np.array_equal(grid[0, 0, 0, :, 3], ref_axis)             # clock axis: the fastest index
+    assert np.array_equal(grid[0, 0, :, 0, 2], ref_axis)
+    assert np.array_equal(grid[0, :, 0, 0, 1], ref_axis)
+    assert np.array_equal(grid[:, 0, 0, 0, 0], ref_axis)             # x: the slowest index
+    if grid_type == 2:
+        assert ref_axis[0] == -6 * sp and ref_axis[1] == -3 * sp      # stretched outer quarter, uniform core
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid_type", [0, 2])
+def test_dpe_flow_with_a_generated_grid(flowapi, tmp_path, grid_type):
+    """LoadPosGrid false: the flow generates its own position grid (GridType, GridDimSpacing).  Its TimeGrid port
+    equals the one the reference produced with the same parameters (tests/golden/ref_grid_t*_n9.npz), and the
+    fixes equal those of the same flow fed the same grid through a CSV file.  (The reference's own fixes of
+    that run are not compared: with identical inputs its centre-candidate score at epoch 0 was 4.03e7 where its
+    other run -- ref_epochs_n9.npz -- and the oracle have 6.14e7: the flip / no-flip race of BCS_ChooseCodeCorr,
+    batchcorrscores.cu:508-541, hit channels 0 and 7.)"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_grid_t%d_n9.npz" % grid_type))
+    n, epochs, first, sp = int(g["n"]), int(g["epochs"]), int(g["first_block"]), float(g["spacing"])
+    sc, _, files = _write_scenario(tmp_path, n, epochs + first, first_block=first)
+    off = g["offset"]
+    init = ["setparam rx DPInit InitDeltaX %r" % float(off[0]), "setparam rx DPInit InitDeltaY %r" % float(off[1]),
+            "setparam rx DPInit InitDeltaZ %r" % float(off[2]), "setparam rx DPInit InitDeltaT %r" % float(off[3]),
+            "setparam rx BatchCorrManifold GridType %d" % grid_type,
+            "setparam rx BatchCorrManifold GridDimSpacing %r" % sp]
+    x_gen, x_csv = str(tmp_path / "XFile_gen.csv"), str(tmp_path / "XFile_csv.csv")
+    sh = _drive(flowapi, files, n, init + ["setparam rx BatchCorrManifold LoadPosGrid false"], epochs, x_gen)
+    assert np.array_equal(sh.read_port("rx", "BatchCorrManifold", "TimeGrid"), g["e0_time_grid"])
+    sh.close()
+    grid = flowapi.make_grid([n] * 4, [sp] * 4, grid_type)
+    np.savetxt(files["grid"], grid, delimiter=",", fmt="%.17g")
+    _drive(flowapi, files, n, init, epochs, x_csv).close()
+    a, b = np.loadtxt(x_gen, delimiter=","), np.loadtxt(x_csv, delimiter=",")
+    assert a.shape == (epochs, 8) and np.array_equal(a, b)
+
+
 @pytest.mark.gpu
 def test_dpe_flow_with_the_kalman_filter_enabled_matches_the_reference(flowapi, tmp_path):
     """`setparam <flow> cuEKF EnableEKF true` (the reference's 8-state KF: H = I, random-walk F,
