@@ -47,6 +47,8 @@ def main():
                     "writes only the per-epoch states (ref_ekf_n<N>.npz)")
     ap.add_argument("--gen-grid", type=int, default=-1, help="let the reference GENERATE its position grid "
                     "(LoadPosGrid=false): ManifoldGridTypes value, 0 Uniform / 2 ArthurBasis; writes ref_grid_t<T>_n<N>.npz")
+    ap.add_argument("--lpower", type=int, default=1, help="BatchCorrManifold LPower; != 1 writes ref_bcm_L<L>_n<N>.npz "
+                    "(the BCM inputs and outputs only)")
     ap.add_argument("--spacing", type=float, default=2.0, help="GridDimSpacing for --gen-grid (all 8 dimensions)")
     ap.add_argument("--offset", type=float, nargs=4, default=[7.0, -4.0, 3.0, 8.0],
                     help="ECEF x,y,z and clock (m) offset of the handed-off state from the truth")
@@ -75,8 +77,8 @@ def main():
     dump = os.path.join(a.work, "dump")
     cmd = [exe, files["dat"], files["handoff"], files["rinex"], files["grid"] if a.gen_grid < 0 else "none", str(a.n), "5",
            str(a.epochs), dump, str(a.W), repr(sc.cfg.fs), "1", "1" if a.ekf else "0"]
-    if a.gen_grid >= 0:
-        cmd += [str(a.gen_grid), repr(a.spacing)]
+    if a.gen_grid >= 0 or a.lpower != 1:
+        cmd += [str(max(a.gen_grid, 0)), repr(a.spacing if a.gen_grid >= 0 else 1.0), str(a.lpower)]
     print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     open(os.path.join(a.out, "ref_run.log"), "w").write(r.stdout)
@@ -113,6 +115,12 @@ def main():
         del pack["grid"]
         pack["grid_type"], pack["spacing"] = a.gen_grid, a.spacing
         name = "ref_grid_t%d_n%d.npz" % (a.gen_grid, a.n)
+    if a.lpower != 1:                                      # BatchCorrManifold in and out: enough to pin sum |v|^L
+        import re
+        drop = ("iq", "carr_scores_win", "sat_raw", "tx_time", "ri_end")
+        pack = {k: v for k, v in pack.items() if not re.match(r"^e\d+_", k) or re.sub(r"^e\d+_", "", k) not in drop}
+        pack["lpower"] = a.lpower
+        name = "ref_bcm_L%d_n%d.npz" % (a.lpower, a.n)
     path = os.path.join(a.out, name)
     np.savez_compressed(path, **pack)
     print("wrote", path, os.path.getsize(path), "bytes")

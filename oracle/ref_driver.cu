@@ -162,7 +162,7 @@ class RefHarness : public dsp::DPEFlow {
 int main(int argc, char** argv) {
     if (argc < 9) {
         fprintf(stderr, "usage: %s samples.dat handoff.csv rinex grid.csv|none pos_dim vel_dim epochs out_dir [W] [fs] [dump] [ekf] "
-                        "[grid_type] [grid_spacing]\n",
+                        "[grid_type] [grid_spacing] [lpower]\n",
                 argv[0]);
         return 2;
     }
@@ -175,6 +175,7 @@ int main(int argc, char** argv) {
     // grid.csv == "none": let the reference generate its grid (BCM_InitPosGrid, batchcorrmanifold.cu:148-255)
     const int grid_type = argc > 13 ? atoi(argv[13]) : 0;           // ManifoldGridTypes: 0 Uniform, 2 ArthurBasis
     const float grid_spacing = argc > 14 ? (float)atof(argv[14]) : 1.0f;
+    const int lpower = argc > 15 ? atoi(argv[15]) : 1;              // BatchCorrManifold LPower (score = sum |v|^L)
     mkdir(out.c_str(), 0755);
     if (!getenv("HOME")) setenv("HOME", "/tmp", 1);
 
@@ -196,6 +197,7 @@ int main(int argc, char** argv) {
     rc |= flow.SetModParam("DPInit", "RINEXFilename", argv[3]);
     rc |= flow.SetModParam("BatchCorrManifold", "LoadPosGridFilename", argv[4]);
     rc |= flow.SetModParam("BatchCorrManifold", "LoadPosGrid", strcmp(argv[4], "none") != 0);
+    rc |= flow.SetModParam("BatchCorrManifold", "LPower", lpower);
     rc |= flow.SetModParam("BatchCorrManifold", "GridType", grid_type);
     rc |= flow.SetModParam("BatchCorrManifold", "GridDimSpacing", grid_spacing);
     rc |= flow.SetModParam("BatchCorrManifold", "PosGridDimSize", pos_dim);

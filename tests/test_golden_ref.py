@@ -104,6 +104,54 @@ def test_oracle_manifold_matches_reference_scores_and_fix(gold):
         assert np.array_equal(gold.k(e, "x_k1k1")[:4], gold.k(e, "zval")[:4])
 
 
+def _bcm_gold(L):
+    g = np.load(os.path.join(os.path.dirname(GOLD), "ref_bcm_L%d_n9.npz" % L))
+    C, T, S, W, fs = int(g["C"]), int(g["T"]), int(g["S"]), int(g["W"]), float(g["fs"])
+    k = lambda n: g["e0_" + n]
+    w = k("code_scores_win").reshape(C, 2 * W + 2, 2)
+    ep = dict(prn=k("prn"), rc_start=k("rc_start"), ri_start=k("ri_start"), fc=k("fc"), fi=k("fi"),
+              cp_start=k("cp_start"), cp_ref=k("cp_ref"), rc_end=k("rc_end"), cp_end=k("cp_end"),
+              cp_ref_tow=k("cp_ref_tow"), rx_time=float(k("rx_time")[0]), center=k("x_kk1"), enu2ecef=k("enu2ecef"),
+              sat_states=k("sat_states").reshape(-1, 8), doppler_sign=1, S=S, fs=fs, time_dim=T)
+    return dict(C=C, T=T, S=S, W=W, fs=fs, grid=g["grid"], win=w[..., 0] + 1j * w[..., 1], ep=ep,
+                pos_scores=k("pos_scores"), zval=k("zval"), lpower=int(g["lpower"]))
+
+
+@pytest.mark.parametrize("L", [2, 3])
+def test_oracle_manifold_matches_reference_for_other_lpower(L):
+    """`setparam <flow> BatchCorrManifold LPower 2|3` in the UNMODIFIED reference (score = sum_prn |v|^L,
+    batchcorrmanifold.cu:1816; tests/golden/ref_bcm_L*_n9.npz, oracle/make_golden_ref.py --lpower)."""
+    b = _bcm_gold(L)
+    assert b["lpower"] == L
+    ep, S, W = b["ep"], b["S"], b["W"]
+    full = np.zeros((b["C"], S), complex)
+    full[:, S // 2 - W: S // 2 - W + 2 * W + 2] = b["win"]
+    r = orc.pos_meas_ml(full, b["grid"], ep["center"], ep["enu2ecef"], ep["sat_states"], b["T"], ep["fc"], ep["rc_end"],
+                        ep["cp_ref_tow"], ep["cp_end"], ep["cp_ref"], ep["rx_time"], b["fs"], S, lpower=L)
+    assert np.max(np.abs(r["scores"] - b["pos_scores"]) / b["pos_scores"]) < 1e-9
+    assert r["argmax"] == int(np.argmax(b["pos_scores"]))
+    assert np.max(np.abs(r["z"] - b["zval"][:4])) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [2, 3])
+def test_cuda_manifold_matches_reference_for_other_lpower(capi, L):
+    b = _bcm_gold(L)
+    G = b["grid"].shape[0]
+    ctx = capi.Context(fs=b["fs"], S=b["S"], max_chan=b["C"], G=G, time_dim=b["T"], lag_halfwidth=b["W"], lpower=L)
+    ctx.grid_set(b["grid"])
+    ctx.epoch_set(b["ep"])
+    ctx.code_scores_set(b["win"])
+    ctx.score_pos(capi.SCORE_LOOKUP, capi.SAT_MIDDLE)
+    ctx.estimate(capi.EST_ARGMAX)
+    res = ctx.result_fetch()
+    scores = ctx.copy_out(capi.PTR_POS_SCORES, np.float64, G)
+    assert np.max(np.abs(scores - b["pos_scores"]) / b["pos_scores"]) < 1e-9
+    assert res.argmax == int(np.argmax(b["pos_scores"]))
+    assert np.max(np.abs(np.array(res.z[:4]) - b["zval"][:4])) < 1e-6
+    ctx.close()
+
+
 def test_oracle_carrier_spectrum_matches_reference(gold):
     """Velocity branch: DC removal, chosen replica, zero-padded 524288-point spectrum
     (batchcorrscores.cu:1158-1180) -- the reference's CarrScores window around 0 Hz."""
