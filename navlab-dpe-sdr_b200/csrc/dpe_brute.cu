@@ -39,17 +39,19 @@ k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, co
             double fs, int S, int W, int T, int64_t G, int64_t grid_offset, int16_t* __restrict__ pair_k,
             float* __restrict__ pair_a, int32_t* __restrict__ blk_hist) {
     extern __shared__ int32_t hs[];
+    __shared__ ChanConst cc[DPE_MAX_CHAN];
     const EpochDev& e = *ep;
     const int NB = 2 * W + 1;
     const int nbuck = e.C * NB;
     for (int i = threadIdx.x; i < nbuck; i += blockDim.x) hs[i] = 0;
+    chan_consts(e, fs, cc);
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < G) {
         const Cand p = cand_ecef(e, grid + 4 * j);
         const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
         for (int c = 0; c < e.C; ++c) {
-            const double idx = code_index(e, p, sat + ((size_t)c * T + it) * 8, c, fs, (double)S);
+            const double idx = code_index(e, cc[c], p, sat + ((size_t)c * T + it) * 8, c, (double)S);
             const Bin b = make_bin(idx, c, S, W);
             pair_k[(size_t)c * G + j] = b.ok ? (int16_t)b.l : (int16_t)-1;
             pair_a[(size_t)c * G + j] = (float)b.wg;

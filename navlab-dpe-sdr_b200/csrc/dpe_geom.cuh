@@ -21,18 +21,31 @@ __device__ __forceinline__ Cand cand_ecef(const EpochDev& e, const double* __res
     return p;
 }
 
+// Per-channel terms of the back-calculation that do not depend on the candidate, evaluated once per
+// CTA with the reference's own operations (so the bins stay bit-identical): fs / fc (one FP64 division
+// per pair otherwise), the two integer -> double conversions and (cpEnd - cpRef) * T_CA.
+struct ChanConst { double ratio, tow, cpd; };
+
+__device__ __forceinline__ void chan_consts(const EpochDev& e, double fs, ChanConst* __restrict__ cc) {
+    for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+        cc[c].ratio = fs / e.fc[c];
+        cc[c].tow = (double)e.cp_ref_tow[c];
+        cc[c].cpd = (e.cp_end[c] - e.cp_ref[c]) * K_T_CA;
+    }
+}
+
 // batchcorrmanifold.cu:1779-1791: geometric back-calculation of the code phase
 // and its (fractional) fft-shifted correlogram index for channel c.
-__device__ __forceinline__ double code_index(const EpochDev& e, const Cand& p, const double* __restrict__ sat,
-                                             int c, double fs, double S) {
+__device__ __forceinline__ double code_index(const EpochDev& e, const ChanConst& k, const Cand& p,
+                                             const double* __restrict__ sat, int c, double S) {
     double los[3] = {sat[0] - p.px, sat[1] - p.py, sat[2] - p.pz};
     const double range = norm(3, los);
     const double pr = range - K_C * sat[3] + p.pt;
     const double tx = e.rx_time - pr / K_C;
-    const double frac = tx - e.cp_ref_tow[c] - ((e.cp_end[c] - e.cp_ref[c]) * K_T_CA);
+    const double frac = tx - k.tow - k.cpd;
     const double bc_rc = frac * K_F_CA;
     const double rc0 = bc_rc - e.rc_end[c];
-    return (fs / e.fc[c]) * (-rc0) + S / 2.0;
+    return k.ratio * (-rc0) + S / 2.0;
 }
 
 struct Bin { int64_t f; double wf, wg; int l; bool ok; };   // v = cs[l+1]*wg + cs[l]*wf

@@ -25,8 +25,11 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
                int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
                unsigned int* __restrict__ ticket, double* __restrict__ partial) {
     __shared__ EpochDev e;
+    __shared__ ChanConst cc[DPE_MAX_CHAN];
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
+    __syncthreads();
+    chan_consts(e, fs, cc);
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < G;
@@ -37,7 +40,7 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         p = cand_ecef(e, grid + 4 * j);
         const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
         for (int c = 0; c < e.C; ++c) {
-            const double idx = code_index(e, p, sat + ((size_t)c * T + it) * 8, c, fs, (double)S);
+            const double idx = code_index(e, cc[c], p, sat + ((size_t)c * T + it) * 8, c, (double)S);
             const Bin b = make_bin(idx, c, S, W);
             if (b.ok) {
                 const double2 lo = cs[(size_t)c * NL + b.l], hi = cs[(size_t)c * NL + b.l + 1];
@@ -67,7 +70,8 @@ __global__ void k_debug_bins(const double* __restrict__ grid, const EpochDev* __
     const Cand p = cand_ecef(e, grid + 4 * j);
     const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
     for (int c = 0; c < e.C; ++c) {
-        const double idx = code_index(e, p, sat + ((size_t)c * T + it) * 8, c, fs, (double)S);
+        const ChanConst k = {fs / e.fc[c], (double)e.cp_ref_tow[c], (e.cp_end[c] - e.cp_ref[c]) * K_T_CA};
+        const double idx = code_index(e, k, p, sat + ((size_t)c * T + it) * 8, c, (double)S);
         const Bin b = make_bin(idx, c, S, W);
         f_idx[t * e.C + c] = b.f;
         alpha[t * e.C + c] = b.wg;
