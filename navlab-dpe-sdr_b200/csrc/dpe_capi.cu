@@ -220,6 +220,12 @@ int dpe_ctx_destroy(dpe_ctx* c) {
 int dpe_grid_set(dpe_ctx* c, const double* enu_dt, int64_t G, void* stream) {
     DPE_REQUIRE(c && enu_dt, DPE_EINVAL, "dpe_grid_set: null argument");
     DPE_REQUIRE(G == c->G, DPE_EINVAL, "dpe_grid_set: G=%lld, context holds %lld", (long long)G, (long long)c->G);
+    if (c->sort_pending) {                         // a presort on another stream still reads the old grid
+        DPE_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_sort, 0));
+        c->sort_pending = 0;
+    }
+    c->sort_valid = 0;
+    c->have_scores = 0;
     DPE_CUDA(cudaMemcpyAsync(c->grid, enu_dt, sizeof(double) * 4 * G, cudaMemcpyDefault, (cudaStream_t)stream));
     return DPE_OK;
 }
