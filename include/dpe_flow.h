@@ -29,6 +29,12 @@ long dpe_shell_read_port(dpe_shell* sh, const char* flow, const char* module, co
  * ephemeris of a RINEX 2.x file, and BCM_InitPosGrid (batchcorrmanifold.cu:148-255) */
 int dpe_host_sat_position(const char* rinex_path, int prn, double tx_time, double* state8);
 int dpe_host_make_grid(const int* dims4, const double* spacing4, int grid_type, double* out, long cap);
+/* the file readers either side of the path, for CPU parity tests: the handoff CSV
+ * (dpinit.cpp:247-400) flattened as [n, rxTime, bytes_read, t_oe, X_ECEF(8), then 8 rows of n:
+ * prn, rc, ri, fc, fi, cp, cp_timestamp, TOW]; the grid CSV (batchcorrmanifold.cu:2433-2444) as
+ * [G][4].  Return the element / candidate count or -1.                                         */
+long dpe_host_read_handoff(const char* path, double* out, long cap);
+long dpe_host_read_grid(const char* path, double* out, long cap);
 
 #ifdef __cplusplus
 }

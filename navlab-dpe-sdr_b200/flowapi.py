@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdpe_flow.so")
 CONSOLE_PATH = os.path.join(_HERE, "lib", "dpe_console")
 EXPORTS = ("dpe_shell_create", "dpe_shell_destroy", "dpe_shell_exec", "dpe_shell_run_blocking",
-           "dpe_shell_flow_stats", "dpe_shell_read_port", "dpe_host_sat_position", "dpe_host_make_grid")
+           "dpe_shell_flow_stats", "dpe_shell_read_port", "dpe_host_sat_position", "dpe_host_make_grid",
+           "dpe_host_read_handoff", "dpe_host_read_grid")
 
 _lib = None
 
@@ -31,6 +32,10 @@ def load_library():
         lib.dpe_shell_read_port.restype = C.c_long
         lib.dpe_host_sat_position.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_void_p]
         lib.dpe_host_make_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+        lib.dpe_host_read_handoff.argtypes = [C.c_char_p, C.c_void_p, C.c_long]
+        lib.dpe_host_read_handoff.restype = C.c_long
+        lib.dpe_host_read_grid.argtypes = [C.c_char_p, C.c_void_p, C.c_long]
+        lib.dpe_host_read_grid.restype = C.c_long
         _lib = lib
     return _lib
 
@@ -88,3 +93,26 @@ def make_grid(dims, spacing, grid_type=0) -> np.ndarray:
     if load_library().dpe_host_make_grid(d.ctypes.data, s.ctypes.data, grid_type, out.ctypes.data, out.size) != n:
         raise RuntimeError("make_grid failed")
     return out.reshape(n, 4)
+
+
+def read_handoff(path: str) -> dict:
+    """The host flow's handoff-CSV reader (DPInit), as a dict of arrays."""
+    out = np.zeros(12 + 8 * 64)
+    n = load_library().dpe_host_read_handoff(path.encode(), out.ctypes.data, out.size)
+    if n < 0:
+        raise RuntimeError("handoff file not readable")
+    c = int(out[0])
+    rows = out[12:12 + 8 * c].reshape(8, c)
+    keys = ("prn", "rc", "ri", "fc", "fi", "cp", "cp_timestamp", "TOW")
+    d = dict(rxTime=out[1], bytes_read=int(out[2]), t_oe=int(out[3]), X_ECEF=out[4:12].copy())
+    d.update({k: rows[i].copy() for i, k in enumerate(keys)})
+    return d
+
+
+def read_grid(path: str, cap: int = 1 << 22) -> np.ndarray:
+    """The host flow's grid-CSV reader (BatchCorrManifold LoadPosGrid)."""
+    out = np.zeros(4 * cap)
+    n = load_library().dpe_host_read_grid(path.encode(), out.ctypes.data, out.size)
+    if n < 0:
+        raise RuntimeError("grid file not readable")
+    return out[:4 * n].reshape(n, 4).copy()

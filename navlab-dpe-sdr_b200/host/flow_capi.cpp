@@ -71,4 +71,31 @@ int dpe_host_make_grid(const int* dims4, const double* spacing4, int grid_type, 
     return (int)(g.size() / 4);
 }
 
+// handoff CSV (dpinit.cpp:247-400) flattened as doubles:
+//   [0] n channels  [1] rxTime  [2] bytes_read  [3] t_oe  [4..11] X_ECEF(8)
+//   then 8 rows of n: prn, rc, ri, fc, fi, cp, cp_timestamp, TOW
+long dpe_host_read_handoff(const char* path, double* out, long cap) {
+    gnss::Handoff h;
+    if (gnss::ReadHandoff(path, &h)) return -1;
+    const long n = (long)h.prn.size(), need = 12 + 8 * n;
+    if (need > cap) return -1;
+    out[0] = (double)n; out[1] = h.rxTime; out[2] = (double)h.bytes_read; out[3] = (double)h.t_oe;
+    for (int i = 0; i < 8; ++i) out[4 + i] = h.X_ECEF[i];
+    double* q = out + 12;
+    for (long i = 0; i < n; ++i) {
+        q[0 * n + i] = h.prn[i]; q[1 * n + i] = h.rc[i]; q[2 * n + i] = h.ri[i]; q[3 * n + i] = h.fc[i];
+        q[4 * n + i] = h.fi[i]; q[5 * n + i] = h.cp[i]; q[6 * n + i] = h.cp_timestamp[i]; q[7 * n + i] = h.TOW[i];
+    }
+    return need;
+}
+
+// grid CSV (`x,y,z,delta_t` per line, batchcorrmanifold.cu:2433-2444): returns the number of candidates
+long dpe_host_read_grid(const char* path, double* out, long cap) {
+    std::vector<double> g;
+    if (gnss::ReadGridCsv(path, &g)) return -1;
+    if ((long)g.size() > cap) return -1;
+    std::memcpy(out, g.data(), g.size() * sizeof(double));
+    return (long)(g.size() / 4);
+}
+
 }  // extern "C"

@@ -296,6 +296,25 @@ def test_dpe_flow_reproduces_the_reference_epochs(flowapi, tmp_path):
     sh.close()
 
 
+def test_host_file_readers_on_the_reference_demo_files(flowapi, tmp_path):
+    """DPInit's handoff-CSV grammar (dpinit.cpp:247-400) on the reference's own shipped file
+    (tests/golden/handoff_params_usrp6.csv = demofiles/handoff_params_usrp6.csv) against the oracle's
+    reader, and the `x,y,z,delta_t` grid CSV (batchcorrmanifold.cu:2433-2444) round trip."""
+    path = os.path.join(ROOT, "tests", "golden", "handoff_params_usrp6.csv")
+    got, ref = flowapi.read_handoff(path), chm.read_handoff(path)
+    assert list(got["prn"].astype(int)) == [2, 3, 6, 12, 17, 19, 24, 28]         # prn_list row of the shipped file
+    assert got["rxTime"] == ref["rxTime"] and got["bytes_read"] == ref["bytes_read"]
+    assert np.array_equal(got["X_ECEF"][:len(ref["X_ECEF"])], ref["X_ECEF"])
+    for k_host, k_ref in (("rc", "rc"), ("ri", "ri"), ("fc", "fc"), ("fi", "fi"), ("cp", "cp"),
+                          ("cp_timestamp", "cp_timestamp"), ("TOW", "TOW")):
+        assert np.array_equal(got[k_host], np.asarray(ref[k_ref], dtype=float)), k_host
+    assert flowapi.read_handoff.__doc__ and pytest.raises(RuntimeError, flowapi.read_handoff, str(tmp_path / "missing.csv"))
+    grid, _ = synth.uniform_grid(5, (5.0, 5.0, 5.0, 6.0))
+    p = str(tmp_path / "rngrid.csv")
+    np.savetxt(p, grid, delimiter=",", fmt="%.17g")
+    assert np.array_equal(flowapi.read_grid(p), grid)
+
+
 @pytest.mark.parametrize("grid_type", [0, 2])
 def test_host_grid_axes_match_the_reference_generator(flowapi, grid_type):
     """BCM_InitPosGrid (batchcorrmanifold.cu:148-255), Uniform and ArthurBasis: the axis values the UNMODIFIED
