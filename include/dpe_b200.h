@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define DPE_MAX_CHAN 37          /* CONST_PRN_MAX, utils/inc/consthelper.h:14 */
-#define DPE_ABI_VERSION 1
+#define DPE_ABI_VERSION 2
 #define DPE_PARTIAL_LEN 16          /* doubles per per-rank partial estimate         */
 
 enum {
@@ -39,7 +39,8 @@ enum {
     DPE_ECUDA = -2,              /* CUDA runtime error (see dpe_last_error)    */
     DPE_ENOMEM = -3,
     DPE_ESTATE = -4,             /* call order violated (e.g. score before prep) */
-    DPE_EWINDOW = -5             /* candidates fell outside the lag window     */
+    DPE_EWINDOW = -5,            /* candidates fell outside the lag window     */
+    DPE_ECOMM = -6               /* NCCL missing / failed (see dpe_last_error) */
 };
 
 /* dpe_score_pos scoring modes */
@@ -251,6 +252,48 @@ int dpe_epoch_run(dpe_ctx* ctx, const int16_t* iq_host, const dpe_epoch* ep,
                   const double* sat_states, int score_mode, int est_mode, int with_vel,
                   dpe_result* out, void* stream);
 
+/* ---- asynchronous epochs ---------------------------------------------------------
+ * dpe_epoch_submit enqueues one whole epoch (parameter + block upload, pre-pass, correlogram,
+ * scoring, estimate, optional velocity manifold, result D2H into page-locked memory) on the
+ * context's OWN stream and returns at once; dpe_epoch_collect waits for that epoch and hands the
+ * result over.  One epoch may be in flight per context.  A caller that holds two contexts and
+ * alternates between them gets cross-epoch overlap: every kernel except k_brute is sized to share
+ * an SM with a running k_brute CTA, so the pre-pass / pair sort / reductions of one epoch run
+ * under the k_brute of the other (the reference overlaps its BCS streams the same way,
+ * batchcorrscores.cu:727-745,1046-1180).  `iq` may be a host or a device pointer; on ranks != 0
+ * of a communicator (below) it is ignored and may be NULL.                                   */
+int dpe_epoch_submit(dpe_ctx* ctx, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                     int score_mode, int est_mode, int with_vel);
+int dpe_epoch_collect(dpe_ctx* ctx, dpe_result* out);
+/* 1 while a submitted epoch has not been collected                                            */
+int dpe_epoch_pending(dpe_ctx* ctx);
+
+/* ---- multi-GPU ---------------------------------------------
+ * The candidate grid is sharded in contiguous index ranges (cfg.grid_offset / G / G_total);
+ * one context per GPU, one NCCL communicator per context, every collective on the context's
+ * own stream between its kernels -- no host code in between:
+ *     rank 0: H2D of one packet {block, channel + geometry parameters, satellite states}
+ *     ncclBroadcast(packet)  ->  pre-pass, scoring of the shard  ->  ncclAllGather(16-double
+ *     partial)  ->  k_finalize on every rank (lowest global index wins arg-max ties)
+ * The reference is single-GPU (no cudaSetDevice anywhere); this replaces nothing of it and
+ * extends BatchCorrManifold::Update (batchcorrmanifold.cu:2501-2635) over `nranks` GPUs.
+ * NCCL is dlopen()ed (libnccl.so.2) on the first dpe_comm_* call; single-GPU use needs none.
+ *
+ * dpe_comm_get_unique_id: rank 0 obtains DPE_COMM_ID_BYTES bytes and ships them to the other
+ * ranks by any means (torch.distributed store, a file, a pipe, shared memory of one process).
+ * dpe_comm_init: collective over all ranks (one process per GPU, or one thread per GPU inside
+ * one process -- dpe_console's NumGPUs); blocks until every rank has joined.
+ * dpe_epoch_run_dist = dpe_epoch_submit + dpe_epoch_collect; every rank passes the same `ep`
+ * (the launch geometry needs C on the host); the device-side parameters, the satellite states
+ * and the block are rank 0's.                                                                 */
+#define DPE_COMM_ID_BYTES 128
+int dpe_comm_get_unique_id(void* id);
+int dpe_comm_init(dpe_ctx* ctx, int nranks, int rank, const void* id);
+int dpe_comm_destroy(dpe_ctx* ctx);
+int dpe_comm_info(dpe_ctx* ctx, int* nranks, int* rank, int* nccl_version);
+int dpe_epoch_run_dist(dpe_ctx* ctx, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                       int score_mode, int est_mode, int with_vel, dpe_result* out);
+
 /* ---- access / introspection ---------------------------------------------------*/
 const void* dpe_dev_ptr(dpe_ctx* ctx, int which);
 /* debug copies (synchronise): chip indices int16 [C][S]; per-channel flags     */
@@ -262,6 +305,11 @@ int dpe_debug_bins(dpe_ctx* ctx, int64_t i0, int64_t n, int sat_mode, int64_t* f
 int dpe_debug_read(dpe_ctx* ctx, int which, size_t offset, void* dst, size_t nbytes);
 /* number of kernels launched by this context since creation                     */
 int64_t dpe_launch_count(dpe_ctx* ctx);
+/* the context's own stream (cudaStream_t as void*): what dpe_epoch_submit launches on          */
+void* dpe_ctx_stream(dpe_ctx* ctx);
+/* registers per thread / dynamic+static shared bytes of a kernel of this library, by name
+ * ("k_brute", "k_prepare", ...): lets a bench report whether the side kernels fit beside k_brute */
+int dpe_kernel_attr(const char* kernel, int* regs, int* smem_bytes, int* max_threads);
 
 /* ---- runtime helpers for host code that does not link the CUDA runtime ------------
  * (the C++ flow mirror in navlab-dpe-sdr_b200/host/ links libdpe_b200.so only).

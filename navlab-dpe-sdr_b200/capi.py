@@ -15,10 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdpe_b200.so")
 
 DPE_MAX_CHAN = 37
-DPE_ABI_VERSION = 1
+DPE_ABI_VERSION = 2
 DPE_PARTIAL_LEN = 16
+DPE_COMM_ID_BYTES = 128
 
-DPE_OK, DPE_EINVAL, DPE_ECUDA, DPE_ENOMEM, DPE_ESTATE, DPE_EWINDOW = 0, -1, -2, -3, -4, -5
+DPE_OK, DPE_EINVAL, DPE_ECUDA, DPE_ENOMEM, DPE_ESTATE, DPE_EWINDOW, DPE_ECOMM = 0, -1, -2, -3, -4, -5, -6
 SCORE_LOOKUP, SCORE_BRUTE = 0, 1
 EST_ARGMAX, EST_WEIGHTED = 0, 1
 SAT_MIDDLE, SAT_PER_TIME = 0, 1
@@ -38,7 +39,9 @@ EXPORTS = (
     "dpe_debug_channel_flags", "dpe_debug_bins", "dpe_debug_read", "dpe_launch_count", "dpe_profile_enable", "dpe_profile_read",
     "dpe_brute_pairs", "dpe_stream_create", "dpe_stream_destroy", "dpe_stream_sync", "dpe_host_alloc",
     "dpe_host_free", "dpe_device_count", "dpe_microbench_fp32",
-    "dpe_microbench_hbm")
+    "dpe_microbench_hbm", "dpe_epoch_submit", "dpe_epoch_collect", "dpe_epoch_pending", "dpe_epoch_run_dist",
+    "dpe_comm_get_unique_id", "dpe_comm_init", "dpe_comm_destroy", "dpe_comm_info", "dpe_ctx_stream",
+    "dpe_kernel_attr")
 
 
 class DpeCfg(C.Structure):
@@ -113,6 +116,17 @@ def load_library(path: str | None = None):
     lib.dpe_profile_read.argtypes = [vp, vp, vp]
     lib.dpe_brute_pairs.argtypes = [vp]
     lib.dpe_brute_pairs.restype = i64
+    lib.dpe_epoch_submit.argtypes = [vp, vp, C.POINTER(DpeEpoch), vp, i32, i32, i32]
+    lib.dpe_epoch_collect.argtypes = [vp, C.POINTER(DpeResult)]
+    lib.dpe_epoch_pending.argtypes = [vp]
+    lib.dpe_epoch_run_dist.argtypes = [vp, vp, C.POINTER(DpeEpoch), vp, i32, i32, i32, C.POINTER(DpeResult)]
+    lib.dpe_comm_get_unique_id.argtypes = [vp]
+    lib.dpe_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.dpe_comm_destroy.argtypes = [vp]
+    lib.dpe_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.dpe_ctx_stream.argtypes = [vp]
+    lib.dpe_ctx_stream.restype = vp
+    lib.dpe_kernel_attr.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dpe_microbench_fp32.argtypes = [i32, i32, C.POINTER(C.c_double)]
     lib.dpe_microbench_hbm.argtypes = [i32, C.c_size_t, C.POINTER(C.c_double)]
     if path is None:
@@ -262,6 +276,47 @@ class Context:
                                                 est_mode, with_vel, C.byref(r), C.c_void_p(stream)))
         return r
 
+    # -- asynchronous epochs / multi-GPU ----------------------------------------
+    def epoch_submit(self, iq, ep, sat_states=None, score_mode=SCORE_LOOKUP, est_mode=EST_ARGMAX, with_vel=0):
+        """Enqueue one whole epoch on the context's own stream (returns at once)."""
+        e = ep if isinstance(ep, DpeEpoch) else make_epoch(ep)
+        sat = sat_states if sat_states is not None else (ep["sat_states"] if isinstance(ep, dict) else None)
+        if sat is not None and not hasattr(sat, "data_ptr"):
+            sat = np.ascontiguousarray(sat, dtype=np.float64)
+        if isinstance(iq, np.ndarray):
+            iq = np.ascontiguousarray(iq, dtype=np.int16)
+        self._sub = (iq, e, sat)                      # keep alive until collected
+        _check(self.lib, self.lib.dpe_epoch_submit(self.h, _ptr(iq), C.byref(e), _ptr(sat), score_mode, est_mode,
+                                                   with_vel))
+
+    def epoch_collect(self) -> DpeResult:
+        r = DpeResult()
+        _check(self.lib, self.lib.dpe_epoch_collect(self.h, C.byref(r)))
+        return r
+
+    def epoch_run_dist(self, iq, ep, sat_states=None, score_mode=SCORE_LOOKUP, est_mode=EST_ARGMAX,
+                       with_vel=0) -> DpeResult:
+        self.epoch_submit(iq, ep, sat_states, score_mode, est_mode, with_vel)
+        return self.epoch_collect()
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        """Collective: join the NCCL communicator of this context (one per context)."""
+        assert len(unique_id) == DPE_COMM_ID_BYTES
+        buf = C.create_string_buffer(bytes(unique_id), DPE_COMM_ID_BYTES)
+        _check(self.lib, self.lib.dpe_comm_init(self.h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        _check(self.lib, self.lib.dpe_comm_destroy(self.h))
+
+    def comm_info(self):
+        n, r, v = C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib, self.lib.dpe_comm_info(self.h, C.byref(n), C.byref(r), C.byref(v)))
+        return n.value, r.value, v.value
+
+    def stream(self) -> int:
+        p = self.lib.dpe_ctx_stream(self.h)
+        return int(p) if p else 0
+
     # -- access ---------------------------------------------------------------
     def dev_ptr(self, which) -> int:
         p = self.lib.dpe_dev_ptr(self.h, which)
@@ -300,6 +355,22 @@ class Context:
         out = np.empty(count, dtype=dtype)
         _check(self.lib, self.lib.dpe_debug_read(self.h, which, offset, _ptr(out), out.nbytes))
         return out
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and ships the bytes to the others)."""
+    lib = load_library()
+    buf = C.create_string_buffer(DPE_COMM_ID_BYTES)
+    _check(lib, lib.dpe_comm_get_unique_id(buf))
+    return buf.raw
+
+
+def kernel_attr(name: str):
+    """(registers per thread, static shared bytes, max threads per block) of a library kernel."""
+    lib = load_library()
+    r, sm, mt = C.c_int(), C.c_int(), C.c_int()
+    _check(lib, lib.dpe_kernel_attr(name.encode(), C.byref(r), C.byref(sm), C.byref(mt)))
+    return r.value, sm.value, mt.value
 
 
 def microbench_fp32(device=0, use_ffma2=True) -> float:

@@ -29,15 +29,21 @@
 namespace dpe {
 
 // ---------------------------------------------------------------------------
-// pass 1: bins of every pair + per-block (PRN, lag) histograms.  The sort below is a stable
-// counting sort (position in the bucket = rank by candidate index), so the composition of every
-// group -- and with it the summation order of the slots that a CTA boundary cuts -- is the same on every run.
+// The pair sort: three launches (round 1: five).
+//   k_pair_bins   bins of every pair + per-CTA (PRN, lag) histograms
+//   k_block_scan  per bucket: exclusive scan of the per-CTA counts; the CTA that takes the last
+//                 ticket lays the buckets out as groups / slots (bucket scan)
+//   k_scatter     group headers + the pairs into their bucket, in candidate order
+// It is a stable counting sort (position in the bucket = rank by candidate index), so the
+// composition of every group -- and with it the summation order of the slots that a CTA boundary
+// of k_brute cuts -- is the same on every run.  No kernel here waits for another CTA (last-ticket
+// tails only): with two epochs in flight these kernels share the SMs with a running k_brute.
 // ---------------------------------------------------------------------------
 template <int SAT_MODE>
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE128
 k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             double fs, int S, int W, int T, int64_t G, int64_t grid_offset, int16_t* __restrict__ pair_k,
-            float* __restrict__ pair_a, int32_t* __restrict__ blk_hist) {
+            float* __restrict__ pair_a, float2* __restrict__ pair_v, int32_t* __restrict__ blk_hist) {
     extern __shared__ int32_t hs[];
     __shared__ ChanConst cc[DPE_MAX_CHAN];
     const EpochDev& e = *ep;
@@ -56,6 +62,7 @@ k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, co
             pair_k[(size_t)c * G + j] = b.ok ? (int16_t)b.l : (int16_t)-1;
             pair_a[(size_t)c * G + j] = (float)b.wg;
             if (b.ok) atomicAdd(&hs[c * NB + b.l], 1);
+            else pair_v[(size_t)c * G + j] = make_float2(__int_as_float(0x7fc00000), 0.f);   // NaN: "not scored"
         }
     }
     __syncthreads();
@@ -63,10 +70,19 @@ k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, co
         blk_hist[(size_t)i * gridDim.x + blockIdx.x] = hs[i];    // bucket-major: the scan below is coalesced
 }
 
-// pass 1b: exclusive scan of every bucket's per-block counts (in place) + bucket totals.
-// One CTA per bucket, 256 blocks per step.
-__global__ void __launch_bounds__(256)
-k_block_scan(int32_t* __restrict__ blk_hist, int nblk, int32_t* __restrict__ hist) {
+// Every non-empty bucket is padded to whole groups of kBfNC pairs and to whole CTA slots of kBfWarps
+// groups (a slot has one PRN and one lag).
+__device__ __forceinline__ int groups_of_count(int cnt) {
+    const int g = (cnt + kBfNC - 1) / kBfNC;
+    return ((g + kBfWarps - 1) / kBfWarps) * kBfWarps;
+}
+
+// One CTA per bucket: exclusive scan of the bucket's per-CTA counts (in place), 256 CTAs per step, bucket
+// total -> hist.  Last CTA: group base of every bucket + total group count.
+__global__ void DPE_SIDE256
+k_block_scan(int32_t* __restrict__ blk_hist, int nblk, int32_t* __restrict__ hist, int nbuck,
+             int32_t* __restrict__ group_base, int64_t* __restrict__ bucket_base, int32_t* __restrict__ n_groups,
+             int64_t max_groups, unsigned int* __restrict__ ticket) {
     __shared__ int32_t wsum[8];
     __shared__ int32_t s_carry;
     int32_t* row = blk_hist + (size_t)blockIdx.x * nblk;
@@ -93,36 +109,19 @@ k_block_scan(int32_t* __restrict__ blk_hist, int nblk, int32_t* __restrict__ his
         __syncthreads();
     }
     if (threadIdx.x == 0) hist[blockIdx.x] = s_carry;
-}
-
-// ---------------------------------------------------------------------------
-// pass 2: bucket -> group layout.  Every non-empty bucket is padded to whole groups of
-// kBfNC pairs and to whole CTA slots of kBfWarps groups (a slot has one PRN and one lag).
-//   k_bucket_scan    (1 CTA)  group base of every bucket, total group count
-//   k_group_headers  (many)   {channel, lag, valid pairs} of every group
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep, int W,
-              int32_t* __restrict__ group_base, int64_t* __restrict__ bucket_base,
-              int32_t* __restrict__ n_groups, int64_t max_groups) {
-    __shared__ int32_t wsum[8];
-    const int NB = 2 * W + 1;
-    const int nbuck = ep->C * NB;
+    if (!take_last_ticket(ticket)) return;
+    // ---- bucket -> group layout (all bucket totals are visible now) ----
     const int per = (nbuck + 255) / 256;                   // consecutive buckets per thread
     const int b0 = threadIdx.x * per, b1 = min(b0 + per, nbuck);
-    auto groups_of = [&](int i) {                          // whole groups, rounded up to whole slots
-        const int g = (hist[i] + kBfNC - 1) / kBfNC;
-        return ((g + kBfWarps - 1) / kBfWarps) * kBfWarps;
-    };
     int32_t mine = 0;
-    for (int i = b0; i < b1; ++i) mine += groups_of(i);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = b0; i < b1; ++i) mine += groups_of_count(__ldcg(hist + i));
     int32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += u;
     }
+    __syncthreads();
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     int32_t base = incl - mine;
@@ -130,7 +129,7 @@ k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep,
     for (int i = b0; i < b1; ++i) {
         group_base[i] = base;
         bucket_base[i] = (int64_t)base * kBfNC;
-        base += groups_of(i);
+        base += groups_of_count(__ldcg(hist + i));
     }
     if (threadIdx.x == 255) {                              // the last thread ends on the total
         group_base[nbuck] = base;
@@ -138,43 +137,43 @@ k_bucket_scan(const int32_t* __restrict__ hist, const EpochDev* __restrict__ ep,
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_group_headers(const int32_t* __restrict__ hist, const int32_t* __restrict__ group_base,
-                const EpochDev* __restrict__ ep, int W, int4* __restrict__ hdr, int64_t max_groups) {
-    extern __shared__ int32_t sm[];        // [nbuck+1] group bases
-    const int NB = 2 * W + 1;
-    const int nbuck = ep->C * NB;
-    for (int i = threadIdx.x; i <= nbuck; i += blockDim.x) sm[i] = group_base[i];
-    __syncthreads();
-    const int total = sm[nbuck];
-    if (total > max_groups) return;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    int lo = 0, hi = nbuck - 1;                // last bucket with base <= g
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (sm[mid] <= g) lo = mid; else hi = mid - 1;
-    }
-    const int q = g - sm[lo];
-    const int cnt = hist[lo];
-    const int ng = (cnt + kBfNC - 1) / kBfNC;
-    int n = 0;
-    if (q < ng) { n = cnt - q * kBfNC; if (n > kBfNC) n = kBfNC; }
-    hdr[g] = make_int4(lo / NB, lo % NB, n, 0);
-}
-
-// pass 3: scatter the pairs into their bucket, in candidate order: bucket base + pairs of earlier
-// blocks (k_block_scan) + pairs of earlier warps of this block + rank among the warp's lanes.
-__global__ void __launch_bounds__(256)
-k_scatter(const int16_t* __restrict__ pair_k, const float* __restrict__ pair_a, int64_t G, int W,
+// Scatter the pairs into their bucket, in candidate order: bucket base + pairs of earlier CTAs
+// (k_block_scan) + pairs of earlier warps of this CTA + rank among the warp's lanes.  The CTAs of channel
+// row 0 also write the group headers {channel, lag, valid pairs}.
+__global__ void DPE_SIDE128
+k_scatter(const int16_t* __restrict__ pair_k, const float* __restrict__ pair_a, int64_t G, int W, int nbuck,
+          const int32_t* __restrict__ hist, const int32_t* __restrict__ group_base,
           const int64_t* __restrict__ bucket_base, const int32_t* __restrict__ blk_base,
-          int32_t* __restrict__ ent_j, float* __restrict__ ent_a) {
-    extern __shared__ int32_t wcnt[];                      // [8 warps][NB]
+          int32_t* __restrict__ ent_j, float* __restrict__ ent_a, int4* __restrict__ hdr, int64_t max_groups) {
+    extern __shared__ int32_t sm[];                        // [kSortBlock/32][NB] warp counts, then [nbuck+1] group bases
+    constexpr int NW = kSortBlock / 32;
     const int NB = 2 * W + 1;
+    int32_t* wcnt = sm;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 8 * NB; i += blockDim.x) wcnt[i] = 0;
+    for (int i = threadIdx.x; i < NW * NB; i += blockDim.x) wcnt[i] = 0;
+    if (c == 0) {
+        int32_t* gb = sm + NW * NB;
+        for (int i = threadIdx.x; i <= nbuck; i += blockDim.x) gb[i] = group_base[i];
+        __syncthreads();
+        const int total = gb[nbuck];
+        if (total <= max_groups) {
+            for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+                int lo = 0, hi = nbuck - 1;                // last bucket with base <= g
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (gb[mid] <= g) lo = mid; else hi = mid - 1;
+                }
+                const int q = g - gb[lo];
+                const int cnt = hist[lo];
+                const int ng = (cnt + kBfNC - 1) / kBfNC;
+                int n = 0;
+                if (q < ng) { n = cnt - q * kBfNC; if (n > kBfNC) n = kBfNC; }
+                hdr[g] = make_int4(lo / NB, lo % NB, n, 0);
+            }
+        }
+    }
     __syncthreads();
     const int k = (j < G) ? (int)pair_k[(size_t)c * G + j] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, k);
@@ -413,10 +412,13 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
     }
 }
 
-// pass 5: per-candidate score from the pair correlations + fused reductions
-__global__ void __launch_bounds__(kReduceBlock)
+// pass 5: per-candidate score from the pair correlations + fused reductions.  A pair that fell outside
+// the lag window carries NaN in pair_v (k_pair_bins).  WITH_SUMS = 0 (arg-max estimate): the candidate
+// states are not needed per candidate -- 8 B x C + 8 B per candidate instead of 10 B x C + 40 B.
+template <int WITH_SUMS>
+__global__ void __launch_bounds__(kReduceBlock, 6)
 k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
-              const int16_t* __restrict__ pair_k, const float2* __restrict__ pair_v, int lpower,
+              const float2* __restrict__ pair_v, int lpower,
               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
               unsigned int* __restrict__ ticket, double* __restrict__ partial) {
     const EpochDev& e = *ep;
@@ -426,15 +428,14 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     int oow = 0;
     Cand p = {0, 0, 0, 0};
     if (active) {
-        p = cand_ecef(e, grid + 4 * j);
+        if (WITH_SUMS) p = cand_ecef(e, grid + 4 * j);
 #pragma unroll 4
-        for (int c = 0; c < e.C; ++c) {                    // both loads unconditional: 2 x C independent requests in flight
-            const int k = pair_k[(size_t)c * G + j];
-            const float2 v = pair_v[(size_t)c * G + j];    // never written for an out-of-window pair: not used then
-            if (k >= 0) score += mag_pow((double)v.x, (double)v.y, lpower);
+        for (int c = 0; c < e.C; ++c) {
+            const float2 v = __ldcs(&pair_v[(size_t)c * G + j]);   // streamed once
+            if (v.x == v.x) score += mag_pow((double)v.x, (double)v.y, lpower);
             else ++oow;
         }
-        scores[j] = score;
+        __stcs(&scores[j], score);
     }
     block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
     if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
@@ -449,53 +450,38 @@ size_t brute_smem_bytes(int) {
 int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int C = c->epoch_C, NB = 2 * c->W + 1, nbuck = C * NB;
     prof_begin(c, DPE_STAGE_BRUTE_BINS, s);
-    const int nblk = (int)((c->G + 255) / 256);
+    const int nblk = (int)((c->G + kSortBlock - 1) / kSortBlock);
     const size_t hs_bytes = sizeof(int32_t) * nbuck;
     if (sat_mode == DPE_SAT_PER_TIME)
-        k_pair_bins<DPE_SAT_PER_TIME><<<nblk, 256, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
-            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->blk_hist);
+        k_pair_bins<DPE_SAT_PER_TIME><<<nblk, kSortBlock, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
+            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist);
     else
-        k_pair_bins<DPE_SAT_MIDDLE><<<nblk, 256, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
-            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->blk_hist);
+        k_pair_bins<DPE_SAT_MIDDLE><<<nblk, kSortBlock, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
+            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    k_block_scan<<<nbuck, 256, 0, s>>>(c->blk_hist, nblk, c->hist);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
-    k_bucket_scan<<<1, 256, 0, s>>>(c->hist, c->ep, c->W, c->group_base, c->bucket_base, c->n_groups,
-                                    c->max_groups);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
-    k_group_headers<<<(int)((c->max_groups + 255) / 256), 256, sizeof(int32_t) * (nbuck + 1), s>>>(
-        c->hist, c->group_base, c->ep, c->W, reinterpret_cast<int4*>(c->hdr), c->max_groups);
+    k_block_scan<<<nbuck, 256, 0, s>>>(c->blk_hist, nblk, c->hist, nbuck, c->group_base, c->bucket_base, c->n_groups,
+                                       c->max_groups, c->ticket + 1);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     dim3 gs(nblk, C);
-    k_scatter<<<gs, 256, sizeof(int32_t) * 8 * NB, s>>>(c->pair_k, c->pair_a, c->G, c->W, c->bucket_base, c->blk_hist,
-                                                        reinterpret_cast<int32_t*>(c->ent_j), c->ent_a);
+    k_scatter<<<gs, kSortBlock, sizeof(int32_t) * ((kSortBlock / 32) * NB + nbuck + 1), s>>>(
+        c->pair_k, c->pair_a, c->G, c->W, nbuck, c->hist, c->group_base, c->bucket_base, c->blk_hist,
+        reinterpret_cast<int32_t*>(c->ent_j), c->ent_a, reinterpret_cast<int4*>(c->hdr), c->max_groups);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     prof_end(c, s);
     return DPE_OK;
 }
 
-int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
-    int rc;
-    if (!c->have_planes) {
-        if ((rc = launch_brute_planes(c, s))) return rc;
-        c->have_planes = 1;
-    }
-    if (c->sort_valid == 1 + sat_mode) {                   // presorted (maybe on another stream), or sorted earlier this epoch
-        if (c->sort_pending) DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
-        c->sort_pending = 0;
-    } else {
-        if (c->sort_pending) { DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0)); c->sort_pending = 0; }
-        if ((rc = launch_brute_sort(c, sat_mode, s))) return rc;
-        c->sort_valid = 1 + sat_mode;
-    }
+// k_brute alone (the pair sort and the planes are in place)
+int launch_brute_corr(dpe_ctx* c, cudaStream_t s) {
     const size_t smem = brute_smem_bytes(c->H);
-    if (!c->brute_attr_set) {          // per context: the attribute belongs to the device the context lives on
+    if (!c->brute_attr_set) {          // per context: the attributes belong to the device the context lives on
         DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        // the whole unified L1 as shared memory: one carve-out for k_brute and the side kernels that share its SMs
+        DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
         c->brute_attr_set = 1;
     }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
@@ -506,15 +492,48 @@ int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
+int launch_brute_score(dpe_ctx* c, cudaStream_t s) {
     prof_begin(c, DPE_STAGE_BRUTE_SCORE, s);
     const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
-    k_score_pairs<<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_k, c->pair_v, c->cfg.lpower, c->G,
-                                                c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
+    if (c->want_sums)
+        k_score_pairs<1><<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_v, c->cfg.lpower, c->G,
+                                                       c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
+    else
+        k_score_pairs<0><<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_v, c->cfg.lpower, c->G,
+                                                       c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
     prof_end(c, s);
     return DPE_OK;
+}
+
+int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s) {
+    int rc;
+    if (!c->have_planes) {
+        if ((rc = launch_brute_planes(c, s))) return rc;
+        c->have_planes = 1;
+    }
+    if (c->sort_pending) { DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0)); c->sort_pending = 0; }
+    if (c->sort_valid != 1 + sat_mode) {                   // not presorted (maybe on another stream) this epoch
+        if ((rc = launch_brute_sort(c, sat_mode, s))) return rc;
+        c->sort_valid = 1 + sat_mode;
+    }
+    if ((rc = launch_brute_corr(c, s))) return rc;
+    return launch_brute_score(c, s);
+}
+
+int kernel_attr_brute(const char* name, cudaFuncAttributes* a) {
+    DPE_KATTR("k_brute", k_brute);
+    DPE_KATTR("k_pair_bins", k_pair_bins<DPE_SAT_MIDDLE>);
+    DPE_KATTR("k_block_scan", k_block_scan);
+    DPE_KATTR("k_scatter", k_scatter);
+    DPE_KATTR("k_score_pairs", k_score_pairs<0>);
+    DPE_KATTR("k_score_pairs_sums", k_score_pairs<1>);
+    return 0;
 }
 
 }  // namespace dpe

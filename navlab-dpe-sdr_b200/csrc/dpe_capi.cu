@@ -67,9 +67,32 @@ extern "C" {
 const char* dpe_last_error(void) { return g_err; }
 int dpe_abi_version(void) { return DPE_ABI_VERSION; }
 
+// failure after `new dpe_ctx`: free what exists, then report
+#define DPE_CREATE_REQUIRE(cond, code, ...)     \
+    do {                                        \
+        if (!(cond)) {                          \
+            dpe::set_error(__VA_ARGS__);        \
+            dpe_ctx_destroy(c);                 \
+            return (code);                      \
+        }                                       \
+    } while (0)
+#define DPE_CREATE_CUDA(call)                                                            \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            dpe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                 \
+                           cudaGetErrorString(e__));                                     \
+            dpe_ctx_destroy(c);                                                          \
+            return DPE_ECUDA;                                                            \
+        }                                                                                \
+    } while (0)
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_REQUIRE(out && cfg, DPE_EINVAL, "dpe_ctx_create: null argument");
     *out = nullptr;
+    // ---- pure parameter checks: nothing is allocated before all of them pass ----
     DPE_REQUIRE(cfg->abi_version == DPE_ABI_VERSION, DPE_EINVAL, "ABI version %u != %d", cfg->abi_version,
                 DPE_ABI_VERSION);
     DPE_REQUIRE(cfg->S >= 64 && (cfg->S % 2) == 0 && cfg->S <= (1 << 26), DPE_EINVAL,
@@ -82,6 +105,25 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_REQUIRE(cfg->grid_offset >= 0 && cfg->G_total >= cfg->grid_offset + cfg->G, DPE_EINVAL,
                 "grid shard [%lld,+%lld) outside G_total=%lld", (long long)cfg->grid_offset, (long long)cfg->G,
                 (long long)cfg->G_total);
+    const int W = cfg->lag_halfwidth > 0 ? cfg->lag_halfwidth : 32;
+    DPE_REQUIRE(2 * W + 2 < cfg->S, DPE_EINVAL, "lag window wider than the block");
+    const bool brute = (cfg->flags & DPE_FLAG_BRUTE_TILES) != 0;
+    DPE_REQUIRE(!brute || sizeof(int32_t) * ((size_t)cfg->max_chan * (2 * W + 1) + 1 + 4 * (2 * W + 1)) <= 48 * 1024,
+                DPE_EINVAL, "max_chan * (2W+1) too large for the pair sort");
+    int64_t nf = 0;
+    int Wd = 0;
+    if (cfg->Gv > 0) {
+        DPE_REQUIRE(cfg->Gv < (1ll << 31), DPE_EINVAL, "Gv out of range");
+        nf = cfg->n_fft;
+        if (nf <= 0) { nf = 1; while (nf < cfg->S) nf <<= 1; nf *= 8; }    // carrSTot, batchcorrscores.cu:761
+        // the Doppler-bin twiddle index n*m mod N_c is turned into an angle in FP32: exact up to 2^24
+        DPE_REQUIRE((nf & (nf - 1)) == 0 && nf >= cfg->S && nf <= (1 << 24), DPE_EINVAL,
+                    "n_fft=%lld must be a power of two, S <= n_fft <= 2^24 (with a velocity grid the default "
+                    "8*2^ceil(log2 S) limits S to 2^21)", (long long)nf);
+        Wd = cfg->dopp_halfwidth > 0 ? cfg->dopp_halfwidth : 64;
+        DPE_REQUIRE(2 * Wd + 2 < nf, DPE_EINVAL, "Doppler window wider than the spectrum");
+    }
+    DevGuard guard(cfg->device >= 0 ? cfg->device : 0);
     int ndev = 0;
     DPE_CUDA(cudaGetDeviceCount(&ndev));
     DPE_REQUIRE(cfg->device >= 0 && cfg->device < ndev, DPE_EINVAL, "device %d of %d", cfg->device, ndev);
@@ -100,21 +142,27 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     c->S_pad = ((cfg->S + kBfTile - 1) / kBfTile) * kBfTile;
     c->G = cfg->G;
     c->Gv = cfg->Gv;
-    c->W = cfg->lag_halfwidth > 0 ? cfg->lag_halfwidth : 32;
-    DPE_REQUIRE(2 * c->W + 2 < c->S, DPE_EINVAL, "lag window wider than the block");
+    c->W = W;
     c->NL = 2 * c->W + 2;
     c->NLp = ((c->NL + kLagTile - 1) / kLagTile) * kLagTile;
     c->H = ((c->W + 8 + 31) / 32) * 32;
     c->nchunk = (int)((c->S + kCorrChunk - 1) / kCorrChunk);
     c->maxC = cfg->max_chan;
     c->T = cfg->time_dim > 0 ? cfg->time_dim : 1;
+    c->nranks = 1;
+    c->want_sums = 1;
     const size_t C = c->maxC, S = c->S, G = c->G;
-    const bool brute = (cfg->flags & DPE_FLAG_BRUTE_TILES) != 0;
 
-    DPE_ALLOC(c->iq_own, 2 * S + 16);
+    // epoch packet {iq | EpochDev | sat}: device copy + page-locked staging copy
+    c->sat_cap = C * c->T * 8;
+    c->pkt_off_ep = round_up(sizeof(int16_t) * 2 * S + 64, 256);
+    c->pkt_off_sat = c->pkt_off_ep + round_up(sizeof(EpochDev), 256);
+    c->pkt_bytes = c->pkt_off_sat + round_up(sizeof(double) * c->sat_cap, 256);
+    DPE_ALLOC(c->pkt, c->pkt_bytes);
+    c->iq_own = reinterpret_cast<int16_t*>(c->pkt);
+    c->ep = reinterpret_cast<EpochDev*>(c->pkt + c->pkt_off_ep);
+    c->sat = reinterpret_cast<double*>(c->pkt + c->pkt_off_sat);
     DPE_ALLOC(c->ca, DPE_MAX_CHAN * 1024);
-    DPE_ALLOC(c->ep, 1);
-    DPE_ALLOC(c->sat, C * c->T * 8);
     DPE_ALLOC(c->xw, C * S);
     DPE_ALLOC(c->rs, C * S);
     if (cfg->flags & DPE_FLAG_KEEP_CHIP_IDX) DPE_ALLOC(c->chip_idx, C * S);
@@ -136,14 +184,12 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->bx, C * 8 * c->bx_stride);
         DPE_ALLOC(c->brd, C * c->brd_stride);
         const size_t NB = 2 * c->W + 1;
-        DPE_REQUIRE(sizeof(int32_t) * (2 * C * NB + 1) <= 48 * 1024, DPE_EINVAL,
-                    "max_chan * (2W+1) too large for the bucket scan");
         c->max_groups = (int64_t)(C * ((G + kBfNC - 1) / kBfNC + NB * kBfWarps));   // every bucket padded to whole slots
         DPE_ALLOC(c->pair_k, C * G);
         DPE_ALLOC(c->pair_a, C * G);
         DPE_ALLOC(c->pair_v, C * G);
         DPE_ALLOC(c->hist, C * NB);
-        DPE_ALLOC(c->blk_hist, C * NB * ((G + 255) / 256));
+        DPE_ALLOC(c->blk_hist, C * NB * ((G + kSortBlock - 1) / kSortBlock));
         DPE_ALLOC(c->bucket_base, C * NB);
         DPE_ALLOC(c->group_base, C * NB + 1);
         DPE_ALLOC(c->hdr, c->max_groups * 4);
@@ -154,14 +200,8 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->tail_ticket, c->sm_count * kBfWarps);
     }
     if (cfg->Gv > 0) {
-        DPE_REQUIRE(cfg->Gv < (1ll << 31), DPE_EINVAL, "Gv out of range");
-        int64_t nf = cfg->n_fft;
-        if (nf <= 0) { nf = 1; while (nf < c->S) nf <<= 1; nf *= 8; }      // carrSTot, batchcorrscores.cu:761
-        DPE_REQUIRE((nf & (nf - 1)) == 0 && nf >= c->S && nf <= (1 << 26), DPE_EINVAL,
-                    "n_fft must be a power of two >= S");
         c->n_fft = (int32_t)nf;
-        c->Wd = cfg->dopp_halfwidth > 0 ? cfg->dopp_halfwidth : 64;
-        DPE_REQUIRE(2 * c->Wd + 2 < nf, DPE_EINVAL, "Doppler window wider than the spectrum");
+        c->Wd = Wd;
         c->NBd = 2 * c->Wd + 2;
         DPE_ALLOC(c->vgrid, (size_t)cfg->Gv * 4);
         DPE_ALLOC(c->vscores, (size_t)cfg->Gv);
@@ -171,43 +211,49 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->vpart, C * c->nchunk * c->NBd);
         DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
     }
-    c->sat_cap = C * c->T * 8;
-    DPE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->ep_pin), sizeof(EpochDev) * kPinSlots));
-    DPE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->sat_pin), sizeof(double) * c->sat_cap * kPinSlots));
-    for (int i = 0; i < kPinSlots; ++i) DPE_CUDA(cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
-    DPE_CUDA(cudaEventCreateWithFlags(&c->ev_epoch, cudaEventDisableTiming));
-    DPE_CUDA(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
+    DPE_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->ep_pin), sizeof(EpochDev) * kPinSlots));
+    DPE_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->sat_pin), sizeof(double) * c->sat_cap * kPinSlots));
+    DPE_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->pkt_pin), c->pkt_bytes));
+    DPE_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->res_pin), sizeof(double) * 16));
+    for (int i = 0; i < kPinSlots; ++i) DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
+    DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_epoch, cudaEventDisableTiming));
+    DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_grid, cudaEventDisableTiming));
+    DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
+    DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
     if (rc) { dpe_ctx_destroy(c); return rc; }
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) {
-        set_error("ctx_create sync -> %s", cudaGetErrorString(e));
-        dpe_ctx_destroy(c);
-        return DPE_ECUDA;
-    }
+    DPE_CREATE_CUDA(cudaDeviceSynchronize());
     *out = c;
     return DPE_OK;
 }
 
 int dpe_ctx_destroy(dpe_ctx* c) {
     if (!c) return DPE_OK;
-    cudaSetDevice(c->cfg.device);
-    void* ptrs[] = {c->iq_own, c->ca, c->ep, c->sat, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
+    DevGuard guard(c->cfg.device);
+    cudaDeviceSynchronize();
+    if (c->comm) dpe_comm_destroy(c);
+    void* ptrs[] = {c->pkt, c->ca, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
                     c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
-                    c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial};
+                    c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial, c->gathered};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    if (c->ep_pin) {
-        cudaFreeHost(c->ep_pin);
-        cudaFreeHost(c->sat_pin);
-        for (int i = 0; i < kPinSlots; ++i) cudaEventDestroy(c->pin_ev[i]);
-    }
+    if (c->ep_pin) cudaFreeHost(c->ep_pin);
+    if (c->sat_pin) cudaFreeHost(c->sat_pin);
+    if (c->pkt_pin) cudaFreeHost(c->pkt_pin);
+    if (c->res_pin) cudaFreeHost(c->res_pin);
+    for (int i = 0; i < kPinSlots; ++i)
+        if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     if (c->ev_epoch) cudaEventDestroy(c->ev_epoch);
+    if (c->ev_grid) cudaEventDestroy(c->ev_grid);
     if (c->ev_sort) cudaEventDestroy(c->ev_sort);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->prof_ev) {
         for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
@@ -219,6 +265,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
 
 int dpe_grid_set(dpe_ctx* c, const double* enu_dt, int64_t G, void* stream) {
     DPE_REQUIRE(c && enu_dt, DPE_EINVAL, "dpe_grid_set: null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(G == c->G, DPE_EINVAL, "dpe_grid_set: G=%lld, context holds %lld", (long long)G, (long long)c->G);
     if (c->sort_pending) {                         // a presort on another stream still reads the old grid
         DPE_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_sort, 0));
@@ -227,21 +274,29 @@ int dpe_grid_set(dpe_ctx* c, const double* enu_dt, int64_t G, void* stream) {
     c->sort_valid = 0;
     c->have_scores = 0;
     DPE_CUDA(cudaMemcpyAsync(c->grid, enu_dt, sizeof(double) * 4 * G, cudaMemcpyDefault, (cudaStream_t)stream));
+    DPE_CUDA(cudaEventRecord(c->ev_grid, (cudaStream_t)stream));    // a presort on another stream waits for the new grid
+    if ((cudaStream_t)stream != c->own_stream) DPE_CUDA(cudaStreamWaitEvent(c->own_stream, c->ev_grid, 0));
     return DPE_OK;
 }
 
 int dpe_vel_grid_set(dpe_ctx* c, const double* venu_ddt, int64_t Gv, void* stream) {
     DPE_REQUIRE(c && venu_ddt, DPE_EINVAL, "dpe_vel_grid_set: null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->Gv > 0, DPE_ESTATE, "context created without a velocity grid (cfg.Gv = 0)");
     DPE_REQUIRE(Gv == c->Gv, DPE_EINVAL, "dpe_vel_grid_set: Gv=%lld, context holds %lld", (long long)Gv,
                 (long long)c->Gv);
     DPE_CUDA(cudaMemcpyAsync(c->vgrid, venu_ddt, sizeof(double) * 4 * Gv, cudaMemcpyDefault, (cudaStream_t)stream));
+    if ((cudaStream_t)stream != c->own_stream) {
+        DPE_CUDA(cudaEventRecord(c->ev_grid, (cudaStream_t)stream));
+        DPE_CUDA(cudaStreamWaitEvent(c->own_stream, c->ev_grid, 0));
+    }
     c->have_vgrid = 1;
     return DPE_OK;
 }
 
 int dpe_block_stage(dpe_ctx* c, const int16_t* iq, int64_t S, void* stream) {
     DPE_REQUIRE(c && iq, DPE_EINVAL, "dpe_block_stage: null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(S == c->S, DPE_EINVAL, "block of %lld samples, context built for %lld", (long long)S,
                 (long long)c->S);
     cudaPointerAttributes at;
@@ -263,6 +318,7 @@ int dpe_block_stage(dpe_ctx* c, const int16_t* iq, int64_t S, void* stream) {
 int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, unsigned parts,
                        void* stream) {
     DPE_REQUIRE(c && ep, DPE_EINVAL, "dpe_epoch_set: null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(parts && !(parts & ~(DPE_PART_CHANNELS | DPE_PART_GEOMETRY)), DPE_EINVAL, "bad parts mask %u", parts);
     DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
     DPE_REQUIRE(!(parts & DPE_PART_GEOMETRY) || sat_states, DPE_EINVAL, "geometry part without sat_states");
@@ -335,6 +391,7 @@ int dpe_epoch_set(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, voi
 
 int dpe_replica_prepare(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->have_block && (c->have_epoch & DPE_PART_CHANNELS), DPE_ESTATE,
                 "replica_prepare before block_stage / the channel part of epoch_set");
     int rc = launch_prepare(c, (cudaStream_t)stream);
@@ -347,6 +404,7 @@ int dpe_replica_prepare(dpe_ctx* c, void* stream) {
 
 int dpe_correlogram(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->have_prepare, DPE_ESTATE, "correlogram before replica_prepare");
     int rc = launch_correlogram(c, (cudaStream_t)stream);
     if (rc) return rc;
@@ -357,6 +415,7 @@ int dpe_correlogram(dpe_ctx* c, void* stream) {
 
 int dpe_code_scores_set(dpe_ctx* c, const double* cs, int C, void* stream) {
     DPE_REQUIRE(c && cs, DPE_EINVAL, "null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->have_epoch, DPE_ESTATE, "code_scores_set before epoch_set");
     DPE_REQUIRE(C == c->epoch_C, DPE_EINVAL, "C=%d, epoch has %d channels", C, c->epoch_C);
     DPE_CUDA(cudaMemcpyAsync(c->cs, cs, sizeof(double2) * (size_t)C * c->NL, cudaMemcpyDefault,
@@ -368,6 +427,7 @@ int dpe_code_scores_set(dpe_ctx* c, const double* cs, int C, void* stream) {
 
 int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->have_corr, DPE_ESTATE, "score_pos before correlogram");
     DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_pos before the geometry part of epoch_set");
     DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
@@ -391,12 +451,14 @@ int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
 
 int dpe_brute_presort(dpe_ctx* c, int sat_mode, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->cfg.flags & DPE_FLAG_BRUTE_TILES, DPE_ESTATE, "context created without DPE_FLAG_BRUTE_TILES");
     DPE_REQUIRE((c->have_epoch & (DPE_PART_CHANNELS | DPE_PART_GEOMETRY)) == (DPE_PART_CHANNELS | DPE_PART_GEOMETRY),
                 DPE_ESTATE, "brute_presort before both parts of epoch_set");
     DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
     cudaStream_t s = (cudaStream_t)stream;
     DPE_CUDA(cudaStreamWaitEvent(s, c->ev_epoch, 0));          // the parameters this epoch's upload put in place
+    DPE_CUDA(cudaStreamWaitEvent(s, c->ev_grid, 0));           // ... and the grid, should it have been replaced since
     if (c->sort_pending) DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
     int rc = launch_brute_sort(c, sat_mode, s);
     if (rc) return rc;
@@ -408,6 +470,7 @@ int dpe_brute_presort(dpe_ctx* c, int sat_mode, void* stream) {
 
 int dpe_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->have_scores, DPE_ESTATE, "estimate before score_pos");
     DPE_REQUIRE(est_mode == DPE_EST_ARGMAX || est_mode == DPE_EST_WEIGHTED, DPE_EINVAL, "bad est_mode");
     DPE_REQUIRE(!gathered || nranks >= 1, DPE_EINVAL, "nranks must be >= 1");
@@ -416,6 +479,7 @@ int dpe_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, v
 
 int dpe_score_vel(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->Gv > 0 && c->have_vgrid, DPE_ESTATE, "score_vel without a velocity grid");
     DPE_REQUIRE(c->have_prepare && c->have_corr, DPE_ESTATE, "score_vel before replica_prepare / correlogram");
     DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_vel before the geometry part of epoch_set");
@@ -424,6 +488,7 @@ int dpe_score_vel(dpe_ctx* c, void* stream) {
 
 int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
     DPE_REQUIRE(c && out, DPE_EINVAL, "null argument");
+    DevGuard guard(c->cfg.device);
     double r[16];
     DPE_CUDA(cudaMemcpyAsync(r, c->result, sizeof(r), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     DPE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -439,23 +504,170 @@ int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
     return DPE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One whole epoch enqueued on stream `s`: packet upload (rank 0) -> [ncclBroadcast] -> pre-pass ->
+// correlogram -> scoring of this context's shard -> [ncclAllGather of the partials] -> estimate ->
+// [velocity manifold].  No host synchronisation; the pair sort of a brute-force epoch runs on the
+// context's second stream beside the sample pre-pass.
+// ---------------------------------------------------------------------------------------------
+static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                         int score_mode, int est_mode, int with_vel, cudaStream_t s) {
+    DPE_REQUIRE(ep, DPE_EINVAL, "epoch: null parameters");
+    DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
+    DPE_REQUIRE(score_mode == DPE_SCORE_LOOKUP || score_mode == DPE_SCORE_BRUTE, DPE_EINVAL, "bad score_mode %d", score_mode);
+    DPE_REQUIRE(est_mode == DPE_EST_ARGMAX || est_mode == DPE_EST_WEIGHTED, DPE_EINVAL, "bad est_mode");
+    DPE_REQUIRE(score_mode != DPE_SCORE_BRUTE || (c->cfg.flags & DPE_FLAG_BRUTE_TILES), DPE_ESTATE,
+                "context created without DPE_FLAG_BRUTE_TILES");
+    DPE_REQUIRE(!with_vel || (c->Gv > 0 && c->have_vgrid), DPE_ESTATE, "velocity manifold requested without a velocity grid");
+    const bool root = !c->comm || c->rank == 0;
+    const int C = ep->C;
+    const size_t sat_bytes = sizeof(double) * 8 * (size_t)C * c->T;
+    const size_t used = c->pkt_off_sat + sat_bytes;
+    if (c->sort_pending) { DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0)); c->sort_pending = 0; }
+    if (root) {
+        DPE_REQUIRE(iq && sat_states, DPE_EINVAL, "epoch: null block / satellite states on the root rank");
+        for (int i = 0; i < C; ++i) {
+            DPE_REQUIRE(ep->prn[i] >= 1 && ep->prn[i] <= DPE_MAX_CHAN, DPE_EINVAL, "PRN %d out of range", ep->prn[i]);
+            DPE_REQUIRE(ep->fc[i] > 0, DPE_EINVAL, "code frequency of channel %d not positive", i);
+        }
+        EpochDev& h = *reinterpret_cast<EpochDev*>(c->pkt_pin + c->pkt_off_ep);
+        h.C = C;
+        h.doppler_sign = ep->doppler_sign;
+        h.rx_time = ep->rx_time;
+        memcpy(h.center, ep->center, sizeof(h.center));
+        memcpy(h.R, ep->enu2ecef, sizeof(h.R));
+        for (int i = 0; i < C; ++i) {
+            h.prn[i] = ep->prn[i];
+            h.rc_start[i] = ep->rc_start[i]; h.ri_start[i] = ep->ri_start[i];
+            h.fc[i] = ep->fc[i]; h.fi[i] = ep->fi[i];
+            h.cp_start[i] = ep->cp_start[i]; h.cp_ref[i] = ep->cp_ref[i];
+            h.rc_end[i] = ep->rc_end[i]; h.cp_end[i] = ep->cp_end[i]; h.cp_ref_tow[i] = ep->cp_ref_tow[i];
+        }
+        c->ep_host = h;
+        cudaPointerAttributes at;
+        bool sat_dev = cudaPointerGetAttributes(&at, sat_states) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        if (!sat_dev) { cudaGetLastError(); memcpy(c->pkt_pin + c->pkt_off_sat, sat_states, sat_bytes); }
+        cudaError_t e = cudaPointerGetAttributes(&at, iq);
+        const bool iq_dev = (e == cudaSuccess) && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (!iq_dev) {
+            // host block: one page-locked packet, ONE H2D for block + parameters + satellite states
+            memcpy(c->pkt_pin, iq, sizeof(int16_t) * 2 * c->S);
+            DPE_CUDA(cudaMemcpyAsync(c->pkt, c->pkt_pin, used, cudaMemcpyHostToDevice, s));
+            c->iq = c->iq_own;
+        } else {
+            DPE_CUDA(cudaMemcpyAsync(c->pkt + c->pkt_off_ep, c->pkt_pin + c->pkt_off_ep, used - c->pkt_off_ep,
+                                     cudaMemcpyHostToDevice, s));
+            const bool in_place = !c->comm && at.device == c->cfg.device && (reinterpret_cast<uintptr_t>(iq) & 15) == 0;
+            if (in_place) {
+                c->iq = iq;                                   // zero copy
+            } else {
+                DPE_CUDA(cudaMemcpyAsync(c->iq_own, iq, sizeof(int16_t) * 2 * c->S, cudaMemcpyDefault, s));
+                c->iq = c->iq_own;
+            }
+        }
+        if (sat_dev) DPE_CUDA(cudaMemcpyAsync(c->sat, sat_states, sat_bytes, cudaMemcpyDeviceToDevice, s));
+    } else {
+        c->iq = c->iq_own;
+        c->ep_host.C = C;
+    }
+    int rc;
+    if (c->comm && (rc = comm_broadcast(c, c->pkt, used, s))) return rc;
+    DPE_CUDA(cudaEventRecord(c->ev_epoch, s));
+    c->epoch_C = C;
+    c->have_block = 1;
+    c->have_epoch = DPE_PART_CHANNELS | DPE_PART_GEOMETRY;
+    c->have_prepare = c->have_corr = c->have_scores = 0;
+    c->sort_valid = 0;
+    const int sat_mode = (est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
+    if (score_mode == DPE_SCORE_BRUTE && (rc = dpe_brute_presort(c, sat_mode, c->aux_stream))) return rc;
+    if ((rc = dpe_replica_prepare(c, s))) return rc;
+    if ((rc = dpe_correlogram(c, s))) return rc;
+    c->want_sums = (est_mode == DPE_EST_WEIGHTED);     // an arg-max epoch needs no per-candidate sum s*x
+    rc = dpe_score_pos(c, score_mode, sat_mode, s);
+    c->want_sums = 1;
+    if (rc) return rc;
+    if (c->comm) {
+        if ((rc = comm_allgather(c, c->partial, c->gathered, kPartialLen, s))) return rc;
+        if ((rc = launch_estimate(c, est_mode, c->gathered, c->nranks, s))) return rc;
+    } else if ((rc = launch_estimate(c, est_mode, nullptr, 1, s))) {
+        return rc;
+    }
+    if (with_vel && (rc = dpe_score_vel(c, s))) return rc;
+    return DPE_OK;
+}
+
+static void unpack_result(const double* r, dpe_result* out) {
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < 8; ++i) out->z[i] = r[i];
+    out->max_score = r[8];
+    out->sum_score = r[9];
+    out->argmax = (int64_t)r[10];
+    out->out_of_window = (int64_t)r[11];
+    out->vel_max_score = r[12];
+    out->vel_argmax = (int64_t)r[13];
+    out->vel_out_of_window = (int64_t)r[14];
+}
+
 int dpe_epoch_run(dpe_ctx* c, const int16_t* iq_host, const dpe_epoch* ep, const double* sat_states,
                   int score_mode, int est_mode, int with_vel, dpe_result* out, void* stream) {
-    int rc;
-    if ((rc = dpe_block_stage(c, iq_host, c ? c->S : 0, stream))) return rc;
-    if ((rc = dpe_epoch_set(c, ep, sat_states, stream))) return rc;
-    const int sat_mode = (est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
-    if (score_mode == DPE_SCORE_BRUTE && (c->cfg.flags & DPE_FLAG_BRUTE_TILES)) {
-        // the pair sort needs the parameters only: run it beside the sample pre-pass
-        if (!c->aux_stream) DPE_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-        if ((rc = dpe_brute_presort(c, sat_mode, c->aux_stream))) return rc;
-    }
-    if ((rc = dpe_replica_prepare(c, stream))) return rc;
-    if ((rc = dpe_correlogram(c, stream))) return rc;
-    if ((rc = dpe_score_pos(c, score_mode, sat_mode, stream))) return rc;
-    if ((rc = dpe_estimate(c, est_mode, nullptr, 1, stream))) return rc;
-    if (with_vel && (rc = dpe_score_vel(c, stream))) return rc;
+    DPE_REQUIRE(c && out, DPE_EINVAL, "dpe_epoch_run: null argument");
+    DPE_REQUIRE(!c->inflight, DPE_ESTATE, "dpe_epoch_run while a submitted epoch is in flight");
+    DevGuard guard(c->cfg.device);
+    int rc = enqueue_epoch(c, iq_host, ep, sat_states, score_mode, est_mode, with_vel, (cudaStream_t)stream);
+    if (rc) return rc;
     return dpe_result_fetch(c, out, stream);
+}
+
+int dpe_epoch_submit(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                     int score_mode, int est_mode, int with_vel) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(!c->inflight, DPE_ESTATE, "dpe_epoch_submit: collect the previous epoch first");
+    DevGuard guard(c->cfg.device);
+    cudaStream_t s = c->own_stream;
+    int rc = enqueue_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s);
+    if (rc) return rc;
+    DPE_CUDA(cudaMemcpyAsync(c->res_pin, c->result, sizeof(double) * 16, cudaMemcpyDeviceToHost, s));
+    DPE_CUDA(cudaEventRecord(c->ev_done, s));
+    c->inflight = 1;
+    return DPE_OK;
+}
+
+int dpe_epoch_collect(dpe_ctx* c, dpe_result* out) {
+    DPE_REQUIRE(c && out, DPE_EINVAL, "null argument");
+    DPE_REQUIRE(c->inflight, DPE_ESTATE, "dpe_epoch_collect without a submitted epoch");
+    DevGuard guard(c->cfg.device);
+    c->inflight = 0;
+    DPE_CUDA(cudaEventSynchronize(c->ev_done));
+    unpack_result(c->res_pin, out);
+    return DPE_OK;
+}
+
+int dpe_epoch_pending(dpe_ctx* c) { return c ? c->inflight : 0; }
+
+int dpe_epoch_run_dist(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                       int score_mode, int est_mode, int with_vel, dpe_result* out) {
+    int rc = dpe_epoch_submit(c, iq, ep, sat_states, score_mode, est_mode, with_vel);
+    if (rc) return rc;
+    return dpe_epoch_collect(c, out);
+}
+
+void* dpe_ctx_stream(dpe_ctx* c) { return c ? (void*)c->own_stream : nullptr; }
+
+int dpe_kernel_attr(const char* kernel, int* regs, int* smem_bytes, int* max_threads) {
+    DPE_REQUIRE(kernel, DPE_EINVAL, "null argument");
+    cudaFuncAttributes a;
+    memset(&a, 0, sizeof(a));
+    if (!(kernel_attr_prepare(kernel, &a) || kernel_attr_score(kernel, &a) || kernel_attr_brute(kernel, &a) ||
+          kernel_attr_vel(kernel, &a))) {
+        cudaGetLastError();
+        set_error("dpe_kernel_attr: no kernel '%s' (or no device)", kernel);
+        return DPE_EINVAL;
+    }
+    if (regs) *regs = a.numRegs;
+    if (smem_bytes) *smem_bytes = (int)a.sharedSizeBytes;
+    if (max_threads) *max_threads = a.maxThreadsPerBlock;
+    return DPE_OK;
 }
 
 const void* dpe_dev_ptr(dpe_ctx* c, int which) {
@@ -481,6 +693,7 @@ const void* dpe_dev_ptr(dpe_ctx* c, int which) {
 
 int dpe_debug_channel_flags(dpe_ctx* c, int32_t* idx_next, int32_t* no_flip, int C) {
     DPE_REQUIRE(c && idx_next && no_flip, DPE_EINVAL, "null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(C >= 1 && C <= c->maxC, DPE_EINVAL, "bad C");
     DPE_CUDA(cudaDeviceSynchronize());
     DPE_CUDA(cudaMemcpy(idx_next, c->idx_next, sizeof(int32_t) * C, cudaMemcpyDeviceToHost));
@@ -491,6 +704,7 @@ int dpe_debug_channel_flags(dpe_ctx* c, int32_t* idx_next, int32_t* no_flip, int
 int dpe_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, int64_t* f_idx, double* alpha,
                    void* stream) {
     DPE_REQUIRE(c && f_idx && alpha, DPE_EINVAL, "null argument");
+    DevGuard guard(c->cfg.device);
     DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "debug_bins before the geometry part of epoch_set");
     DPE_REQUIRE(i0 >= 0 && n >= 1 && i0 + n <= c->G, DPE_EINVAL, "candidate range outside the grid");
     const size_t cnt = (size_t)n * c->epoch_C;
@@ -507,6 +721,7 @@ int dpe_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, int64_t* f_i
 
 int dpe_debug_read(dpe_ctx* c, int which, size_t offset, void* dst, size_t nbytes) {
     DPE_REQUIRE(c && dst, DPE_EINVAL, "null argument");
+    DevGuard guard(c->cfg.device);
     const char* p = static_cast<const char*>(dpe_dev_ptr(c, which));
     DPE_REQUIRE(p, DPE_ESTATE, "buffer %d not allocated", which);
     DPE_CUDA(cudaDeviceSynchronize());
@@ -548,6 +763,7 @@ int dpe_device_count(void) {
 
 int dpe_profile_enable(dpe_ctx* c, int on) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
     if (on && !c->prof_ev) {
         c->prof_ev = new (std::nothrow) cudaEvent_t[2 * kProfMax];
         c->prof_stage = new (std::nothrow) int[kProfMax];
@@ -561,6 +777,7 @@ int dpe_profile_enable(dpe_ctx* c, int on) {
 
 int dpe_profile_read(dpe_ctx* c, double* ms, int64_t* count) {
     DPE_REQUIRE(c && ms && count, DPE_EINVAL, "null argument");
+    DevGuard guard(c->cfg.device);
     DPE_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < c->prof_n; ++i) {
         float t = 0.f;
@@ -574,6 +791,7 @@ int dpe_profile_read(dpe_ctx* c, double* ms, int64_t* count) {
 
 int64_t dpe_brute_pairs(dpe_ctx* c) {
     if (!c || !c->hist) return -1;
+    DevGuard guard(c->cfg.device);
     const int n = c->epoch_C * (2 * c->W + 1);
     int32_t* h = new (std::nothrow) int32_t[n];
     if (!h) return -1;

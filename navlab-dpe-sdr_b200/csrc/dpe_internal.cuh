@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/dpe_b200.h"
 
 // utils/inc/consthelper.h:5-27 of the reference
@@ -38,7 +39,8 @@ namespace dpe {
 constexpr int kCorrChunk = 1024;       // samples per partial-correlogram block
 constexpr int kLagTile = 8;            // lags per thread in the correlogram kernel
 constexpr int kPartialLen = DPE_PARTIAL_LEN;
-constexpr int kReduceBlock = 256;
+constexpr int kReduceBlock = 128;
+constexpr int kSortBlock = 128;        // candidates per CTA of the pair sort (k_pair_bins / k_scatter)
 constexpr int kProfMax = 8192;
 constexpr int kPinSlots = 8;
 
@@ -50,6 +52,13 @@ constexpr int kBfTile = 1024;          // samples per TMA stage
 constexpr int kBfWarps = 8;            // consumer warps per CTA
 constexpr int kBfStages = 4;            // TMA stages of 20 KB (sample tile + replica tile)
 constexpr int kBfLag = 1;               // a stage is refilled this many tiles after its release (8 / 4: no gain)
+
+// Every kernel except k_brute is a "side" kernel: 128 threads x <= 80 registers or 256 threads x <= 40
+// registers (10 240 registers), so that one CTA of it fits on an SM beside the persistent k_brute CTA
+// (256 threads x 216 registers = 55 296 of 65 536).  With two contexts in flight the pre-pass, the pair
+// sort and the reductions of one epoch then run UNDER the k_brute of the other.
+#define DPE_SIDE128 __launch_bounds__(128, 6)
+#define DPE_SIDE256 __launch_bounds__(256, 6)
 
 // Device copy of the per-epoch parameters (+ values derived on the device).
 struct EpochDev {
@@ -79,10 +88,13 @@ struct dpe_ctx {
     int32_t maxC, T;
     int sm_count;
     // device buffers
-    int16_t* iq_own; const int16_t* iq;
+    // epoch packet: {iq int16[2S] | EpochDev | sat double[maxC][T][8]} -- one H2D / one ncclBroadcast per epoch
+    unsigned char* pkt; unsigned char* pkt_pin;
+    size_t pkt_off_ep, pkt_off_sat, pkt_bytes;
+    int16_t* iq_own; const int16_t* iq;    // iq_own = pkt
     int8_t* ca;
-    dpe::EpochDev* ep;
-    double* sat;                       // [C][T][8]
+    dpe::EpochDev* ep;                 // = pkt + pkt_off_ep
+    double* sat;                       // = pkt + pkt_off_sat, [C][T][8]
     float2* xw; int8_t* rs; int16_t* chip_idx;
     int32_t* idx_next; int32_t* no_flip;
     double2* cpart; double2* cs;
@@ -116,9 +128,19 @@ struct dpe_ctx {
     int have_planes;                   // brute-force planes match the current prepare + correlogram
     int sort_valid;                    // 0, or 1 + sat_mode the brute-force work lists were built for (this epoch)
     int sort_pending;                  // a presort on another stream has not been waited for yet
-    cudaEvent_t ev_epoch, ev_sort;     // epoch upload done / presort done
+    cudaEvent_t ev_epoch, ev_grid, ev_sort;   // epoch upload done / grid upload done / presort done
     cudaStream_t aux_stream;           // dpe_epoch_run's own presort stream (created on first use)
     int64_t launches;
+    int want_sums;                     // k_score_pairs accumulates sum s*x (0 only inside an arg-max dpe_epoch_submit)
+    // asynchronous epochs (dpe_epoch_submit / dpe_epoch_collect)
+    cudaStream_t own_stream;
+    cudaEvent_t ev_done;
+    double* res_pin;                   // page-locked mirror of `result` [16]
+    int inflight;
+    // multi-GPU
+    void* comm;                        // ncclComm_t
+    int nranks, rank;
+    double* gathered;                  // [nranks][kPartialLen]
     dpe::EpochDev ep_host;
     // page-locked staging ring for the per-epoch uploads (no implicit stream sync, safe reuse)
     dpe::EpochDev* ep_pin; double* sat_pin; cudaEvent_t pin_ev[dpe::kPinSlots]; int pin_next; size_t sat_cap;
@@ -150,6 +172,26 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s);
 int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
+int launch_brute_corr(dpe_ctx* c, cudaStream_t s);
+int launch_brute_score(dpe_ctx* c, cudaStream_t s);
+// cudaFuncGetAttributes of a kernel by name, one lookup per translation unit (1 = found)
+int kernel_attr_prepare(const char* name, cudaFuncAttributes* a);
+int kernel_attr_score(const char* name, cudaFuncAttributes* a);
+int kernel_attr_brute(const char* name, cudaFuncAttributes* a);
+int kernel_attr_vel(const char* name, cudaFuncAttributes* a);
+#define DPE_KATTR(kname, sym) if (!strcmp(name, kname)) return cudaFuncGetAttributes(a, sym) == cudaSuccess
+// NCCL (dlopen'ed, dpe_comm.cu)
+int comm_broadcast(dpe_ctx* c, void* buf, size_t bytes, cudaStream_t s);
+int comm_allgather(dpe_ctx* c, const double* send, double* recv, size_t count, cudaStream_t s);
+// RAII: bind the context's device for the duration of an extern "C" entry, restore the caller's on exit
+struct DevGuard {
+    int prev, dev;
+    explicit DevGuard(int d) : prev(-1), dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
 int launch_brute_planes(dpe_ctx* c, cudaStream_t s);
 int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_vel(dpe_ctx* c, cudaStream_t s);

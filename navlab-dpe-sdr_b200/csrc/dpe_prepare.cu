@@ -61,7 +61,7 @@ __device__ __forceinline__ int nav_edge_index(const EpochDev& e, int c, double f
 // the chip index and of the wiped samples does not survive FP32: t*fc ~ 2e4
 // chips, fi*t ~ 1e2 cycles), FP32 results.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE128
 k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
           const EpochDev* __restrict__ ep, double fs, int S, int S_pad,
           float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
@@ -126,7 +126,7 @@ k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
 // copy s read at element offset 8 q: 16-byte aligned for the TMA bulk copy and in
 // phase with the float4 skew for every lag.  One thread per element pair.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE256
 k_sample_planes(const float2* __restrict__ xw, const EpochDev* __restrict__ ep, int S, int n_elem, int H,
                 float* __restrict__ bx, int64_t bx_stride) {
     const int c = blockIdx.y, s = blockIdx.z;
@@ -148,7 +148,7 @@ k_sample_planes(const float2* __restrict__ xw, const EpochDev* __restrict__ ep, 
 // Part A = samples before the nav-bit edge, part B = from the edge on, so that
 // no-flip = A + B and flipped = A - B without a second pass.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE128
 k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
                const int32_t* __restrict__ idx_next, const EpochDev* __restrict__ ep,
                int S, int W, int NLp, int nchunk, double2* __restrict__ cpart) {
@@ -177,7 +177,7 @@ k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
     if (!(edge > 0 && edge < S)) edge = S;           // no edge in block: everything is part A
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_lag_runs = NLp / kLagTile;
-    for (int lr = warp; lr < n_lag_runs; lr += 8) {
+    for (int lr = warp; lr < n_lag_runs; lr += (int)(blockDim.x >> 5)) {
         float2 accA[kLagTile], accB[kLagTile];
 #pragma unroll
         for (int l = 0; l < kLagTile; ++l) { accA[l] = make_float2(0.f, 0.f); accB[l] = accA[l]; }
@@ -253,7 +253,7 @@ __device__ __forceinline__ void sum_chunks(const double2* __restrict__ cpart, in
         for (int k = 0; k < 4; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE256
 k_corr_finalize(const double2* __restrict__ cpart, const int32_t* __restrict__ idx_next,
                 const EpochDev* __restrict__ ep, int S, int W, int NL, int NLp,
                 int nchunk, double2* __restrict__ cs, int32_t* __restrict__ no_flip) {
@@ -281,7 +281,7 @@ k_corr_finalize(const double2* __restrict__ cpart, const int32_t* __restrict__ i
 // k_replica_rd: chosen replica (flip applied) by position pair for the brute-force kernel:
 // (d[p], d[p+1], r[p], r[p+1]) with d[p] = r[(p-1) mod S] - r[p], so that the blended chip of a
 // candidate is r + alpha d; zero beyond S (the padded tail of the last tile contributes nothing).
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE256
 k_replica_rd(const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
              const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep,
              int S, int S_pad, float* __restrict__ brd, int64_t brd_stride) {
@@ -318,10 +318,10 @@ int launch_gen_ca(dpe_ctx* c, cudaStream_t s) {
 int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S;
     const int S4 = ((S + 3) / 4) * 4;
-    dim3 grid((S4 / 4 + 255) / 256, c->epoch_C);
+    dim3 grid((S4 / 4 + 127) / 128, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
     if (c->Gv > 0) { int rc = launch_dc_sum(c, s); if (rc) return rc; }
-    k_prepare<<<grid, 256, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, S4, c->xw, c->rs, c->chip_idx, c->idx_next,
+    k_prepare<<<grid, 128, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, S4, c->xw, c->rs, c->chip_idx, c->idx_next,
                                    c->Gv > 0 ? c->dc_sum : nullptr, c->Gv > 0 ? c->bb : nullptr);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
@@ -336,7 +336,7 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
                         (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float);
     dim3 grid(c->nchunk, c->epoch_C);
     prof_begin(c, DPE_STAGE_CORRELOGRAM, s);
-    k_corr_partial<<<grid, 256, smem, s>>>(c->xw, c->rs, c->idx_next, c->ep, S, c->W, c->NLp,
+    k_corr_partial<<<grid, 128, smem, s>>>(c->xw, c->rs, c->idx_next, c->ep, S, c->W, c->NLp,
                                            c->nchunk, c->cpart);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
@@ -363,6 +363,16 @@ int launch_brute_planes(dpe_ctx* c, cudaStream_t s) {
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;
+}
+
+int kernel_attr_prepare(const char* name, cudaFuncAttributes* a) {
+    DPE_KATTR("k_gen_ca", k_gen_ca);
+    DPE_KATTR("k_prepare", k_prepare);
+    DPE_KATTR("k_sample_planes", k_sample_planes);
+    DPE_KATTR("k_corr_partial", k_corr_partial);
+    DPE_KATTR("k_corr_finalize", k_corr_finalize);
+    DPE_KATTR("k_replica_rd", k_replica_rd);
+    return 0;
 }
 
 }  // namespace dpe

@@ -59,7 +59,7 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
 
 // Bins only (parity tests: "code-phase bins bit-exact").
 template <int SAT_MODE>
-__global__ void k_debug_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
+__global__ void __launch_bounds__(256) k_debug_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
                              const double* __restrict__ sat, double fs, int S, int W, int T,
                              int64_t i0, int64_t n, int64_t grid_offset, int64_t* __restrict__ f_idx,
                              double* __restrict__ alpha) {
@@ -150,6 +150,12 @@ int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStrea
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;
+}
+
+int kernel_attr_score(const char* name, cudaFuncAttributes* a) {
+    DPE_KATTR("k_score_lookup", k_score_lookup<DPE_SAT_MIDDLE>);
+    DPE_KATTR("k_finalize", k_finalize);
+    return 0;
 }
 
 }  // namespace dpe

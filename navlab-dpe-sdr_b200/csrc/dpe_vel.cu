@@ -16,7 +16,7 @@
 namespace dpe {
 
 // integer sum of the block (exact; the reference reduces doubles with thrust, :1065)
-__global__ void __launch_bounds__(256) k_dc_sum(const int16_t* __restrict__ iq, int S, long long* __restrict__ out) {
+__global__ void DPE_SIDE256 k_dc_sum(const int16_t* __restrict__ iq, int S, long long* __restrict__ out) {
     long long si = 0, sq = 0;
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < S; n += gridDim.x * blockDim.x) {
         const short2 v = reinterpret_cast<const short2*>(iq)[n];
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_dc_sum(const int16_t* __restrict__ iq, 
 // Twiddles: lane handles samples n0 + lane + 32 i; exp(-j 2 pi n m / N_c) is evaluated exactly
 // (integer n*m mod N_c -> sincospif) every 8th step and advanced by the exact 32-sample rotation in
 // between (7 complex multiplies: < 5e-7 relative drift).
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE256
 k_carr_partial(const float2* __restrict__ zw, const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
                const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
                int n_fft, int nchunk, double2* __restrict__ vpart) {
@@ -92,7 +92,7 @@ k_carr_partial(const float2* __restrict__ zw, const int8_t* __restrict__ rs, con
 }
 
 // one warp per bin, lanes stride the chunks, xor-tree (fixed order)
-__global__ void __launch_bounds__(256)
+__global__ void DPE_SIDE256
 k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ ep, int NBd,
                 int nchunk, double2* __restrict__ carr) {
     const int c = blockIdx.x;
@@ -115,7 +115,7 @@ k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ 
 
 // BCM_VelMeasML with the arg-max fused (batchcorrmanifold.cu:1896-1962); partial layout as the
 // position kernels' (sum s*v, sum s, max, argmax, out-of-window).
-__global__ void __launch_bounds__(kReduceBlock)
+__global__ void __launch_bounds__(kReduceBlock, 6)
 k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
             double* __restrict__ vscores, double* __restrict__ blk_partial, unsigned int* __restrict__ ticket,
@@ -213,6 +213,14 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     prof_end(c, s);
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;
+}
+
+int kernel_attr_vel(const char* name, cudaFuncAttributes* a) {
+    DPE_KATTR("k_dc_sum", k_dc_sum);
+    DPE_KATTR("k_carr_partial", k_carr_partial);
+    DPE_KATTR("k_carr_finalize", k_carr_finalize);
+    DPE_KATTR("k_score_vel", k_score_vel);
+    return 0;
 }
 
 }  // namespace dpe
