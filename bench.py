@@ -7,11 +7,22 @@ A "step" is one 20 ms epoch of the hot path over one synthetic block:
     ->  sum over PRNs, arg-max / score-weighted fix.
 metric = candidate-PRN correlations per second (BASELINE.json), whole job over all ranks.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload demo|c3|c4|tiny] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload demo|c3|c4|c5|tiny]
+                    [--configs c3,c4,c5|none] [--impl reference]
 
-N > 1 (torchrun, one rank per GPU): the candidate grid is sharded in contiguous index ranges,
-rank 0 broadcasts the 20 ms block over NCCL, every rank scores its shard, the per-rank partial
-estimates are all-gathered and reduced (lowest global index wins arg-max ties).
+Every epoch is ONE C-ABI call pair, dpe_epoch_submit / dpe_epoch_collect (include/dpe_b200.h), at
+every N.  N > 1 (torchrun, one rank per GPU): the candidate grid is sharded in contiguous index
+ranges; inside the library rank 0 uploads one packet {block, parameters, satellite states}, NCCL
+broadcasts it, every rank scores its shard, the 16-double partials are all-gathered and reduced on
+every rank (lowest global index wins arg-max ties) -- no Python between the stages.  Two contexts
+per rank alternate, so the pre-pass / pair sort / reductions of one epoch run under the k_brute of
+the other (the side kernels are sized to share an SM with k_brute).
+
+`value`   K pipelined epochs, inputs resident in HBM, one CUDA-event bracket around all K.
+`e2e`     the same with HOST buffers (page-locked block + parameters H2D, result D2H per epoch).
+`latency` one epoch at a time (no overlap), L2 flushed between epochs, per-stage event brackets:
+          the k_brute duration used for `roofline` comes from here.
+`configs` sub-records for the other BASELINE.json workloads (c3, c4; c5 at N = 8), same code path.
 
 --impl reference: the reference's CPU DPE path (NumPy restatement of PyGNSS / CUDARecv in
 oracle/, the one place outside tests where oracle/ may be executed) on the host cores.
@@ -37,20 +48,21 @@ WORKLOADS = {
     "c4": dict(fs=10.0e6, prns="12", grid=("uniform", 51, (2.0, 2.0, 2.0, 2.0)),
                desc="synthetic L1 C/A 10 MHz, 12 PRNs, uniform 51^4 grid (6765201 candidates)"),
     "c5": dict(fs=2.5e6, prns="8", grid=("uniform", 21, (5.0, 5.0, 5.0, 6.0)), streams=256,
-               desc="256 independent synthetic receiver streams, 2.5 MHz, 8 PRNs, uniform 21^4 grid each "
-                    "(streams sharded over ranks, no collective: replicas)"),
+               desc="256 independent synthetic receiver streams (seeds 20180704+k), 2.5 MHz, 8 PRNs, uniform 21^4 "
+                    "grid each (streams sharded over ranks, no collective: replicas)"),
     "tiny": dict(fs=2.5e6, prns="8", grid=("uniform", 9, (5.0, 5.0, 5.0, 6.0)),
                  desc="synthetic 2.5 MHz, 8 PRNs, 9^4 grid (CI-sized)"),
 }
 FLOP_PER_SAMPLE_PAIR = 6.0     # 1 blend FMA + 2 accumulate FMAs per (candidate, PRN, sample); DESIGN.md section 4
+SEED0 = 20180704
 
 
-def build_workload(name):
+def build_workload(name, seed=SEED0):
     import dpe_pkg
     synth = dpe_pkg.submodule("synth")
     w = WORKLOADS[name]
     prns = synth.PRNS_8 if w["prns"] == "8" else synth.PRNS_12
-    sc = synth.Scenario(synth.ScenarioConfig(fs=w["fs"], prns=prns))
+    sc = synth.Scenario(synth.ScenarioConfig(fs=w["fs"], prns=prns, seed=seed))
     if w["grid"] == "spread25":
         grid = synth.spread_grid()
         tg = 6.0 * synth.spread_axis()
@@ -66,6 +78,19 @@ def epoch_for_block(sc, b, tg, offset=(4.0, -3.0, 2.0, 5.0)):
     return sc.epoch_inputs(b, center=center, time_grid=tg)
 
 
+def config_for(args, workload=None):
+    """The `config` object: identical in both arms (ours / --impl reference) for the same command line."""
+    name = workload or args.workload
+    w = WORKLOADS[name]
+    fs = w["fs"]
+    S = int(round(fs * 0.02))
+    C = 8 if w["prns"] == "8" else 12
+    n = 25 if w["grid"] == "spread25" else w["grid"][1]
+    return dict(workload="%s: %s" % (name, w["desc"]), S=S, prns=C, candidates=n ** 4, streams=w.get("streams", 1),
+                path=args.path, estimate=args.estimate,
+                unit_of_work="one candidate-PRN pair scored per 20 ms epoch")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -74,7 +99,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.p = None
-        self.path = "/tmp/dpe_clocks_%d.csv" % os.getpid()
+        self.path = "/tmp/dpe_clocks_%d_%d.csv" % (os.getpid(), int(time.time() * 1e3) % 100000)
         try:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
@@ -109,263 +134,386 @@ class ClockSampler:
             busy = [s for s in sm if s > 0.5 * max(sm)] or sm
             out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
                        samples=len(sm))
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
         return out
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import dpe_pkg
-    capi = dpe_pkg.submodule("capi")
+class Rig:
+    """torch / torch.distributed plumbing shared by every measurement of one bench run (timing barrier,
+    max over ranks, exchange of the NCCL unique ids).  The data path itself never touches torch."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import dpe_pkg
+        self.torch, self.dist = torch, dist
+        self.capi = dpe_pkg.submodule("capi")
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+        self.flush_stream = torch.cuda.Stream(device=self.dev)
 
-    sc, grid, tg = build_workload(args.workload)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def unique_id(self):
+        """ncclGetUniqueId on rank 0 (through the library), shipped to the other ranks."""
+        t = self.torch.zeros(self.capi.DPE_COMM_ID_BYTES, dtype=self.torch.uint8, device=self.dev)
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(self.capi.comm_unique_id()), dtype=self.torch.uint8))
+        self.dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure(rig, args, workload, steps, warmup, with_latency=True, with_e2e=True, with_other=False):
+    """All numbers of one workload on this rank set.  Returns a dict on every rank."""
+    torch, capi = rig.torch, rig.capi
+    world, rank, dev = rig.world, rig.rank, rig.dev
+    streams = WORKLOADS[workload].get("streams", 0)          # c5: independent receivers, sharded by stream
+    sc, grid, tg = build_workload(workload)
     G_total, C, S, T = grid.shape[0], sc.C, sc.S, len(tg)
-    streams = WORKLOADS[args.workload].get("streams", 0)          # c5: independent receivers, sharded by stream
     if streams:
         lo, hi = 0, G_total
-        my_streams = len(range(rank, streams, world))
+        my_streams = list(range(rank, streams, world))
     else:
         per = (G_total + world - 1) // world
         lo, hi = min(rank * per, G_total), min((rank + 1) * per, G_total)
+        my_streams = [0]
     shard = np.ascontiguousarray(grid[lo:hi])
     score_mode = capi.SCORE_LOOKUP if args.path == "lookup" else capi.SCORE_BRUTE
     est_mode = capi.EST_WEIGHTED if args.estimate == "weighted" else capi.EST_ARGMAX
-    sat_mode = capi.SAT_PER_TIME if est_mode == capi.EST_WEIGHTED else capi.SAT_MIDDLE
+    use_comm = world > 1 and not streams
+    W = args.lag_halfwidth
 
-    ctx = capi.Context(fs=sc.cfg.fs, S=S, max_chan=C, G=hi - lo, time_dim=T, lag_halfwidth=args.lag_halfwidth,
-                       flags=capi.FLAG_BRUTE_TILES, device=local, grid_offset=lo, G_total=G_total)
-    ctx.grid_set(shard)
-    n_blocks = 8 if streams else 4
-    blocks_host = [torch.from_numpy(sc.block(b).copy()).pin_memory() for b in range(n_blocks)]
-    blocks_dev = [b.to(dev) for b in blocks_host]                 # resident inputs for `value`
-    epochs = [epoch_for_block(sc, b, tg) for b in range(n_blocks)]
-    ep_structs = [capi.make_epoch(e) for e in epochs]
-    sats = [np.ascontiguousarray(e["sat_states"]) for e in epochs]
-    stream = torch.cuda.current_stream().cuda_stream
-    aux = torch.cuda.Stream(device=dev)                            # the pair sort runs beside the sample pre-pass
-    gathered = torch.zeros(world * capi.DPE_PARTIAL_LEN, dtype=torch.float64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    recv = torch.empty(2 * S, dtype=torch.int16, device=dev)
-    recv_u8 = recv.view(torch.uint8)                               # NCCL has no int16: broadcast the bytes
+    depth = max(1, args.depth)
+    ctxs = []
+    for d in range(depth):
+        ctx = capi.Context(fs=sc.cfg.fs, S=S, max_chan=C, G=hi - lo, time_dim=T, lag_halfwidth=W,
+                           flags=capi.FLAG_BRUTE_TILES, device=rig.local, grid_offset=lo, G_total=G_total)
+        ctx.grid_set(shard)
+        if use_comm:
+            ctx.comm_init(world, rank, rig.unique_id())
+        ctxs.append(ctx)
+    torch.cuda.synchronize()
 
-    def one_stream_epoch(b, host):
-        if host:
-            return ctx.epoch_run(blocks_host[b], ep_structs[b], sats[b], score_mode, est_mode, 0, stream)
-        ctx.block_stage(blocks_dev[b], stream)
-        ctx.epoch_set(ep_structs[b], sats[b], stream)
-        if score_mode == capi.SCORE_BRUTE:
-            ctx.brute_presort(sat_mode, aux.cuda_stream)
-        ctx.replica_prepare(stream)
-        ctx.correlogram(stream)
-        ctx.score_pos(score_mode, sat_mode, stream)
-        ctx.estimate(est_mode, None, 1, stream)
+    # inputs: `n_in` distinct (block, epoch parameters) sets; c5: one per stream this rank owns (own seed each)
+    if streams:
+        scen = [build_workload(workload, SEED0 + k)[0] for k in my_streams]
+        inputs = [(s_.block(0), epoch_for_block(s_, 0, tg)) for s_ in scen]
+    else:
+        n_in = 8 if S <= 60000 else 3
+        inputs = [(sc.block(b), epoch_for_block(sc, b, tg)) for b in range(n_in)]
+    blocks_host = [torch.from_numpy(b.copy()).pin_memory() for b, _ in inputs]
+    need_dev = rank == 0 or not use_comm
+    blocks_dev = [b.to(dev) if need_dev else None for b in blocks_host]
+    eps = [capi.make_epoch(e) for _, e in inputs]
+    sats = [np.ascontiguousarray(e["sat_states"]) for _, e in inputs]
+    n_in = len(inputs)
+    epochs_per_step = len(my_streams)
 
-    def step_resident(i):
-        b = i % n_blocks
-        if streams:                                                # one epoch of every stream this rank owns
-            for s_ in range(my_streams):
-                one_stream_epoch((i + s_) % n_blocks, False)
-            return
-        if world > 1:
-            if rank == 0:
-                recv.copy_(blocks_dev[b], non_blocking=True)
-            dist.broadcast(recv_u8, 0)
-            ctx.block_stage(recv, stream)
-        else:
-            ctx.block_stage(blocks_dev[b], stream)
-        ctx.epoch_set(ep_structs[b], sats[b], stream)
-        if score_mode == capi.SCORE_BRUTE:
-            ctx.brute_presort(sat_mode, aux.cuda_stream)
-        ctx.replica_prepare(stream)
-        ctx.correlogram(stream)
-        ctx.score_pos(score_mode, sat_mode, stream)
-        if world > 1:
-            part = _as_tensor(torch, ctx.dev_ptr(capi.PTR_PARTIAL), capi.DPE_PARTIAL_LEN, dev)
-            dist.all_gather_into_tensor(gathered, part)
-            ctx.estimate(est_mode, gathered, world, stream)
-        else:
-            ctx.estimate(est_mode, None, 1, stream)
-
-    def step_e2e(i):
-        b = i % n_blocks
-        if streams:
-            r_ = None
-            for s_ in range(my_streams):
-                r_ = one_stream_epoch((i + s_) % n_blocks, True)
-            return r_
-        if world > 1:
-            if rank == 0:
-                recv.copy_(blocks_host[b], non_blocking=True)     # H2D from pinned memory, then NVLink broadcast
-            dist.broadcast(recv_u8, 0)
-            ctx.block_stage(recv, stream)
-            ctx.epoch_set(ep_structs[b], sats[b], stream)
-            if score_mode == capi.SCORE_BRUTE:
-                ctx.brute_presort(sat_mode, aux.cuda_stream)
-            ctx.replica_prepare(stream)
-            ctx.correlogram(stream)
-            ctx.score_pos(score_mode, sat_mode, stream)
-            part = _as_tensor(torch, ctx.dev_ptr(capi.PTR_PARTIAL), capi.DPE_PARTIAL_LEN, dev)
-            dist.all_gather_into_tensor(gathered, part)
-            ctx.estimate(est_mode, gathered, world, stream)
-            return ctx.result_fetch(stream)
-        return ctx.epoch_run(blocks_host[b], ep_structs[b], sats[b], score_mode, est_mode, 0, stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, K, W, with_flush=True):
-        for i in range(W):
-            step_fn(i)
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        t0 = time.perf_counter()
+    def run_steps(K, host, score=None, first=0):
+        """K pipelined steps (c5: one epoch of every stream of this rank per step); returns the last result."""
+        sm = score_mode if score is None else score
+        res = None
+        n = 0
         for i in range(K):
-            if with_flush:
-                flush.zero_()                                      # L2 flush between timed iterations (untimed)
-            ev[i][0].record()
-            step_fn(i)
-            ev[i][1].record()
-        barrier()
+            with torch.cuda.stream(rig.flush_stream):
+                rig.flush.zero_()                                   # L2 flush every step, on a side stream
+            for s_ in range(epochs_per_step):
+                ctx = ctxs[n % depth]
+                if ctx.lib.dpe_epoch_pending(ctx.h):
+                    res = ctx.epoch_collect()
+                b = (first + i + s_) % n_in if not streams else s_
+                src = (blocks_host if host else blocks_dev)[b] if need_dev else None
+                ctx.epoch_submit(src, eps[b], sats[b], sm, est_mode, 0)
+                n += 1
+        for d in range(depth):
+            ctx = ctxs[(n + d) % depth]
+            if ctx.lib.dpe_epoch_pending(ctx.h):
+                res = ctx.epoch_collect()
+        return res
+
+    def timed(K, Wm, host, score=None):
+        run_steps(Wm, host, score)
+        rig.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        res = run_steps(K, host, score, first=Wm)
+        e1.record()
+        rig.barrier()
         wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall
+        return rig.max_over_ranks(e0.elapsed_time(e1)), wall, res
 
     pairs_per_step = G_total * C * (streams if streams else 1)
-    n_epochs_rank = my_streams if streams else 1
-    # --- resident-input throughput (`value`) with per-stage device timing -----------------------
-    sampler = ClockSampler(local) if rank == 0 else None
-    ctx.profile_enable(True)
-    launches0 = ctx.launch_count()
-    ms_total, wall = timed(step_resident, args.steps, args.warmup)
-    stage_ms, stage_cnt = ctx.profile_read()
+    out = dict(workload=workload)
+
+    # --- pipelined throughput, resident inputs (`value`) -----------------------------------------
+    sampler = ClockSampler(rig.local) if rank == 0 else None
+    launches0 = sum(c.launch_count() for c in ctxs)
+    ms_total, wall, res = timed(steps, warmup, host=False)
+    launches = sum(c.launch_count() for c in ctxs) - launches0
     clocks = sampler.stop() if sampler else None
-    launches = (ctx.launch_count() - launches0) // ((args.steps + args.warmup) * n_epochs_rank)
-    ctx.profile_enable(False)
-    res = ctx.result_fetch(stream)
-    valid_pairs = ctx.brute_pairs() if score_mode == capi.SCORE_BRUTE else (hi - lo) * C
-    ms_per_step = ms_total / args.steps
-    value = pairs_per_step / (ms_per_step * 1e-3)
+    ms_per_step = ms_total / steps
+    out.update(ms_per_step=ms_per_step, value=pairs_per_step / (ms_per_step * 1e-3), wall_s=wall, clocks=clocks,
+               launches_per_epoch=launches // ((steps + warmup) * epochs_per_step),
+               gpu_launches=(launches // (steps + warmup)) * steps,
+               fix=dict(z=[res.z[i] for i in range(4)], argmax=res.argmax, out_of_window=res.out_of_window))
 
-    # --- end to end: host buffers through the C-ABI epoch call ---------------------------------
-    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
-    e2e_ms /= args.steps
-    e2e_value = pairs_per_step / (e2e_ms * 1e-3)
-    h2d = (4 * S + 8 * 8 * C * T + 2300) * n_epochs_rank         # block + sat states + dpe_epoch per epoch
-    d2h = 16 * 8 * n_epochs_rank
+    # --- end to end: host buffers through the same call ------------------------------------------
+    if with_e2e:
+        e2e_ms, _, _ = timed(steps, warmup, host=True)
+        e2e_ms /= steps
+        out["e2e"] = dict(value=pairs_per_step / (e2e_ms * 1e-3), unit="corr/s",
+                          h2d_bytes_per_step=(4 * S + 8 * 8 * C * T + 2048) * epochs_per_step,    # rank 0's uploads
+                          d2h_bytes_per_step=16 * 8 * epochs_per_step, ms_per_step=e2e_ms,
+                          epochs_per_s=1e3 * (streams if streams else 1) / e2e_ms,
+                          note="page-locked host block + parameters -> one H2D packet on rank 0 (-> ncclBroadcast), "
+                               "result D2H per epoch, all inside dpe_epoch_submit / dpe_epoch_collect")
 
-    # --- the other path for context (lookup when the headline is brute and vice versa) ----------
-    other = None
-    if args.both:
-        keep = score_mode
-        score_mode = capi.SCORE_LOOKUP if keep == capi.SCORE_BRUTE else capi.SCORE_BRUTE
-        o_ms, _ = timed(step_resident, args.steps, args.warmup)
-        o_e2e, _ = timed(step_e2e, args.steps, args.warmup)
-        other = dict(path="lookup" if score_mode == capi.SCORE_LOOKUP else "brute",
-                     ms_per_step=o_ms / args.steps, epochs_per_s=1e3 * args.steps / o_ms,
-                     value=pairs_per_step * args.steps / (o_ms * 1e-3),
-                     e2e_value=pairs_per_step * args.steps / (o_e2e * 1e-3),
-                     e2e_epochs_per_s=1e3 * args.steps / o_e2e)
-        score_mode = keep
+    # --- latency mode: one epoch at a time, L2 flushed between epochs, per-stage brackets ---------
+    if with_latency:
+        ctx = ctxs[0]
+        K = max(3, min(steps, 10))
+        for i in range(2):
+            ctx.epoch_run_dist(blocks_dev[i % n_in] if need_dev else None, eps[i % n_in], sats[i % n_in], score_mode,
+                               est_mode, 0)
+        rig.barrier()
+        ctx.profile_enable(True)
+        own = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+        lat = 0.0
+        for i in range(K):
+            rig.flush.zero_()
+            rig.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(own)
+            ctx.epoch_run_dist(blocks_dev[i % n_in] if need_dev else None, eps[i % n_in], sats[i % n_in], score_mode,
+                               est_mode, 0)
+            e1.record(own)
+            torch.cuda.synchronize()
+            lat += e0.elapsed_time(e1)
+        stage_ms, stage_cnt = ctx.profile_read()
+        ctx.profile_enable(False)
+        names = ("prepare", "correlogram", "lookup", "brute_bins", "brute_corr", "brute_score", "estimate", "velocity")
+        out["latency"] = dict(ms_per_epoch=rig.max_over_ranks(lat / K), epochs=K,
+                              stage_ms={n_: round(float(stage_ms[i] / K), 5) for i, n_ in enumerate(names)},
+                              note="one epoch at a time on one context, 256 MiB L2 flush between epochs (untimed); "
+                                   "the pair sort (brute_bins) overlaps prepare + correlogram on a second stream")
+        if score_mode == capi.SCORE_BRUTE:
+            k_ms = float(stage_ms[capi.STAGE_BRUTE_CORR] / max(int(stage_cnt[capi.STAGE_BRUTE_CORR]), 1))
+            valid_pairs = ctx.brute_pairs()
+            out["k_brute"] = dict(ms=k_ms, valid_pairs=valid_pairs, flop=FLOP_PER_SAMPLE_PAIR * S * valid_pairs)
+        else:
+            k_ms = float(stage_ms[capi.STAGE_LOOKUP] / max(int(stage_cnt[capi.STAGE_LOOKUP]), 1))
+            out["k_lookup"] = dict(ms=k_ms, bytes=(32 + 8) * (hi - lo) + 16 * C * (2 * W + 2))
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    # --- the other scoring path (lookup when the headline is brute and vice versa) -----------------
+    if with_other:
+        o_mode = capi.SCORE_LOOKUP if score_mode == capi.SCORE_BRUTE else capi.SCORE_BRUTE
+        o_steps = max(steps, 50) if o_mode == capi.SCORE_LOOKUP else steps
+        o_ms, _, _ = timed(o_steps, warmup, host=False, score=o_mode)
+        o_e2e, _, _ = timed(o_steps, warmup, host=True, score=o_mode)
+        # latency of the other path, one epoch at a time (resident inputs, no flush: launch-latency bound)
+        ctx = ctxs[0]
+        rig.barrier()
+        t0 = time.perf_counter()
+        for i in range(o_steps):
+            ctx.epoch_run_dist(blocks_dev[i % n_in] if need_dev else None, eps[i % n_in], sats[i % n_in], o_mode, est_mode, 0)
+        rig.barrier()
+        o_lat = (time.perf_counter() - t0) / o_steps * 1e3
+        launches1 = ctx.launch_count()
+        ctx.epoch_run_dist(blocks_dev[0] if need_dev else None, eps[0], sats[0], o_mode, est_mode, 0)
+        byts = (32 + 8) * (hi - lo) + 16 * C * S
+        out["other_path"] = dict(path="lookup" if o_mode == capi.SCORE_LOOKUP else "brute", steps=o_steps,
+                                 ms_per_step=o_ms / o_steps, epochs_per_s=1e3 * o_steps / o_ms,
+                                 value=pairs_per_step * o_steps / (o_ms * 1e-3),
+                                 e2e_value=pairs_per_step * o_steps / (o_e2e * 1e-3), e2e_ms_per_step=o_e2e / o_steps,
+                                 e2e_epochs_per_s=1e3 * o_steps / o_e2e, latency_ms_per_epoch=o_lat,
+                                 launches_per_epoch=ctx.launch_count() - launches1,
+                                 hbm=dict(algorithmic_bytes_per_epoch=byts,
+                                          achieved_gbs=byts / (o_ms / o_steps * 1e-3) / 1e9,
+                                          note="SURVEY 8(d): 32 B grid + 8 B score per candidate + 16 B x C x S of "
+                                               "correlogram the reference's formulation touches, / pipelined epoch time"))
+    out["side_kernels"] = side_kernel_report(capi)
+    for c in ctxs:
+        c.close()
+    return out
+
+
+def side_kernel_report(capi):
+    """Registers x threads of every kernel: do the side kernels fit on an SM beside a k_brute CTA?"""
+    rep = {}
+    try:
+        rb, _, _ = capi.kernel_attr("k_brute")
+        alloc = lambda r: (r + 7) // 8 * 8
+        free = 65536 - alloc(rb) * 256
+        rep["k_brute_regs"] = rb
+        rep["free_regs_per_sm_beside_k_brute"] = free
+        side = {"k_prepare": 128, "k_corr_partial": 128, "k_corr_finalize": 256, "k_sample_planes": 256,
+                "k_replica_rd": 256, "k_pair_bins": 128, "k_block_scan": 256, "k_scatter": 128,
+                "k_score_pairs": 128, "k_score_lookup": 128, "k_finalize": 32}
+        worst = 0
+        for k, thr in side.items():
+            r, _, _ = capi.kernel_attr(k)
+            rep[k] = [r, thr]
+            worst = max(worst, alloc(r) * thr)
+        rep["all_fit"] = worst <= free
+    except Exception as exc:
+        rep["error"] = repr(exc)
+    return rep
+
+
+def roofline_of(m, S, clocks, peaks, fp32_peak):
+    if "k_brute" in m:
+        kb = m["k_brute"]
+        achieved = kb["flop"] / (kb["ms"] * 1e-3) / 1e12
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        nominal = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        step_frac = kb["flop"] / (m["ms_per_step"] * 1e-3) / 1e12 / fp32_peak if WORKLOADS[m["workload"]].get("streams") is None else None
+        return dict(bound="fp32", kernel="k_brute", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
+                    frac=achieved / fp32_peak, traffic=None,
+                    traffic_note="not measured in this run (ncu --set full capture of the same command: profiles/); "
+                                 "k_brute streams its planes from L2, DRAM traffic is ~60 MB per launch",
+                    peak_source="FFMA2 issue-limit micro-benchmark in this run (dpe_microbench_fp32: scalar multiplier, "
+                                "shared pair); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                    algorithmic="6 FLOP x S x valid (candidate,PRN) pairs per launch (this rank's shard)",
+                    kernel_ms=kb["ms"], kernel_share=kb["ms"] / m["latency"]["ms_per_epoch"],
+                    kernel_share_pipelined=kb["ms"] / m["ms_per_step"] if step_frac is not None else None,
+                    whole_step_frac=step_frac,
+                    peak_nominal=nominal, frac_nominal=achieved / nominal,
+                    nominal_source="148 SM x 128 FP32 lanes x 2 FLOP x %.0f MHz (median SM clock under load)" % mhz)
+    kl = m["k_lookup"]
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    achieved = kl["bytes"] / (kl["ms"] * 1e-3) / 1e9
+    return dict(bound="hbm", kernel="k_score_lookup", achieved=achieved, peak=hbm, unit="GB/s", frac=achieved / hbm,
+                traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                algorithmic="32 B grid + 8 B score per candidate + correlogram window", kernel_ms=kl["ms"],
+                kernel_share=kl["ms"] / m["latency"]["ms_per_epoch"])
+
+
+def run_ours(args):
+    rig = Rig()
+    capi = rig.capi
+    main = measure(rig, args, args.workload, args.steps, args.warmup, with_other=args.both)
+    # the other BASELINE.json workloads, same code path, fewer steps (sub-records)
+    subs = {}
+    names = [n for n in args.configs.split(",") if n and n != "none"]
+    if args.configs == "auto":
+        names = ["c3", "c4"] + (["c5"] if rig.world >= 8 else [])
+    for n in names:
+        if n == args.workload or n not in WORKLOADS:
+            continue
+        k = dict(c3=10, c4=2 if rig.world == 1 else 4, c5=2, demo=10, tiny=10)[n]
+        try:
+            subs[n] = measure(rig, args, n, steps=k, warmup=1 if n in ("c4", "c5") else 3, with_e2e=(n != "c5"))
+        except Exception as exc:                                   # reported, never silently dropped
+            subs[n] = dict(error=repr(exc))
+    if rig.rank != 0:
+        rig.close()
         return
 
-    # --- roofline of the dominant kernel ------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    if score_mode == capi.SCORE_BRUTE:
-        fp32_peak = capi.microbench_fp32(local, True)             # FFMA2 stream, measured in this run
-        n = max(int(stage_cnt[capi.STAGE_BRUTE_CORR]), 1)
-        k_ms = stage_ms[capi.STAGE_BRUTE_CORR] / n                # this rank's k_brute, average per launch
-        flop = FLOP_PER_SAMPLE_PAIR * S * valid_pairs
-        achieved = flop / (k_ms * 1e-3) / 1e12
-        roofline = dict(bound="fp32", kernel="k_brute", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
-                        frac=achieved / fp32_peak, traffic=None,
-                        peak_source="FFMA2 issue-limit micro-benchmark in this run (dpe_microbench_fp32: scalar multiplier, shared pair); nominal "
-                                    "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                        algorithmic="6 FLOP x S x valid (candidate,PRN) pairs per launch",
-                        kernel_ms=k_ms, kernel_share=stage_ms[capi.STAGE_BRUTE_CORR] / max(stage_ms.sum(), 1e-9))
-        mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        nominal = 148 * 128 * 2 * mhz * 1e6 / 1e12
-        try:                                                       # DRAM traffic of one launch, from the committed ncu capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "k_brute_traffic.json")))
-            if tr.get("workload") == args.workload and world == 1:
-                roofline["traffic"] = tr["dram_bytes_per_launch"]
-                roofline["traffic_source"] = tr["source"]
-        except Exception:
-            pass
-        roofline.update(peak_nominal=nominal, frac_nominal=achieved / nominal,
-                        nominal_source="148 SM x 128 FP32 lanes x 2 FLOP x %.0f MHz (median SM clock under load)" % mhz)
-    else:
-        n = max(int(stage_cnt[capi.STAGE_LOOKUP]), 1)
-        k_ms = stage_ms[capi.STAGE_LOOKUP] / n
-        byts = (32 + 8) * (hi - lo) + 16 * C * (2 * args.lag_halfwidth + 2)
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        achieved = byts / (k_ms * 1e-3) / 1e9
-        roofline = dict(bound="hbm", kernel="k_score_lookup", achieved=achieved, peak=hbm, unit="GB/s",
-                        frac=achieved / hbm, traffic=None,
-                        peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                        algorithmic="32 B grid + 8 B score per candidate + correlogram window", kernel_ms=k_ms,
-                        kernel_share=stage_ms[capi.STAGE_LOOKUP] / max(stage_ms.sum(), 1e-9))
-    stages = {name: round(float(stage_ms[i] / max(args.steps + args.warmup, 1)), 5) for i, name in enumerate(
-        ("prepare", "correlogram", "lookup", "brute_bins", "brute_corr", "brute_score", "estimate"))}
+    fp32_peak = capi.microbench_fp32(rig.local, True)              # FFMA2 stream, measured in this run
+    cfg = config_for(args)
+    S = cfg["S"]
+    roofline = roofline_of(main, S, main["clocks"], peaks, fp32_peak)
+    configs = {}
+    for n, m in subs.items():
+        if "error" in m:
+            configs[n] = m
+            continue
+        c2 = config_for(args, n)
+        configs[n] = dict(config=c2, n_gpus=rig.world, value=m["value"], unit="corr/s", ms_per_step=m["ms_per_step"],
+                          epochs_per_s=1e3 * c2["streams"] / m["ms_per_step"],
+                          e2e=m.get("e2e"), latency=m.get("latency"), clocks=m["clocks"],
+                          roofline=roofline_of(m, c2["S"], m["clocks"], peaks, fp32_peak), fix=m["fix"],
+                          launches_per_epoch=m["launches_per_epoch"])
 
     cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, budget_s=args.cpu_budget)
     flow = None
-    if world == 1 and args.flow_epochs > 0 and args.workload == "demo":
+    ref_gpu = None
+    if rig.world == 1 and args.flow_epochs > 0 and args.workload == "demo":
         try:
-            ctx.close()
             flow = [flow_realtime(args, "brute"), flow_realtime(args, "lookup")]
-        except Exception as exc:                                   # reported, never silently dropped
+        except Exception as exc:
             flow = dict(error=repr(exc))
+        try:
+            ref_gpu = reference_gpu_leg(args)
+        except Exception as exc:
+            ref_gpu = dict(error=repr(exc))
+    like = None
+    if cpu and main.get("other_path") and main["other_path"]["path"] == "lookup":
+        o = main["other_path"]
+        like = dict(ours_lookup_e2e=o["e2e_value"], ours_lookup_resident=o["value"], cpu_lookup=cpu["value"],
+                    cpu_cores=cpu["cores"], ratio_e2e=o["e2e_value"] / cpu["value"],
+                    note="like for like: both sides score a pair by interpolating a correlogram (the reference's own "
+                         "formulation); the headline metric instead runs a full S-sample correlation per pair")
+        if ref_gpu and "epochs_per_s" in ref_gpu:
+            like["reference_gpu_epochs_per_s"] = ref_gpu["epochs_per_s"]
+            like["ratio_vs_reference_gpu"] = o["e2e_epochs_per_s"] / ref_gpu["epochs_per_s"]
 
-    line = dict(metric="DPE candidate-PRN correlations/s (20 ms epochs, %s BCM)" % args.path, value=value,
-                unit="corr/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
-                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32 (f64 geometry/bins)",
-                data="synthetic",
-                config=dict(workload="%s: %s" % (args.workload, WORKLOADS[args.workload]["desc"]),
-                            S=S, prns=C, candidates=G_total, path=args.path, estimate=args.estimate,
-                            lag_halfwidth=args.lag_halfwidth,
-                            sharding=("independent streams, %d per rank, no collective" % n_epochs_rank) if streams
-                            else "grid candidates, contiguous index ranges",
-                            l2="flushed (256 MiB memset) between timed iterations",
-                            unit_of_work=("one candidate-PRN pair scored; brute = a full S-sample correlation per pair "
-                                          "(6*S FLOP, the north-star kernel); the reference arm and other_path=lookup "
-                                          "score a pair by interpolating a precomputed correlogram (same result)")),
-                epochs_per_s=1e3 * (streams if streams else 1) / ms_per_step,
-                realtime_factor=(1e3 / ms_per_step) / 50.0,
-                e2e=dict(value=e2e_value, unit="corr/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=e2e_ms, epochs_per_s=1e3 / e2e_ms),
-                gpu_launches=int(launches) * args.steps * n_epochs_rank, gpu_launches_per_epoch=int(launches),
-                stage_ms_per_step=stages, roofline=roofline, cpu_baseline=cpu,
-                clocks=clocks, other_path=other, flow=flow, wall_s=wall,
-                fix=dict(z=[res.z[i] for i in range(4)], argmax=res.argmax, out_of_window=res.out_of_window))
+    streams = cfg["streams"]
+    line = dict(metric="DPE candidate-PRN correlations/s (20 ms epochs, %s BCM)" % args.path, value=main["value"],
+                unit="corr/s", n_gpus=rig.world, steps=args.steps, warmup=args.warmup, ms_per_step=main["ms_per_step"],
+                higher_is_better=True, scaling="strong" if streams == 1 else "weak", vs_baseline=None,
+                dtype="f32 (f64 geometry/bins)", data="synthetic", config=cfg,
+                run=dict(lag_halfwidth=args.lag_halfwidth, contexts_in_flight=args.depth,
+                         sharding=("independent streams, no collective" if streams > 1 else
+                                   "grid candidates, contiguous index ranges; ncclBroadcast of the epoch packet + "
+                                   "ncclAllGather of the partials inside libdpe_b200"),
+                         l2="256 MiB flush memset every step on a side stream (inside the timed region); inputs rotate over "
+                            "8 blocks and 2 contexts",
+                         brute="a full S-sample correlation per pair (6*S FLOP); the reference arm and other_path=lookup "
+                               "score a pair by interpolating a precomputed correlogram (same result)"),
+                epochs_per_s=1e3 * streams / main["ms_per_step"],
+                realtime_factor=(1e3 / main["ms_per_step"]) / 50.0,
+                e2e=main["e2e"], gpu_launches=int(main["gpu_launches"]),
+                gpu_launches_per_epoch=int(main["launches_per_epoch"]),
+                latency=main.get("latency"), roofline=roofline, cpu_baseline=cpu, like_for_like=like,
+                reference_gpu=ref_gpu, clocks=main["clocks"], other_path=main.get("other_path"), flow=flow,
+                configs=configs, side_kernels=main.get("side_kernels"), wall_s=main["wall_s"], fix=main["fix"])
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    rig.close()
 
 
 _FLOW_FILES = {}
+
+
+def _flow_files(n_epochs):
+    sc, grid, tg = build_workload("demo")
+    d = "/tmp/dpe_bench_flow"
+    need = 4 * sc.S * (n_epochs + 36)                                    # + the reader's 32-block read-ahead
+    files = _FLOW_FILES.get("files")
+    if not files or os.path.getsize(files["dat"]) < need:
+        files = sc.write_files(d, n_epochs + 36, grid=grid, handoff_block=1)
+        _FLOW_FILES["files"] = files
+    return sc, d, files
 
 
 def flow_realtime(args, path):
@@ -375,15 +523,8 @@ def flow_realtime(args, path):
     (the reference's `[Flow] Average ... block duration`, flow.cu:172-191) and the real-time factor."""
     import dpe_pkg
     flowapi = dpe_pkg.submodule("flowapi")
-    synth = dpe_pkg.submodule("synth")
-    sc, grid, tg = build_workload("demo")
-    d = "/tmp/dpe_bench_flow"
     n_epochs = args.flow_epochs
-    need = 4 * sc.S * (n_epochs + 34)                                    # + the reader's 32-block read-ahead
-    files = _FLOW_FILES.get("files")
-    if not files or os.path.getsize(files["dat"]) < need:
-        files = sc.write_files(d, n_epochs + 34, grid=grid, handoff_block=0)
-        _FLOW_FILES["files"] = files
+    sc, d, files = _flow_files(n_epochs)
     sh = flowapi.Shell()
     cmds = ["newflow dpe rx", "loadflow rx",
             'setparam rx SampleBlock Filename "%s"' % files["dat"],
@@ -402,7 +543,7 @@ def flow_realtime(args, path):
         raise RuntimeError("flow failed")
     st = sh.stats("rx")
     rows = np.loadtxt(os.path.join(d, "XFile.csv"), delimiter=",")
-    truth = sc.rx_state(sc.cfg.rx_time0 + n_epochs * sc.cfg.T)
+    truth = sc.rx_state(sc.cfg.rx_time0 + (n_epochs + 1) * sc.cfg.T)
     err = float(np.linalg.norm(rows[-1, :3] - truth[:3]))
     sh.close()
     return dict(path=path, epochs=st["run_count"], avg_epoch_us=st["avg_us"], min_epoch_us=st["min_us"],
@@ -412,11 +553,27 @@ def flow_realtime(args, path):
                      "grid (0.5 m/s), 8 PRNs, host buffers, per-epoch D2H of the fix, CSV logging")
 
 
-def _as_tensor(torch, ptr, n, dev):
-    """Zero-copy float64 view of a context-owned device buffer (for NCCL)."""
-    class _A:
-        __cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=2)
-    return torch.as_tensor(_A(), device=dev)
+def reference_gpu_leg(args):
+    """The reference's own kernels (CUDARecv rebuilt unmodified for sm_100a, oracle/_ref/ref_dpe -- a
+    checker binary, executed here as a reported baseline only) on the same capture, same box."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dpe")
+    if not os.path.exists(exe):
+        return None
+    n_epochs = min(args.flow_epochs, 100)
+    sc, d, files = _flow_files(args.flow_epochs)
+    cmd = [exe, files["dat"], files["handoff"], files["rinex"], files["grid"], "25", "25", str(n_epochs),
+           os.path.join(d, "ref_out"), "32", repr(sc.cfg.fs), "0"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    us = None
+    for l in r.stdout.splitlines():
+        if l.startswith("REF_MEAN_EPOCH_US"):
+            us = float(l.split()[1])
+    if r.returncode != 0 or not us:
+        return dict(error="ref_dpe exit %d: %s" % (r.returncode, r.stdout[-300:]))
+    return dict(avg_epoch_us=us, epochs_per_s=1e6 / us, epochs=n_epochs,
+                value=390625 * 8 * 1e6 / us, unit="corr/s (lookups)",
+                note="reference CUDARecv kernels rebuilt for sm_100a (FFT correlogram + BCM_PosMeasML lookup + 25^4 "
+                     "velocity grid), timer as flow.cu:132-135")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -486,17 +643,18 @@ def run_reference(args):
             pairs += sum(o[1] for o in pool.map(_cpu_epoch, jobs(i)))
         wall = time.perf_counter() - t0
     v = pairs / wall
+    cfg = config_for(args)
     cpu = dict(value=v, unit="corr/s", cores=procs, kind="port",
                sample="%d step(s) x %d process(es), one epoch of workload %s per process and step "
                       "(NumPy FFT correlogram + grid lookup, oracle/dpe_oracle.py)" % (args.steps, procs, args.workload),
                epochs_per_s=args.steps * procs / wall)
     line = dict(impl="reference", metric="DPE candidate-PRN correlations/s (20 ms epochs, %s BCM)" % args.path,
                 value=v, unit="corr/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype="f64", data="synthetic",
-                config=dict(workload="%s: %s" % (args.workload, WORKLOADS[args.workload]["desc"]),
-                            note="reference CPU DPE path (py3/NumPy restatement of PyGNSS / CUDARecv), "
-                                 "%d process(es), each step = one epoch per process" % procs),
+                ms_per_step=1e3 * wall / args.steps, higher_is_better=True,
+                scaling="strong" if cfg["streams"] == 1 else "weak", vs_baseline=None,
+                dtype="f64", data="synthetic", config=cfg,
+                run=dict(note="reference CPU DPE path (py3/NumPy restatement of PyGNSS / CUDARecv): a pair is scored by "
+                              "interpolating the FFT correlogram; %d process(es), each step = one epoch per process" % procs),
                 cpu_baseline=cpu, e2e=dict(value=v, unit="corr/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -507,10 +665,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="demo", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("DPE_BENCH_WORKLOAD", "demo"), choices=sorted(WORKLOADS))
+    ap.add_argument("--configs", default=os.environ.get("DPE_BENCH_CONFIGS", "auto"),
+                    help="comma list of further workloads timed as sub-records (auto: c3,c4 and c5 at >= 8 GPUs; none)")
     ap.add_argument("--path", default="brute", choices=["brute", "lookup"])
     ap.add_argument("--estimate", default="argmax", choices=["argmax", "weighted"])
     ap.add_argument("--lag-halfwidth", type=int, default=16)
+    ap.add_argument("--depth", type=int, default=2, help="contexts in flight per rank (1 = no cross-epoch overlap)")
     ap.add_argument("--both", action="store_true", default=True, help="also time the other scoring path")
     ap.add_argument("--no-both", dest="both", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")

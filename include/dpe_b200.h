@@ -190,6 +190,32 @@ int dpe_epoch_set(dpe_ctx* ctx, const dpe_epoch* ep, const double* sat_states, v
 int dpe_epoch_set_part(dpe_ctx* ctx, const dpe_epoch* ep, const double* sat_states, unsigned parts,
                        void* stream);
 
+/* dpe_epoch_set_device: the same upload when the parameters already live on the DEVICE -- the
+ * reference's cuChanMgr and cuEKF publish every one of them as a CUDA_DEVICE port
+ * (cuchanmgr.cu:973-990,1136-1171; cuekf.cu xCurrkk1) and BatchCorrScores / BatchCorrManifold read them
+ * there (batchcorrscores.cu:991-1005, batchcorrmanifold.cu:2512-2533).  A one-block kernel on `stream`
+ * packs them; nothing is copied through the host.  Pointers of a part that is not selected may be NULL.
+ * rx_time is a host value (the "rxTime" port is HOST, cuchanmgr.cu:973).                          */
+typedef struct dpe_epoch_dev {
+    int32_t C;                       /* host: VectorLength of the channel ports                      */
+    const uint8_t* prn;              /* "ValidPRNs"          char   [C]                               */
+    const double*  rc_start;         /* "CodePhaseStart"     double [C]                               */
+    const double*  ri_start;         /* "CarrierPhaseStart"                                           */
+    const double*  fc;               /* "CodeFrequency"                                               */
+    const double*  fi;               /* "CarrierFrequency"                                            */
+    const int32_t* cp_start;         /* "cpElapsedStart"     int    [C]                               */
+    const int32_t* cp_ref;           /* "cpReference" / "cpRef"                                       */
+    const int32_t* doppler_sign;     /* "DopplerSign"        int    [1]                               */
+    const double*  rc_end;           /* "CodePhase" (= CodePhaseEnd)                                  */
+    const int32_t* cp_end;           /* "cpElapsedEnd"                                                */
+    const int32_t* cp_ref_tow;       /* "cpRefTOW"                                                    */
+    const double*  center;           /* "xCurrkk1"           double [8]                               */
+    const double*  enu2ecef;         /* "ENU2ECEFMat"        double [9]                               */
+    const double*  sat_states;       /* "SatStates"          double [C][T][8]                         */
+    double rx_time;                  /* "rxTime" (host double, already += T)                          */
+} dpe_epoch_dev;
+int dpe_epoch_set_device(dpe_ctx* ctx, const dpe_epoch_dev* ep, unsigned parts, void* stream);
+
 /* dpe_replica_prepare: int16 unpack, carrier NCO wipe-off, C/A chip index and
  * replica sign, nav-bit edge, per-lag partial correlations.  Replaces BCS_Load,
  * BCS_NavBitBoundary, BCS_ComputeDopplerWipeoff, BCS_ComputeCodeReplica,

@@ -384,6 +384,59 @@ int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states
     return DPE_OK;
 }
 
+// packs device-resident channel / geometry parameters into the context's EpochDev + satellite states
+__global__ void DPE_SIDE128
+k_pack_epoch(dpe_epoch_dev p, unsigned parts, int T, EpochDev* __restrict__ e, double* __restrict__ sat) {
+    const int C = p.C;
+    if (threadIdx.x == 0) e->C = C;
+    if (parts & DPE_PART_CHANNELS) {
+        if (threadIdx.x == 0) e->doppler_sign = p.doppler_sign ? p.doppler_sign[0] : 1;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            e->prn[i] = p.prn[i];
+            e->rc_start[i] = p.rc_start[i]; e->ri_start[i] = p.ri_start[i];
+            e->fc[i] = p.fc[i]; e->fi[i] = p.fi[i];
+            e->cp_start[i] = p.cp_start[i]; e->cp_ref[i] = p.cp_ref[i];
+        }
+    }
+    if (parts & DPE_PART_GEOMETRY) {
+        if (threadIdx.x == 0) e->rx_time = p.rx_time;
+        if (threadIdx.x < 8) e->center[threadIdx.x] = p.center[threadIdx.x];
+        if (threadIdx.x < 9) e->R[threadIdx.x] = p.enu2ecef[threadIdx.x];
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            e->fc[i] = p.fc[i];
+            e->cp_ref[i] = p.cp_ref[i];
+            e->rc_end[i] = p.rc_end[i]; e->cp_end[i] = p.cp_end[i]; e->cp_ref_tow[i] = p.cp_ref_tow[i];
+        }
+        for (int i = threadIdx.x; i < 8 * C * T; i += blockDim.x) sat[i] = p.sat_states[i];
+    }
+}
+
+int dpe_epoch_set_device(dpe_ctx* c, const dpe_epoch_dev* ep, unsigned parts, void* stream) {
+    DPE_REQUIRE(c && ep, DPE_EINVAL, "dpe_epoch_set_device: null argument");
+    DevGuard guard(c->cfg.device);
+    DPE_REQUIRE(parts && !(parts & ~(DPE_PART_CHANNELS | DPE_PART_GEOMETRY)), DPE_EINVAL, "bad parts mask %u", parts);
+    DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
+    DPE_REQUIRE(ep->fc && ep->cp_ref, DPE_EINVAL, "null fc / cp_ref");
+    DPE_REQUIRE(!(parts & DPE_PART_CHANNELS) || (ep->prn && ep->rc_start && ep->ri_start && ep->fi && ep->cp_start),
+                DPE_EINVAL, "channel part: null pointer");
+    DPE_REQUIRE(!(parts & DPE_PART_GEOMETRY) || (ep->rc_end && ep->cp_end && ep->cp_ref_tow && ep->center &&
+                                                 ep->enu2ecef && ep->sat_states), DPE_EINVAL, "geometry part: null pointer");
+    if (c->have_epoch && c->epoch_C != ep->C) c->have_epoch = 0;      // channel count changed: both parts again
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->sort_pending) { DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0)); c->sort_pending = 0; }
+    c->sort_valid = 0;
+    k_pack_epoch<<<1, 128, 0, s>>>(*ep, parts, c->T, c->ep, c->sat);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    DPE_CUDA(cudaEventRecord(c->ev_epoch, s));
+    c->epoch_C = ep->C;
+    c->ep_host.C = ep->C;
+    c->have_epoch |= (int)parts;
+    if (parts & DPE_PART_CHANNELS) c->have_prepare = c->have_corr = 0;
+    c->have_scores = 0;
+    return DPE_OK;
+}
+
 int dpe_epoch_set(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, void* stream) {
     DPE_REQUIRE(sat_states, DPE_EINVAL, "dpe_epoch_set: null argument");
     return dpe_epoch_set_part(c, ep, sat_states, DPE_PART_CHANNELS | DPE_PART_GEOMETRY, stream);

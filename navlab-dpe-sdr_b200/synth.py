@@ -42,6 +42,7 @@ class ScenarioConfig:
     truth_ecef: tuple = (151158.46510991786, -4885422.338576897, 4090087.0543405097)
     truth_clock_bias_m: float = 175068.5560268988
     truth_clock_drift_mps: float = -0.11462027018250964
+    truth_vel_enu: tuple = (0.0, 0.0, 0.0)      # receiver velocity, east / north / up m/s (0 = the static demo receiver)
     rx_time0: float = 414006.0680031631
     tow_ref: int = 414006
     cp_ref_base: int = 1000
@@ -88,6 +89,9 @@ class Scenario:
         self.phi0 = rng.random(self.C)
         self.bits = rng.integers(0, 2, size=(self.C, 4096)) * 2 - 1
         self._noise_seed = c.seed + 1
+        lat, lon = gm.ecef_to_latlon(np.asarray(c.truth_ecef, dtype=np.float64))
+        self.vel_ecef = np.asarray(gm.enu_to_ecef_matrix(lat, lon), dtype=np.float64).reshape(3, 3) @ \
+            np.asarray(c.truth_vel_enu, dtype=np.float64)
         self._pr0 = np.array([self.link(k, c.rx_time0)["pr"] for k in range(self.C)])
         self._edge_cache = {}
 
@@ -95,8 +99,9 @@ class Scenario:
     def rx_state(self, rx_time):
         c = self.cfg
         dt = c.truth_clock_bias_m + c.truth_clock_drift_mps * (rx_time - c.rx_time0)
-        return np.array([c.truth_ecef[0], c.truth_ecef[1], c.truth_ecef[2], dt,
-                         0.0, 0.0, 0.0, c.truth_clock_drift_mps])
+        p = np.asarray(c.truth_ecef, dtype=np.float64) + self.vel_ecef * (rx_time - c.rx_time0)
+        return np.array([p[0], p[1], p[2], dt, self.vel_ecef[0], self.vel_ecef[1], self.vel_ecef[2],
+                         c.truth_clock_drift_mps])
 
     def link(self, k, rx_time, state=None):
         """Solve the light-time equation for PRN index k at receiver clock time

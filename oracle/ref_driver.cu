@@ -17,6 +17,17 @@
 //
 // usage: ref_dpe <samples.dat> <handoff.csv> <rinex.n> <grid.csv> <pos_dim> <vel_dim>
 //                <epochs> <out_dir> [lag_halfwidth=32] [fs=2.5e6]
+//
+// Built a second time with -DREF_WEIGHTED (oracle/_ref/ref_dpe_weighted): this translation unit then
+// takes the place of batchcorrmanifold.o by #including the reference's batchcorrmanifold.cu where it
+// lies, so that its DORMANT score-weighted estimator -- BCM_PosMeasReduction (:816-1056) +
+// BCM_ReduceAndPosMeas (:1365-1510), launches commented out at :2547-2567 -- can be launched on the
+// module's own device buffers after every BatchCorrManifold::Update, with exactly the arguments of the
+// commented launch.  Dumps e<epoch>_zval_weighted.bin (4 doubles) and e<epoch>_weighted_parts.bin
+// (8 x weightState_t {a,b,c,d,score}).
+#ifdef REF_WEIGHTED
+#include "batchcorrmanifold.cu"
+#endif
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <sys/stat.h>
@@ -40,9 +51,36 @@ static void dump_host(const std::string& dir, int epoch, const char* name, const
     fclose(f);
 }
 
+#ifdef REF_WEIGHTED
+// adds no data: only a door to the protected members of the module the reference flow created
+class BcmProbe : public dsp::BatchCorrManifold {
+  public:
+    int RunWeighted(double z[4], double parts[40]) {
+        double *z_d = NULL, *R_d = NULL;
+        if (cudaMalloc((void**)&z_d, 16 * sizeof(double)) != cudaSuccess) return -1;
+        if (cudaMalloc((void**)&R_d, 64 * sizeof(double)) != cudaSuccess) return -1;
+        cudaMemset(z_d, 0, 16 * sizeof(double));
+        // batchcorrmanifold.cu:2548-2553 and :2562-2563, verbatim arguments
+        BCM_PosMeasReduction<<<threadsPerMeasRedBlock, threadsPerPosManiBlock,
+                               sizeof(dsp::utils::weightState_t<double>) * threadsPerPosManiBlock, posStream>>>(
+            satStates_d, codeScores_d, xCurr_d, gridPosLocs_d, enu2ecefMat_d, codeFrequency_d, txTimePtr_d, *rxTimePtr,
+            numChan, currSamplingFreq, numSamps, weightedPosStates_d);
+        BCM_ReduceAndPosMeas<<<1, threadsPerMeasRedBlock,
+                               sizeof(dsp::utils::weightState_t<double>) * threadsPerMeasRedBlock, posStream>>>(
+            weightedPosStates_d, threadsPerMeasRedBlock, z_d, R_d);
+        if (cudaStreamSynchronize(posStream) != cudaSuccess) return -2;
+        cudaMemcpy(z, z_d, 4 * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(parts, weightedPosStates_d, 40 * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaFree(z_d);
+        cudaFree(R_d);
+        return cudaGetLastError() == cudaSuccess ? 0 : -3;
+    }
+};
+#endif
+
 class RefHarness : public dsp::DPEFlow {
   public:
-    int Run(int epochs, const std::string& out, int W, bool dump) {
+    int Run(int epochs, const std::string& out, int W, int dump) {   // dump: 0 none, 1 everything, 2 light (long runs)
         if (cudaStreamCreate(&cuStream) != cudaSuccess) return -1;
         for (size_t i = 0; i < Mods.size(); ++i)
             if (Mods[i]->Start((void*)&cuStream)) {
@@ -53,7 +91,7 @@ class RefHarness : public dsp::DPEFlow {
         double total_us = 0;
         int done = 0;
         for (int e = 0; e < epochs; ++e) {
-            if (dump) DumpInputs(out, e);
+            if (dump) DumpInputs(out, e, dump == 2);
             struct timeval t0, t1;
             int rc = 0;
             for (size_t i = 0; i < Mods.size() && !rc; ++i) {
@@ -61,7 +99,14 @@ class RefHarness : public dsp::DPEFlow {
                 if (i == 0) gettimeofday(&t0, NULL);           // as flow.cu:132-135
                 if (dump && !rc && Mods[i]->GetModuleName() == "BatchCorrManifold") {
                     cudaStreamSynchronize(cuStream);
-                    DumpOutputs(out, e, W);
+                    DumpOutputs(out, e, W, dump == 2);
+#ifdef REF_WEIGHTED
+                    double zw[4], parts[40];
+                    int wr = static_cast<BcmProbe*>(static_cast<dsp::BatchCorrManifold*>(Mods[i]))->RunWeighted(zw, parts);
+                    if (wr) { fprintf(stderr, "weighted kernels failed (%d)\n", wr); exit(6); }
+                    dump_host(out, e, "zval_weighted", zw, sizeof(zw));
+                    dump_host(out, e, "weighted_parts", parts, sizeof(parts));
+#endif
                 }
             }
             cudaStreamSynchronize(cuStream);
@@ -96,7 +141,7 @@ class RefHarness : public dsp::DPEFlow {
         }
         dump_host(out, e, name, h.data(), bytes);
     }
-    void DumpInputs(const std::string& out, int e) {
+    void DumpInputs(const std::string& out, int e, bool light) {
         cudaDeviceSynchronize();
         const int C = P("cuChanMgr", "CodeFrequency")->VectorLength;
         const int CT = P("cuChanMgr", "SatStates")->VectorLength;
@@ -109,8 +154,10 @@ class RefHarness : public dsp::DPEFlow {
         DumpDev(out, e, "ri_end", m, "CarrierPhaseEnd", C * sizeof(double));
         DumpDev(out, e, "fc", m, "CodeFrequency", C * sizeof(double));
         DumpDev(out, e, "fi", m, "CarrierFrequency", C * sizeof(double));
-        DumpDev(out, e, "sat_states", m, "SatStates", (size_t)CT * 8 * sizeof(double));
-        DumpDev(out, e, "sat_raw", m, "SatStatesOld", (size_t)C * 8 * sizeof(double));
+        if (!light) {
+            DumpDev(out, e, "sat_states", m, "SatStates", (size_t)CT * 8 * sizeof(double));
+            DumpDev(out, e, "sat_raw", m, "SatStatesOld", (size_t)C * 8 * sizeof(double));
+        }
         DumpDev(out, e, "prn", m, "ValidPRNs", C);
         DumpDev(out, e, "cp_ref", m, "cpReference", C * sizeof(int));
         DumpDev(out, e, "cp_start", m, "cpElapsedStart", C * sizeof(int));
@@ -124,12 +171,16 @@ class RefHarness : public dsp::DPEFlow {
             fclose(f);
         }
     }
-    void DumpOutputs(const std::string& out, int e, int W) {
+    void DumpOutputs(const std::string& out, int e, int W, bool light) {
         const int C = P("cuChanMgr", "CodeFrequency")->VectorLength;
         dsp::Port* smp = P("SampleBlock", "Samples");
         const size_t S = smp->VectorLength;
         // the 20 ms block the reference just processed (int16 I,Q)
-        DumpDev(out, e, "iq", "SampleBlock", "Samples", S * 2 * sizeof(short));
+        if (!light) DumpDev(out, e, "iq", "SampleBlock", "Samples", S * 2 * sizeof(short));
+#ifdef REF_BRIDGE
+        // bridge build (oracle/ref_bridge.cu): "CodeScores" is this repository's lag window, not [C][S] rows
+        light = true;
+#else
         // CodeScores window: fft-shifted bins S/2-W .. S/2+W+1 of every channel
         dsp::Port* cs = P("BatchCorrScores", "CodeScores");
         const int NL = 2 * W + 2;
@@ -139,6 +190,16 @@ class RefHarness : public dsp::DPEFlow {
                        (const char*)cs->Data + ((size_t)c * S + S / 2 - W) * 2 * sizeof(double),
                        (size_t)NL * 2 * sizeof(double), cudaMemcpyDeviceToHost);
         dump_host(out, e, "code_scores_win", win.data(), win.size() * sizeof(double));
+#endif
+        DumpDev(out, e, "zval", "BatchCorrManifold", "zVal", 8 * sizeof(double));
+#ifdef REF_BRIDGE
+        {
+            int Gb = 0;
+            GetModParam("BatchCorrManifold", "PosGridDimSize", &Gb);
+            DumpDev(out, e, "pos_scores", "BatchCorrManifold", "PosScores", (size_t)Gb * Gb * Gb * Gb * sizeof(double));
+        }
+#endif
+        if (light) return;
         // CarrScores window: fft-shifted bins N_c/2-Wd .. N_c/2+Wd+1 of the zero-padded carrier spectrum
         dsp::Port* cr = P("BatchCorrScores", "CarrScores");
         const int Nc = *(int*)P("BatchCorrScores", "NumFFTPoints")->Data;
@@ -154,7 +215,6 @@ class RefHarness : public dsp::DPEFlow {
         GetModParam("BatchCorrManifold", "PosGridDimSize", &G);
         const size_t Gtot = (size_t)G * G * G * G;
         DumpDev(out, e, "pos_scores", "BatchCorrManifold", "PosScores", Gtot * sizeof(double));
-        DumpDev(out, e, "zval", "BatchCorrManifold", "zVal", 8 * sizeof(double));
         DumpDev(out, e, "time_grid", "BatchCorrManifold", "TimeGrid", (size_t)G * sizeof(double));
     }
 };
@@ -170,7 +230,7 @@ int main(int argc, char** argv) {
     const std::string out = argv[8];
     const int W = argc > 9 ? atoi(argv[9]) : 32;
     const double fs = argc > 10 ? atof(argv[10]) : 2.5e6;
-    const bool dump = argc > 11 ? atoi(argv[11]) != 0 : true;
+    const int dump = argc > 11 ? atoi(argv[11]) : 1;              // 0 none, 1 everything, 2 light
     const bool ekf = argc > 12 ? atoi(argv[12]) != 0 : false;      // run the reference with its 8-state KF enabled
     // grid.csv == "none": let the reference generate its grid (BCM_InitPosGrid, batchcorrmanifold.cu:148-255)
     const int grid_type = argc > 13 ? atoi(argv[13]) : 0;           // ManifoldGridTypes: 0 Uniform, 2 ArthurBasis

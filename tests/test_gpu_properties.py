@@ -181,3 +181,101 @@ def test_ten_megahertz_block_length_beyond_16_bits(capi):
     r_b, s_b = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, G)
     assert np.max(np.abs(s_b - s_l) / s_l) < RTOL and r_b.argmax == r_l.argmax
     ctx.close()
+
+
+# ---- BASELINE.json configs at size, each spot-checked against the oracle -----------
+def _spot_check(capi, ctx, sc, grid_shard, ep, iq, bcs, lo, seed, n_spot=2000):
+    """brute == lookup on every candidate of the shard, and n_spot random candidates == the oracle."""
+    G = grid_shard.shape[0]
+    r_l, s_l = _scores(capi, ctx, iq, ep, capi.SCORE_LOOKUP, G)
+    r_b, s_b = _scores(capi, ctx, iq, ep, capi.SCORE_BRUTE, G)
+    assert r_b.out_of_window == 0 and r_l.out_of_window == 0
+    assert np.max(np.abs(s_b - s_l) / s_l) < RTOL
+    assert r_b.argmax == r_l.argmax == lo + int(np.argmax(s_l))
+    idx = np.random.default_rng(seed).choice(G, n_spot, replace=False)
+    ref = H.oracle_pos(bcs, grid_shard[idx], ep)
+    assert np.max(np.abs(s_l[idx] - ref["scores"]) / ref["scores"]) < 1e-9      # lookup: FP64 throughout
+    assert np.max(np.abs(s_b[idx] - ref["scores"]) / ref["scores"]) < RTOL
+    return r_b
+
+
+def test_c3_full_grid_21_pow_4_times_12_prns_against_the_oracle(capi):
+    """BASELINE.json config 3 at size: 2.5 MHz, 12 PRNs, uniform 21^4 grid (194 481 candidates)."""
+    sc = H.scenario(2.5e6, synth.PRNS_12)
+    grid, tg = synth.uniform_grid(21, (5.0, 5.0, 5.0, 6.0))
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[:4] += (4.0, -3.0, 2.0, 5.0)
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=grid.shape[0], time_dim=len(tg), lag_halfwidth=16,
+                       flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    r = _spot_check(capi, ctx, sc, grid, ep, iq, H.oracle_bcs(2.5e6, synth.PRNS_12), 0, seed=3)
+    assert ctx.brute_pairs() == grid.shape[0] * 12
+    truth = sc.rx_state(ep["rx_time"])
+    assert np.max(np.abs(np.array(r.z[:3]) - truth[:3])) <= 10.0 and abs(r.z[3] - truth[3]) <= 12.0   # within two grid steps
+    ctx.close()
+
+
+def test_c4_shard_rank_3_of_8_of_51_pow_4_at_10_megahertz_against_the_oracle(capi):
+    """BASELINE.json config 4: what rank 3 of 8 holds of the 51^4 grid (845 651 candidates, 10 MHz, 12 PRNs,
+    S = 200 000): global indices, per-shard arg-max, scores against the oracle."""
+    sc = H.scenario(10.0e6, synth.PRNS_12)
+    grid, tg = synth.uniform_grid(51, (2.0, 2.0, 2.0, 2.0))
+    G = grid.shape[0]
+    per = (G + 7) // 8
+    lo, hi = 3 * per, 4 * per
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[:4] += (4.0, -3.0, 2.0, 5.0)
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    shard = np.ascontiguousarray(grid[lo:hi])
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=hi - lo, time_dim=len(tg), lag_halfwidth=16,
+                       flags=capi.FLAG_BRUTE_TILES, grid_offset=lo, G_total=G)
+    ctx.grid_set(shard)
+    _spot_check(capi, ctx, sc, shard, ep, iq, H.oracle_bcs(10.0e6, synth.PRNS_12), lo, seed=4)
+    assert ctx.brute_pairs() == (hi - lo) * 12
+    ctx.close()
+
+
+def test_c5_independent_streams_own_seed_each_through_two_contexts(capi):
+    """BASELINE.json config 5: independent receiver streams, seeds 20180704 + k, 21^4 grid each.  Streams
+    k = 0, 1, 100, 255 go through two contexts in flight (what bench.py does for all 256); every stream's
+    scores are spot-checked against the oracle and the fix lands within a grid step of its own truth."""
+    grid, tg = synth.uniform_grid(21, (5.0, 5.0, 5.0, 6.0))
+    G = grid.shape[0]
+    ks = (0, 1, 100, 255)
+    cases = []
+    for k in ks:
+        sc = H.scenario(2.5e6, synth.PRNS_8, 20180704 + k)
+        center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+        center[:4] += (4.0, -3.0, 2.0, 5.0)
+        cases.append((sc, sc.block(0), sc.epoch_inputs(0, center=center, time_grid=tg)))
+    assert len({c[1].tobytes() for c in cases}) == len(ks)       # the streams really differ
+    ctxs = []
+    for _ in range(2):
+        c = capi.Context(fs=2.5e6, S=cases[0][0].S, max_chan=8, G=G, time_dim=len(tg), lag_halfwidth=16,
+                         flags=capi.FLAG_BRUTE_TILES)
+        c.grid_set(grid)
+        ctxs.append(c)
+    out = {}
+    for i, (sc, iq, ep) in enumerate(cases):
+        c = ctxs[i % 2]
+        if c.lib.dpe_epoch_pending(c.h):
+            out[i - 2] = (c.epoch_collect(), c.copy_out(capi.PTR_POS_SCORES, np.float64, G))
+        c.epoch_submit(iq, ep, score_mode=capi.SCORE_BRUTE)
+    for i in (len(cases) - 2, len(cases) - 1):
+        c = ctxs[i % 2]
+        out[i] = (c.epoch_collect(), c.copy_out(capi.PTR_POS_SCORES, np.float64, G))
+    for i, (sc, iq, ep) in enumerate(cases):
+        r, s = out[i]
+        idx = np.random.default_rng(50 + i).choice(G, 2000, replace=False)
+        bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                    ep["cp_ref"], ep["fs"])
+        ref = H.oracle_pos(bcs, grid[idx], ep)
+        assert np.max(np.abs(s[idx] - ref["scores"]) / ref["scores"]) < RTOL
+        assert r.argmax == int(np.argmax(s)) and r.out_of_window == 0
+        truth = sc.rx_state(ep["rx_time"])
+        assert np.max(np.abs(np.array(r.z[:3]) - truth[:3])) <= 10.0 and abs(r.z[3] - truth[3]) <= 12.0
+    for c in ctxs:
+        c.close()
