@@ -8,6 +8,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -19,11 +20,18 @@ namespace dsp {
 
 /** One dpe_ctx per flow, shared by the modules of that flow (they all receive the same
  *  `void* cuFlowStream`, which keys the registry).  BatchCorrManifold::Start creates it. */
+struct RankPool;
 struct SharedCtx {
-    dpe_ctx* ctx = nullptr;
+    dpe_ctx* ctx = nullptr;       // rank 0 (the only one when NumGPUs = 1)
     dpe_epoch ep;                 // filled in two halves by BatchCorrScores / BatchCorrManifold
     int score_mode = DPE_SCORE_LOOKUP;
     int est_mode = DPE_EST_ARGMAX;
+    // NumGPUs > 1: the grid is sharded over one context per GPU, each driven by its own host thread; the
+    // whole epoch is then ONE dpe_epoch_run_dist per rank, issued from BatchCorrManifold::Update
+    // (BatchCorrScores::Update only records the block and the channel half of `ep`)
+    RankPool* pool = nullptr;
+    const int16_t* iq = nullptr;  // the block SampleBlock handed over this epoch
+    int64_t iq_len = 0;
 };
 SharedCtx* SharedFor(void* cuFlowStream);
 void SharedRelease(void* cuFlowStream);
@@ -117,6 +125,7 @@ class BatchCorrManifold : public Module {
     // extensions (not in the reference): scoring path, estimator, lag window
     bool bruteForce = false, weightedMean = false;
     int lagHalfwidth = 0, doppHalfwidth = 0;       // 0 = sized from the extent of the grids
+    int numGPUs = 1, device = 0;                   // NumGPUs GPUs starting at ordinal Device
     bool Started = false, haveVel = false;
     void* flowStream = nullptr;
     std::vector<double> grid, timeGrid;
@@ -185,6 +194,13 @@ class DataLogger : public Module {
     char Filename[kNameCap] = {0};
     bool csv = true, Started = false;
     FILE* fp = nullptr;
+    struct Row { int dtype = 0; int64_t n = 0; std::vector<unsigned char> bytes; };
+    std::deque<Row> rows;                          // filled by the flow thread, drained by the writer thread
+    std::thread writer;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool KeepRunning = false, writeFailed = false;
+    void WriterThread();
 };
 
 }  // namespace dsp

@@ -7,12 +7,87 @@
 #include <iostream>
 #include <map>
 #include <mutex>
+#include <string>
+#include <thread>
+#include <condition_variable>
 #include "modules.h"
 
 namespace dsp {
 
 static std::mutex g_mu;
 static std::map<void*, SharedCtx*> g_shared;
+
+// ------------------------------------------------------------------------------------------
+// RankPool: ranks 1..N-1 of a multi-GPU flow, one host thread per GPU (NCCL collectives of one
+// communicator must be issued by concurrent callers; the flow thread is rank 0).  Each worker owns a
+// context holding its contiguous shard of the grid and runs dpe_epoch_run_dist once per epoch.
+// ------------------------------------------------------------------------------------------
+struct RankPool {
+    struct Job { const dpe_epoch* ep = nullptr; const double* sat = nullptr; int score = 0, est = 0; };
+    std::vector<dpe_ctx*> ctx;            // [r], r = 0 is owned by SharedCtx
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    long epoch = 0;
+    int pending = 0, failed = 0;
+    bool quit = false;
+    Job job;
+    std::string error;
+
+    void Worker(int r, dpe_cfg cfg, std::vector<double> shard, int nranks, std::vector<unsigned char> id) {
+        bool ok = dpe_ctx_create(&ctx[r], &cfg) == DPE_OK &&
+                  dpe_grid_set(ctx[r], shard.data(), cfg.G, dpe_ctx_stream(ctx[r])) == DPE_OK &&
+                  dpe_comm_init(ctx[r], nranks, r, id.data()) == DPE_OK;
+        std::vector<double>().swap(shard);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!ok) { ++failed; error = dpe_last_error(); }
+            --pending;
+        }
+        cv.notify_all();
+        long seen = 0;
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || epoch != seen; });
+                if (quit) break;
+                seen = epoch;
+                j = job;
+            }
+            dpe_result res;
+            const int rc = ok ? dpe_epoch_run_dist(ctx[r], nullptr, j.ep, j.sat, j.score, j.est, 0, &res) : DPE_ESTATE;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (rc) { ++failed; error = dpe_last_error(); }
+                --pending;
+            }
+            cv.notify_all();
+        }
+        if (ctx[r]) { dpe_ctx_destroy(ctx[r]); ctx[r] = nullptr; }
+    }
+    // rank 0's side of one epoch: wake the workers, run the root's call, wait for everybody
+    int Run(dpe_ctx* root, const int16_t* iq, const dpe_epoch* ep, const double* sat, int score, int est, int with_vel,
+            dpe_result* out) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job.ep = ep; job.sat = sat; job.score = score; job.est = est;
+            pending = (int)workers.size();
+            ++epoch;
+        }
+        cv.notify_all();
+        const int rc = dpe_epoch_run_dist(root, iq, ep, sat, score, est, with_vel, out);
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return pending == 0; });
+        return (rc || failed) ? -1 : 0;
+    }
+    void Shutdown() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        for (size_t i = 0; i < workers.size(); ++i) if (workers[i].joinable()) workers[i].join();
+        workers.clear();
+    }
+};
 
 SharedCtx* SharedFor(void* key) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -25,6 +100,7 @@ void SharedRelease(void* key) {
     std::lock_guard<std::mutex> lk(g_mu);
     std::map<void*, SharedCtx*>::iterator it = g_shared.find(key);
     if (it == g_shared.end()) return;
+    if (it->second->pool) { it->second->pool->Shutdown(); delete it->second->pool; }
     if (it->second->ctx) dpe_ctx_destroy(it->second->ctx);
     delete it->second;
     g_shared.erase(it);
@@ -91,6 +167,12 @@ int BatchCorrScores::Update(void* cuFlowStream) {
         ep.cp_start[i] = In<int>(6)[i];
         ep.cp_ref[i] = In<int>(7)[i];
     }
+    if (sh->pool) {                                // multi-GPU: the epoch runs as one call in BatchCorrManifold::Update
+        sh->iq = In<int16_t>(0);
+        sh->iq_len = InLen(0);
+        UpdateOutput(0, C, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_CODE_SCORES)), 0);
+        return 0;
+    }
     DPE_CALL(dpe_block_stage(sh->ctx, In<int16_t>(0), InLen(0), stream));
     DPE_CALL(dpe_epoch_set_part(sh->ctx, &ep, nullptr, DPE_PART_CHANNELS, stream));
     DPE_CALL(dpe_replica_prepare(sh->ctx, stream));
@@ -137,6 +219,8 @@ BatchCorrManifold::BatchCorrManifold() {
     InsertParam("WeightedMean", &weightedMean, BOOL_t, sizeof(bool), sizeof(bool));      // dormant Method 1
     InsertParam("LagHalfwidth", &lagHalfwidth, INT_t, sizeof(int), sizeof(int));
     InsertParam("DopplerHalfwidth", &doppHalfwidth, INT_t, sizeof(int), sizeof(int));
+    InsertParam("NumGPUs", &numGPUs, INT_t, sizeof(int), sizeof(int));                    // grid sharded over GPUs
+    InsertParam("Device", &device, INT_t, sizeof(int), sizeof(int));                      // first CUDA ordinal
     AllocateOutputs(4);
     ConfigOutput(0, "zVal", DOUBLE_t, STATE, HOST, 8, zVal, 0);
     ConfigOutput(1, "RVal", DOUBLE_t, COVARIANCE, HOST, 64, RVal, 0);
@@ -170,7 +254,13 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
     dpe_cfg cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.abi_version = DPE_ABI_VERSION;
-    cfg.device = 0;
+    const int ndev = dpe_device_count();
+    if (numGPUs < 1 || device < 0 || device + numGPUs > ndev) {
+        std::cerr << "[" << ModuleName << "] Device " << device << " + NumGPUs " << numGPUs << " exceeds the "
+                  << ndev << " visible GPU(s)" << std::endl;
+        return -1;
+    }
+    cfg.device = device;
     cfg.fs = fs;
     cfg.S = (int64_t)(fs * T + 0.5);
     cfg.max_chan = DPE_MAX_CHAN;
@@ -211,17 +301,50 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
         cfg.dopp_halfwidth = Wd;
     }
     SharedCtx* sh = SharedFor(cuFlowStream);
+    if (sh->pool) { sh->pool->Shutdown(); delete sh->pool; sh->pool = nullptr; }
     if (sh->ctx) { dpe_ctx_destroy(sh->ctx); sh->ctx = nullptr; }
+    const int64_t G_total = cfg.G_total;
+    const int64_t per = (G_total + numGPUs - 1) / numGPUs;          // contiguous index ranges (sharding.py::shard_range)
+    cfg.G = std::min(per, G_total);
+    cfg.grid_offset = 0;
     DPE_CALL(dpe_ctx_create(&sh->ctx, &cfg));
     sh->score_mode = bruteForce ? DPE_SCORE_BRUTE : DPE_SCORE_LOOKUP;
     sh->est_mode = weightedMean ? DPE_EST_WEIGHTED : DPE_EST_ARGMAX;
     void* stream = StreamOf(cuFlowStream);
+    if (numGPUs > 1) {
+        unsigned char id[DPE_COMM_ID_BYTES];
+        DPE_CALL(dpe_comm_get_unique_id(id));
+        RankPool* pool = new RankPool();
+        sh->pool = pool;
+        pool->ctx.assign(numGPUs, nullptr);
+        pool->ctx[0] = sh->ctx;
+        pool->pending = numGPUs - 1;
+        for (int r = 1; r < numGPUs; ++r) {
+            dpe_cfg rc = cfg;
+            rc.device = device + r;
+            rc.grid_offset = std::min((int64_t)r * per, G_total);
+            rc.G = std::min(per, G_total - rc.grid_offset);
+            rc.Gv = 0;                                              // the velocity manifold runs on rank 0 only
+            if (rc.G < 1) { std::cerr << "[" << ModuleName << "] more GPUs than grid points" << std::endl; return -1; }
+            std::vector<double> shard(grid.begin() + 4 * rc.grid_offset, grid.begin() + 4 * (rc.grid_offset + rc.G));
+            pool->workers.emplace_back(&RankPool::Worker, pool, r, rc, std::move(shard), numGPUs,
+                                       std::vector<unsigned char>(id, id + DPE_COMM_ID_BYTES));
+        }
+        DPE_CALL(dpe_comm_init(sh->ctx, numGPUs, 0, id));           // collective: returns once every rank has joined
+        std::unique_lock<std::mutex> lk(pool->mu);
+        pool->cv.wait(lk, [&] { return pool->pending == 0; });
+        if (pool->failed) {
+            std::cerr << "[" << ModuleName << "] a GPU rank failed to start: " << pool->error << std::endl;
+            return -1;
+        }
+        std::clog << "[" << ModuleName << "] grid sharded over " << numGPUs << " GPUs, " << per << " candidates each" << std::endl;
+    }
     DPE_CALL(dpe_grid_set(sh->ctx, grid.data(), cfg.G, stream));
     if (cfg.Gv > 0) DPE_CALL(dpe_vel_grid_set(sh->ctx, vgrid.data(), cfg.Gv, stream));
     haveVel = cfg.Gv > 0;
     DPE_CALL(dpe_stream_sync(stream));
     UpdateOutput(2, (int64_t)timeGrid.size(), timeGrid.data(), 0);
-    UpdateOutput(3, cfg.G, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_POS_SCORES)), 0);
+    UpdateOutput(3, cfg.G, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_POS_SCORES)), 0);   // rank 0's shard
     flowStream = cuFlowStream;
     Started = true;
     return 0;
@@ -244,12 +367,21 @@ int BatchCorrManifold::Update(void* cuFlowStream) {
     ep.rx_time = *In<double>(5);
     for (int i = 0; i < 8; ++i) ep.center[i] = In<double>(2)[i];
     for (int i = 0; i < 9; ++i) ep.enu2ecef[i] = In<double>(12)[i];
-    DPE_CALL(dpe_epoch_set_part(sh->ctx, &ep, In<double>(4), DPE_PART_GEOMETRY, stream));
-    const int sat_mode = (sh->est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
-    DPE_CALL(dpe_score_pos(sh->ctx, sh->score_mode, sat_mode, stream));
-    DPE_CALL(dpe_estimate(sh->ctx, sh->est_mode, nullptr, 1, stream));
-    if (haveVel) DPE_CALL(dpe_score_vel(sh->ctx, stream));
-    DPE_CALL(dpe_result_fetch(sh->ctx, &last, stream));
+    if (sh->pool) {
+        // one dpe_epoch_run_dist per GPU: rank 0 uploads the packet, NCCL broadcasts it, every rank scores its
+        // shard, the partials are all-gathered and reduced on every rank (include/dpe_b200.h, "multi-GPU")
+        if (sh->pool->Run(sh->ctx, sh->iq, &ep, In<double>(4), sh->score_mode, sh->est_mode, haveVel ? 1 : 0, &last)) {
+            std::cerr << "[" << ModuleName << "] multi-GPU epoch failed: " << dpe_last_error() << " " << sh->pool->error << std::endl;
+            return -1;
+        }
+    } else {
+        DPE_CALL(dpe_epoch_set_part(sh->ctx, &ep, In<double>(4), DPE_PART_GEOMETRY, stream));
+        const int sat_mode = (sh->est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
+        DPE_CALL(dpe_score_pos(sh->ctx, sh->score_mode, sat_mode, stream));
+        DPE_CALL(dpe_estimate(sh->ctx, sh->est_mode, nullptr, 1, stream));
+        if (haveVel) DPE_CALL(dpe_score_vel(sh->ctx, stream));
+        DPE_CALL(dpe_result_fetch(sh->ctx, &last, stream));
+    }
     if (last.out_of_window)
         std::clog << "[" << ModuleName << "] " << last.out_of_window << " candidate-PRN pairs outside the lag window"
                   << std::endl;

@@ -232,6 +232,9 @@ int SampleBlock::Stop() {
     if (!Started) return 0;
     KeepRunning = false;
     { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
+    // a reader blocked in read() on an idle TCP sender must come back: shut the socket down first
+    // (ENOTSOCK on a capture file, harmless)
+    if (fd >= 0) ::shutdown(fd, SHUT_RDWR);
     if (reader.joinable()) reader.join();
     for (size_t i = 0; i < Blocks.size(); ++i) dpe_host_free(Blocks[i]);
     Blocks.clear();
@@ -382,31 +385,67 @@ int DataLogger::Start(void*) {
     if (inputs[0]->MemLoc != HOST) { std::cerr << "[" << ModuleName << "] only HOST ports can be logged" << std::endl; return -1; }
     fp = std::fopen(Filename, csv ? "w" : "wb");
     if (!fp) { std::cerr << "[" << ModuleName << "] cannot open " << Filename << std::endl; return -1; }
+    KeepRunning = true;
+    writeFailed = false;
+    writer = std::thread(&DataLogger::WriterThread, this);
     Started = true;
     return 0;
 }
 
+// The flow thread only copies the port into a queued row; formatting and file I/O happen on the writer
+// thread (the reference: double-buffered D2H + writer pthread, datalogger.cu:113-213,215-278).
 int DataLogger::Update(void*) {
     const Port* p = inputs[0];
     const int64_t n = p->Length;
-    if (!csv) {
-        const size_t sz = (p->Datatype == DOUBLE_t) ? 8 : (p->Datatype == INT_t || p->Datatype == FLOAT_t) ? 4 : 1;
-        return std::fwrite(p->Data, sz, (size_t)n, fp) == (size_t)n ? 0 : -1;
+    const size_t sz = (p->Datatype == DOUBLE_t) ? 8 : (p->Datatype == INT_t || p->Datatype == FLOAT_t) ? 4 : 1;
+    Row r;
+    r.dtype = p->Datatype;
+    r.n = n;
+    r.bytes.assign(static_cast<const unsigned char*>(p->Data), static_cast<const unsigned char*>(p->Data) + sz * (size_t)n);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (writeFailed) return -1;
+        rows.push_back(std::move(r));
     }
-    for (int64_t i = 0; i < n; ++i) {
-        double v = 0;
-        switch (p->Datatype) {
-            case DOUBLE_t: v = static_cast<const double*>(p->Data)[i]; break;
-            case FLOAT_t: v = static_cast<const float*>(p->Data)[i]; break;
-            case INT_t: v = static_cast<const int*>(p->Data)[i]; break;
-            default: v = static_cast<const char*>(p->Data)[i]; break;
-        }
-        std::fprintf(fp, (i + 1 < n) ? "%f, " : "%f\n", v);
-    }
+    cv.notify_one();
     return 0;
 }
 
+void DataLogger::WriterThread() {
+    for (;;) {
+        Row r;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !rows.empty() || !KeepRunning; });
+            if (rows.empty()) break;                  // stop requested and everything written
+            r = std::move(rows.front());
+            rows.pop_front();
+        }
+        bool ok = true;
+        if (!csv) {
+            ok = std::fwrite(r.bytes.data(), 1, r.bytes.size(), fp) == r.bytes.size();
+        } else {
+            for (int64_t i = 0; i < r.n && ok; ++i) {
+                double v = 0;
+                switch (r.dtype) {
+                    case DOUBLE_t: v = reinterpret_cast<const double*>(r.bytes.data())[i]; break;
+                    case FLOAT_t: v = reinterpret_cast<const float*>(r.bytes.data())[i]; break;
+                    case INT_t: v = reinterpret_cast<const int*>(r.bytes.data())[i]; break;
+                    default: v = reinterpret_cast<const char*>(r.bytes.data())[i]; break;
+                }
+                ok = std::fprintf(fp, (i + 1 < r.n) ? "%f, " : "%f\n", v) > 0;
+            }
+        }
+        if (!ok) { std::lock_guard<std::mutex> lk(mu); writeFailed = true; }
+    }
+}
+
 int DataLogger::Stop() {
+    if (writer.joinable()) {
+        { std::lock_guard<std::mutex> lk(mu); KeepRunning = false; }
+        cv.notify_all();
+        writer.join();                                // drains the queue first
+    }
     if (fp) { std::fclose(fp); fp = nullptr; }
     Started = false;
     return 0;

@@ -24,7 +24,9 @@ import numpy as np
 from . import gpsmath as gm
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_RINEX = os.path.join(os.path.dirname(_HERE), "tests", "golden", "nist_brdc_toe417600.18n")
+# broadcast ephemerides of the TOE = 417600 s set (GPS week 2008, day 186 of 2018) in RINEX 2.10 nav format:
+# the records of the reference's demofiles/nist1860.18n the demo epoch uses
+DEFAULT_RINEX = os.path.join(_HERE, "data", "brdc_toe417600.18n")
 
 PRNS_8 = (2, 3, 6, 12, 17, 19, 24, 28)          # demofiles/handoff_params_usrp6.csv:5
 PRNS_12 = PRNS_8 + (1, 5, 22, 30)               # the other TOE=417600 satellites

@@ -21,5 +21,5 @@ within 0.006 chip of the handed-off code phase for all 8 PRNs), and (c) outputs
 of the reference CUDARecv modules themselves, rebuilt unmodified for sm_100a
 (``oracle/Makefile`` -> ``oracle/_ref``) and run on a B200 through
 ``oracle/ref_driver.cu``; those outputs are committed under ``tests/golden/``
-together with the script that produced them (``oracle/make_golden_ref.sh``).
+together with the script that produced them (``oracle/make_golden_ref.py``).
 """

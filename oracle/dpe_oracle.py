@@ -364,6 +364,49 @@ def pos_meas_weighted(code_scores, grid, center, enu2ecef, sat_states, time_dim,
     return dict(scores=scores, z=z, sum_score=tot)
 
 
+def pos_meas_reduction(code_scores, grid, center, enu2ecef, sat_states, time_dim, code_freq, tx_time,
+                       rx_time, fs, S, lpower=1, n_blocks=8, n_threads=64):
+    """The reference's DORMANT weighted-mean estimator exactly as written: BCM_PosMeasReduction
+    (batchcorrmanifold.cu:816-1056) + BCM_ReduceAndPosMeas (:1365-1510), launch shape <<<8, 64>>> then
+    <<<1, 8>>> (:2548-2563, commented out there; oracle/ref_driver.cu -DREF_WEIGHTED launches them).
+
+    Differences from the ML kernel that this restatement keeps: the satellite state is the one of the
+    candidate's own time-grid index (:865-873), and the code index is back-calculated from ``txTime``
+    (:876-882: satPosTransmitTime = rxTime - (txTime + dt/c) + sat.dt; bc_rc0 = F_CA (that - range/c)),
+    algebraically the ML expression (:1779-1791) in another rounding order.
+
+    Returns dict(z[4], parts[n_blocks][5] = per-block {a, b, c, d, score} (grid-stride partition of the
+    candidates over blocks * threads), sum_score, scores[G]).
+    """
+    grid = np.asarray(grid, np.float64)
+    G = grid.shape[0]
+    C = len(code_freq)
+    sat = np.asarray(sat_states, np.float64).reshape(C, time_dim, 8)
+    px, py, pz, pt = candidate_ecef(grid, center, enu2ecef)
+    it = np.arange(G) % time_dim                                          # :865
+    flat = np.asarray(code_scores).reshape(-1)
+    scores = np.zeros(G)
+    for c in range(C):
+        s = sat[c, it]                                                    # :873
+        tof = rx_time - (tx_time[c] + (pt / CONST_C)) + s[:, 3]           # :876
+        rngt = _norm3(s[:, 0] - px, s[:, 1] - py, s[:, 2] - pz) / CONST_C  # :880
+        bc_rc0 = CONST_F_CA * (tof - rngt)                                # :881
+        idx_base = (fs / code_freq[c]) * (-bc_rc0) + S / 2.0              # :882
+        idxo = idx_base + S * c                                           # :888
+        f_idx = np.floor(idxo).astype(np.int64)
+        c_idx = np.floor(idxo + 1).astype(np.int64)
+        v = flat[np.minimum(c_idx, flat.shape[0] - 1)] * (idxo - f_idx) + flat[f_idx] * (c_idx - idxo)   # :901-902
+        scores = scores + np.abs(v) ** lpower                             # :906
+    stride = n_blocks * n_threads
+    parts = np.zeros((n_blocks, 5))
+    w = np.stack([scores * px, scores * py, scores * pz, scores * pt, scores], axis=1)    # :911-915
+    tid = np.arange(G) % stride
+    for b in range(n_blocks):
+        parts[b] = w[(tid // n_threads) == b].sum(axis=0)
+    tot = parts.sum(axis=0)
+    return dict(z=tot[:4] / tot[4], parts=parts, sum_score=tot[4], scores=scores)   # :1497-1500
+
+
 # ---- velocity manifold (next row f-1) --------------------------------------
 
 def init_vel_grid(dims, spacing):

@@ -50,8 +50,8 @@ def golden_files(work, epochs, n, offset):
         if l.startswith("X_ECEF,"):
             v = [float(x) for x in l.split(",")[1:]]
             for k in range(4):
-                v[k] += offset[k]
-            lines[i] = "X_ECEF," + ",".join(repr(x) for x in v)
+                v[k] += float(offset[k])
+            lines[i] = "X_ECEF," + ",".join(repr(float(x)) for x in v)
     open(files["handoff"], "w").write("\n".join(lines) + "\n")
     return sc, grid, files
 
@@ -152,7 +152,7 @@ def main():
         open(os.path.join(a.out, "ref_XFile.csv"), "w").write(open(os.path.join(dump, "XFile.csv")).read())
 
 
-LONGRUN = dict(truth_vel_enu=(2.0, 1.5, 0.3), offset=(3.3, -2.1, 1.7, 4.4), vel_dim=25, vel_spacing=0.5, W=4)
+LONGRUN = dict(truth_vel_enu=(12.0, 8.0, 1.0), offset=(3.3, -2.1, 1.7, 4.4), vel_dim=25, vel_spacing=0.5, W=4)
 
 
 def longrun_scenario():
@@ -169,8 +169,8 @@ def longrun_files(work, epochs):
         if l.startswith("X_ECEF,"):
             v = [float(x) for x in l.split(",")[1:]]
             for k in range(4):
-                v[k] += LONGRUN["offset"][k]
-            lines[i] = "X_ECEF," + ",".join(repr(x) for x in v)
+                v[k] += float(LONGRUN["offset"][k])
+            lines[i] = "X_ECEF," + ",".join(repr(float(x)) for x in v)
     open(files["handoff"], "w").write("\n".join(lines) + "\n")
     return sc, files
 
@@ -188,7 +188,8 @@ def longrun(a, exe):
     if r.returncode != 0:
         sys.exit("reference run failed (%d)" % r.returncode)
     n = a.longrun
-    names_f = ("rx_time", "rc_start", "ri_start", "rc_end", "fc", "fi", "x_kk1", "x_k1k1", "zval", "code_scores_win")
+    names_f = ("rx_time", "tx_time", "rc_start", "ri_start", "rc_end", "fc", "fi", "x_kk1", "x_k1k1", "zval",
+               "code_scores_win", "sat_raw", "enu2ecef")
     names_i = ("cp_ref", "cp_start", "cp_end", "cp_ref_tow")
     pack = dict(epochs=n, W=W, S=sc.S, fs=sc.cfg.fs, first_block=1, truth_vel_enu=np.array(LONGRUN["truth_vel_enu"]),
                 offset=np.array(LONGRUN["offset"]), vel_dim=LONGRUN["vel_dim"], vel_spacing=LONGRUN["vel_spacing"],

@@ -154,10 +154,8 @@ class RefHarness : public dsp::DPEFlow {
         DumpDev(out, e, "ri_end", m, "CarrierPhaseEnd", C * sizeof(double));
         DumpDev(out, e, "fc", m, "CodeFrequency", C * sizeof(double));
         DumpDev(out, e, "fi", m, "CarrierFrequency", C * sizeof(double));
-        if (!light) {
-            DumpDev(out, e, "sat_states", m, "SatStates", (size_t)CT * 8 * sizeof(double));
-            DumpDev(out, e, "sat_raw", m, "SatStatesOld", (size_t)C * 8 * sizeof(double));
-        }
+        if (!light) DumpDev(out, e, "sat_states", m, "SatStates", (size_t)CT * 8 * sizeof(double));
+        DumpDev(out, e, "sat_raw", m, "SatStatesOld", (size_t)C * 8 * sizeof(double));
         DumpDev(out, e, "prn", m, "ValidPRNs", C);
         DumpDev(out, e, "cp_ref", m, "cpReference", C * sizeof(int));
         DumpDev(out, e, "cp_start", m, "cpElapsedStart", C * sizeof(int));

@@ -11,7 +11,7 @@ sc = synth.Scenario()
 grid, _ = synth.uniform_grid(9, (5.0, 5.0, 5.0, 6.0))
 print(sc.write_files("/tmp/refrun", 6, grid=grid, handoff_block=1))
 PY
-R=tests/golden/nist_brdc_toe417600.18n
+R=navlab-dpe-sdr_b200/data/brdc_toe417600.18n
 timeout 300 compute-sanitizer --tool memcheck --print-limit 5 oracle/_ref/ref_dpe /tmp/refrun/synthetic_l1ca_2500kHz.dat \
    /tmp/refrun/handoff_params_synth.csv $R /tmp/refrun/rngrid_synth.csv 9 5 1 /tmp/refrun/dump 32 2.5e6 1 \
    > gpurun_out/ref_sanitizer.log 2>&1

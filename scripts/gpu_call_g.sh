@@ -10,7 +10,7 @@ synth = dpe_pkg.submodule("synth")
 sc = synth.Scenario()
 print(sc.write_files("/tmp/refrun", 110, grid=synth.spread_grid(), handoff_block=1))
 PY
-R=tests/golden/nist_brdc_toe417600.18n
+R=navlab-dpe-sdr_b200/data/brdc_toe417600.18n
 for V in 5 25; do
   timeout 300 oracle/_ref/ref_dpe /tmp/refrun/synthetic_l1ca_2500kHz.dat /tmp/refrun/handoff_params_synth.csv $R \
      /tmp/refrun/rngrid_synth.csv 25 $V 60 /tmp/refrun/dump_v$V 32 2.5e6 0 > gpurun_out/ref/ref_timing_pos25_vel$V.log 2>&1

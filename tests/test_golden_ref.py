@@ -263,3 +263,64 @@ def test_cuda_path_matches_reference_golden(gold, capi):
         assert np.max(np.abs(np.array(rv.z[4:8]) - gold.k(e, "zval")[4:8])) < 1e-9
         cv.close()
     assert n_race_free >= gold.epochs * gold.C // 3
+
+
+# ---- a13: the reference's DORMANT score-weighted estimator, executed -----------------
+# tests/golden/ref_weighted_n9.npz: oracle/_ref/ref_dpe_weighted launches BCM_PosMeasReduction <<<8,64>>> +
+# BCM_ReduceAndPosMeas <<<1,8>>> (batchcorrmanifold.cu:816-1056, 1365-1510; launches commented out at
+# :2547-2567) on the module's own buffers after every epoch (oracle/make_golden_ref.py --weighted).
+def _weighted_gold():
+    g = np.load(os.path.join(os.path.dirname(GOLD), "ref_weighted_n9.npz"))
+    C, T, S, W, fs = int(g["C"]), int(g["T"]), int(g["S"]), int(g["W"]), float(g["fs"])
+    out = []
+    for e in range(int(g["epochs"])):
+        k = lambda n: g["e%d_%s" % (e, n)]
+        w = k("code_scores_win").reshape(C, 2 * W + 2, 2)
+        ep = dict(prn=k("prn"), rc_start=k("rc_start"), ri_start=k("ri_start"), fc=k("fc"), fi=k("fi"),
+                  cp_start=k("cp_start"), cp_ref=k("cp_ref"), rc_end=k("rc_end"), cp_end=k("cp_end"),
+                  cp_ref_tow=k("cp_ref_tow"), rx_time=float(k("rx_time")[0]), center=k("x_kk1"), enu2ecef=k("enu2ecef"),
+                  sat_states=k("sat_states").reshape(-1, 8), doppler_sign=1, S=S, fs=fs, time_dim=T)
+        out.append(dict(ep=ep, win=w[..., 0] + 1j * w[..., 1], tx_time=k("tx_time"), z=k("zval_weighted"),
+                        parts=k("weighted_parts"), z_ml=k("zval")))
+    return dict(C=C, T=T, S=S, W=W, fs=fs, grid=g["grid"], epochs=out)
+
+
+def test_oracle_weighted_estimator_matches_the_reference_kernels():
+    wg = _weighted_gold()
+    S, W, C = wg["S"], wg["W"], wg["C"]
+    assert len(wg["epochs"]) == 3
+    for e in wg["epochs"]:
+        ep = e["ep"]
+        full = np.zeros((C, S), complex)
+        full[:, S // 2 - W: S // 2 - W + 2 * W + 2] = e["win"]
+        # the kernel as written: txTime form of the code index, per-time satellite state, <<<8,64>>> partition
+        r = orc.pos_meas_reduction(full, wg["grid"], ep["center"], ep["enu2ecef"], ep["sat_states"], wg["T"], ep["fc"],
+                                   e["tx_time"], ep["rx_time"], wg["fs"], S)
+        assert np.max(np.abs(r["z"] - e["z"])) < 1e-7                           # metres
+        assert np.max(np.abs(r["parts"] - e["parts"]) / np.abs(e["parts"])) < 1e-11
+        # the form the product uses (the ML kernel's code-index expression, :1779-1791): same estimate to 2e-5 m
+        # (txTime ~ 4e5 s carries 6e-11 s = 6e-5 chip of rounding into every bin of the reduction kernel)
+        r2 = orc.pos_meas_weighted(full, wg["grid"], ep["center"], ep["enu2ecef"], ep["sat_states"], wg["T"], ep["fc"],
+                                   ep["rc_end"], ep["cp_ref_tow"], ep["cp_end"], ep["cp_ref"], ep["rx_time"], wg["fs"], S,
+                                   per_time_sat=True)
+        assert np.max(np.abs(r2["z"] - e["z"])) < 1e-4
+        assert abs(r2["sum_score"] / e["parts"][:, 4].sum() - 1.0) < 1e-5
+        # and it is a different estimate from the arg-max the reference actually publishes
+        assert np.max(np.abs(e["z"] - e["z_ml"][:4])) > 1e-3
+
+
+@pytest.mark.gpu
+def test_cuda_weighted_estimator_matches_the_reference_kernels(capi):
+    wg = _weighted_gold()
+    G = wg["grid"].shape[0]
+    for e in wg["epochs"]:
+        ctx = capi.Context(fs=wg["fs"], S=wg["S"], max_chan=wg["C"], G=G, time_dim=wg["T"], lag_halfwidth=wg["W"])
+        ctx.grid_set(wg["grid"])
+        ctx.epoch_set(e["ep"])
+        ctx.code_scores_set(e["win"])                       # the reference's own CodeScores rows
+        ctx.score_pos(capi.SCORE_LOOKUP, capi.SAT_PER_TIME)
+        ctx.estimate(capi.EST_WEIGHTED)
+        res = ctx.result_fetch()
+        assert np.max(np.abs(np.array(res.z[:4]) - e["z"])) < 1e-4          # bar: 0.1 m / 0.2998 m
+        assert abs(res.sum_score / e["parts"][:, 4].sum() - 1.0) < 1e-5
+        ctx.close()

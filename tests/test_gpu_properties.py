@@ -194,7 +194,7 @@ def _spot_check(capi, ctx, sc, grid_shard, ep, iq, bcs, lo, seed, n_spot=2000):
     assert r_b.argmax == r_l.argmax == lo + int(np.argmax(s_l))
     idx = np.random.default_rng(seed).choice(G, n_spot, replace=False)
     ref = H.oracle_pos(bcs, grid_shard[idx], ep)
-    assert np.max(np.abs(s_l[idx] - ref["scores"]) / ref["scores"]) < 1e-9      # lookup: FP64 throughout
+    assert np.max(np.abs(s_l[idx] - ref["scores"]) / ref["scores"]) < 1e-6      # lookup: FP32 products in the correlogram
     assert np.max(np.abs(s_b[idx] - ref["scores"]) / ref["scores"]) < RTOL
     return r_b
 

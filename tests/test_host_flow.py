@@ -384,3 +384,67 @@ def test_dpe_flow_with_the_kalman_filter_enabled_matches_the_reference(flowapi, 
     xkk1 = sh.read_port("rx", "cuEKF", "xCurrkk1")
     assert abs((xkk1[3] - g["e0_x_kk1"][3]) - epochs * 0.02 * g["e0_x_kk1"][7]) < 1e-3
     sh.close()
+
+
+REF_RINEX = "/root/reference/demofiles/nist1860.18n"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_RINEX), reason="the reference checkout is not on this box")
+def test_host_rinex_reader_and_nearest_toe_on_the_reference_demo_file(flowapi):
+    """The reference's shipped RINEX 2.10 nav file holds 26 TOE sets (172752 ... 432000 s) with 1 to 15
+    satellites each: ReadRinexNav's grouping (rinexparse.cpp:199-217) and the brute-force nearest-TOE
+    selection (cuchanmgr.cu:276-292) of the host C++ against the oracle, for every PRN across the day,
+    including times exactly between two sets and the 16-second-apart pairs (…584 / …600)."""
+    nav = chm.read_rinex_nav(REF_RINEX)
+    assert len(nav) == 26 and {s.toes for s in nav} >= {417600.0, 395968.0, 395984.0, 396000.0, 172752.0}
+    toes = sorted(s.toes for s in nav)
+    times = [345000.0 + 1777.0 * k for k in range(52)]
+    times += [0.5 * (a + b) for a, b in zip(toes[:-1], toes[1:])]           # ties / midpoints
+    times += [t + d for t in (395968.0, 395984.0, 396000.0, 410384.0) for d in (-8.0, -0.001, 0.0, 0.001, 8.0)]
+    n = 0
+    for prn in range(1, 33):
+        for t in times:
+            e = chm.select_eph(nav, prn, t)
+            assert e is not None
+            ref = chm.get_sat_pos(e, t)
+            got = flowapi.sat_position(REF_RINEX, prn, t)
+            assert np.max(np.abs(got[:3] - ref[:3])) < 1e-5, (prn, t, e.toes)      # a wrong set is off by metres to km
+            assert np.max(np.abs(got[4:7] - ref[4:7])) < 1e-8
+            assert abs(got[3] - ref[3]) < 1e-14 and abs(got[7] - ref[7]) < 1e-17
+            n += 1
+    assert n == 32 * len(times)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("brute", [False, True])
+def test_dpe_flow_sharded_over_gpus_equals_the_single_gpu_flow(flowapi, tmp_path, brute):
+    """`setparam <flow> BatchCorrManifold NumGPUs N`: the console flow shards the grid over N GPUs of this
+    process (one host thread + one NCCL rank per GPU, one dpe_epoch_run_dist per rank and epoch) and logs
+    the same fixes as the single-GPU flow."""
+    import torch
+    ngpu = min(torch.cuda.device_count(), 4)
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    n, epochs = 7, 5
+    sc, grid, files = _write_scenario(tmp_path, n, epochs, first_block=0)
+    extra = ["setparam rx DPInit InitDeltaX 6.0", "setparam rx DPInit InitDeltaY -4.0",
+             "setparam rx DPInit InitDeltaZ 3.0", "setparam rx DPInit InitDeltaT 7.0"]
+    if brute:
+        extra.append("setparam rx BatchCorrManifold BruteForce true")
+    x1, xn = str(tmp_path / "X1.csv"), str(tmp_path / "XN.csv")
+    _drive(flowapi, files, n, extra, epochs, x1).close()
+    sh = _drive(flowapi, files, n, extra + ["setparam rx BatchCorrManifold NumGPUs %d" % ngpu], epochs, xn)
+    assert sh.stats("rx")["run_count"] == epochs
+    sh.close()
+    a, b = np.loadtxt(x1, delimiter=","), np.loadtxt(xn, delimiter=",")
+    assert a.shape == b.shape == (epochs, 8)
+    assert np.array_equal(a, b)
+    # a device ordinal that does not exist is refused at start
+    sh = flowapi.Shell()
+    for c in ["newflow dpe rx", "loadflow rx", 'setparam rx SampleBlock Filename "%s"' % files["dat"],
+              'setparam rx DPInit HandoffFilename "%s"' % files["handoff"],
+              'setparam rx DPInit RINEXFilename "%s"' % files["rinex"],
+              "setparam rx BatchCorrManifold PosGridDimSize 5", "setparam rx BatchCorrManifold Device 64"]:
+        assert sh.exec(c) == 0
+    assert sh.run_blocking("rx", 1) != 0
+    sh.close()

@@ -103,7 +103,7 @@ def test_demo_handoff_and_rinex_are_mutually_consistent():
     """The reference's two checked-in demo inputs: the code phase back-calculated from
     ephemeris + handoff state (cuchanmgr.cu:85-210, batchcorrmanifold.cu:1779-1790) lands
     within 0.006 chip of the handed-off code phase for all 8 PRNs."""
-    nav = chm.read_rinex_nav(os.path.join(GOLDEN, "nist_brdc_toe417600.18n"))
+    nav = chm.read_rinex_nav(synth.DEFAULT_RINEX)
     h = chm.read_handoff(os.path.join(GOLDEN, "handoff_params_usrp6.csv"))
     assert list(h["prn_list"]) == [2, 3, 6, 12, 17, 19, 24, 28]
     x = h["X_ECEF"]
