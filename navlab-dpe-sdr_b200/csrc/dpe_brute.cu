@@ -485,7 +485,11 @@ int launch_brute_corr(dpe_ctx* c, cudaStream_t s) {
         c->brute_attr_set = 1;
     }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
-    k_brute<<<c->sm_count, kBfWarps * 32, smem, s>>>(
+    // With a communicator, k_brute leaves `comm_reserve_sms` SMs alone: an NCCL kernel needs a whole SM, and with
+    // every SM under a persistent k_brute CTA the broadcast of the NEXT epoch (and the all-gather of the previous one)
+    // would wait for this launch to end -- the pre-pass they gate could then not run under it.
+    const int n_cta = c->sm_count - (c->comm ? c->comm_reserve_sms : 0);
+    k_brute<<<n_cta > 0 ? n_cta : 1, kBfWarps * 32, smem, s>>>(
         c->bx, c->brd, c->bx_stride, c->brd_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
         c->H, c->W, c->tail_part, c->tail_ticket);

@@ -8,6 +8,7 @@
 // this extends BatchCorrManifold::Update (batchcorrmanifold.cu:2501-2635) over the GPUs of a box.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "dpe_internal.cuh"
@@ -125,6 +126,9 @@ int dpe_comm_init(dpe_ctx* c, int nranks, int rank, const void* id) {
         return DPE_ENOMEM;
     }
     cudaMemset(gathered, 0, sizeof(double) * dpe::kPartialLen * nranks);
+    const char* rs = getenv("DPE_COMM_RESERVE_SMS");
+    c->comm_reserve_sms = rs ? atoi(rs) : 1;
+    if (c->comm_reserve_sms < 0 || c->comm_reserve_sms > c->sm_count / 2) c->comm_reserve_sms = 1;
     c->comm = comm;
     c->nranks = nranks;
     c->rank = rank;

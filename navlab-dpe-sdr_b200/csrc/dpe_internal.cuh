@@ -140,6 +140,7 @@ struct dpe_ctx {
     // multi-GPU
     void* comm;                        // ncclComm_t
     int nranks, rank;
+    int comm_reserve_sms;              // SMs k_brute leaves free for the NCCL kernels (DPE_COMM_RESERVE_SMS, default 1)
     double* gathered;                  // [nranks][kPartialLen]
     dpe::EpochDev ep_host;
     // page-locked staging ring for the per-epoch uploads (no implicit stream sync, safe reuse)

@@ -163,7 +163,7 @@ def test_nccl_ranks_equal_the_single_context(capi, mode, est):
                     assert abs(g[1] - w[1]) / w[1] < 2e-6 and g[4] == w[4]
             else:                                                          # weighted: sums in another order
                 assert np.max(np.abs(np.array(g[4]) - np.array(w[4]))) < 1e-6
-            assert abs(g[2] - w[2]) / w[2] < 1e-9
+            assert abs(g[2] - w[2]) / w[2] < (1e-9 if mode == 0 else 2e-6)   # sum of scores
     assert got[0] == got[-1]                                               # every rank ends on the same estimate
     if mode == 0:
         assert np.array_equal(got_scores, want_scores)
