@@ -324,7 +324,10 @@ int dpe_epoch_run_dist(dpe_ctx* ctx, const int16_t* iq, const dpe_epoch* ep, con
 const void* dpe_dev_ptr(dpe_ctx* ctx, int which);
 /* debug copies (synchronise): chip indices int16 [C][S]; per-channel flags     */
 int dpe_debug_channel_flags(dpe_ctx* ctx, int32_t* idx_next, int32_t* no_flip, int C);
-/* bins of candidate range [i0, i0+n): f_idx int64 [n][C], alpha double [n][C]    */
+/* bins of candidate range [i0, i0+n): f_idx int64 [n][C], alpha double [n][C].  sat_mode may be OR-ed with
+ * DPE_DEBUG_BINS_EXACT: evaluate the reference's FP64 chain (batchcorrmanifold.cu:1779-1791) literally instead
+ * of the centre-relative form the scoring kernels use -- the two must agree bit for bit.   */
+#define DPE_DEBUG_BINS_EXACT 16
 int dpe_debug_bins(dpe_ctx* ctx, int64_t i0, int64_t n, int sat_mode, int64_t* f_idx,
                    double* alpha, void* stream);
 /* synchronous D2H read of `nbytes` at byte `offset` of a dpe_dev_ptr buffer       */

@@ -28,6 +28,7 @@ SAT_MIDDLE, SAT_PER_TIME = 0, 1
  PTR_CA_TABLE) = range(14)
 FLAG_KEEP_CHIP_IDX, FLAG_BRUTE_TILES, FLAG_KEEP_BINS = 1, 2, 4
 PART_CHANNELS, PART_GEOMETRY = 1, 2
+DEBUG_BINS_EXACT = 16
 (STAGE_PREPARE, STAGE_CORRELOGRAM, STAGE_LOOKUP, STAGE_BRUTE_BINS, STAGE_BRUTE_CORR, STAGE_BRUTE_SCORE,
  STAGE_ESTIMATE, STAGE_VELOCITY) = range(8)
 
@@ -344,10 +345,13 @@ class Context:
         _check(self.lib, self.lib.dpe_debug_channel_flags(self.h, _ptr(a), _ptr(b), n_chan))
         return a, b
 
-    def debug_bins(self, i0, n, n_chan, sat_mode=SAT_MIDDLE, stream=0):
+    def debug_bins(self, i0, n, n_chan, sat_mode=SAT_MIDDLE, stream=0, exact=False):
+        """Bins of candidates [i0, i0+n): (floor index, lerp weight).  exact=True evaluates the reference's FP64
+        chain literally; the default is the centre-relative form the scoring kernels use (bit-identical)."""
         f = np.zeros((n, n_chan), dtype=np.int64)
         a = np.zeros((n, n_chan), dtype=np.float64)
-        _check(self.lib, self.lib.dpe_debug_bins(self.h, i0, n, sat_mode, _ptr(f), _ptr(a), C.c_void_p(stream)))
+        _check(self.lib, self.lib.dpe_debug_bins(self.h, i0, n, sat_mode | (DEBUG_BINS_EXACT if exact else 0), _ptr(f),
+                                                 _ptr(a), C.c_void_p(stream)))
         return f, a
 
     def copy_out(self, which, dtype, count, offset=0):

@@ -43,21 +43,28 @@ template <int SAT_MODE>
 __global__ void DPE_SIDE128
 k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             double fs, int S, int W, int T, int64_t G, int64_t grid_offset, int16_t* __restrict__ pair_k,
-            float* __restrict__ pair_a, float2* __restrict__ pair_v, int32_t* __restrict__ blk_hist) {
+            float* __restrict__ pair_a, float2* __restrict__ pair_v, int32_t* __restrict__ blk_hist,
+            const SatGeo* __restrict__ geo_tab) {
     extern __shared__ int32_t hs[];
     __shared__ ChanConst cc[DPE_MAX_CHAN];
+    __shared__ SatGeo geo_mid[DPE_MAX_CHAN];
     const EpochDev& e = *ep;
     const int NB = 2 * W + 1;
     const int nbuck = e.C * NB;
     for (int i = threadIdx.x; i < nbuck; i += blockDim.x) hs[i] = 0;
     chan_consts(e, fs, cc);
+    if (SAT_MODE == DPE_SAT_MIDDLE)
+        for (int c = threadIdx.x; c < e.C; c += blockDim.x) geo_mid[c] = make_sat_geo(e, sat + ((size_t)c * T + T / 2) * 8);
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < G) {
-        const Cand p = cand_ecef(e, grid + 4 * j);
+        CandRel rel;
+        const Cand p = cand_ecef(e, grid + 4 * j, &rel);
         const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
+#pragma unroll 2
         for (int c = 0; c < e.C; ++c) {
-            const double idx = code_index(e, cc[c], p, sat + ((size_t)c * T + it) * 8, c, (double)S);
+            const SatGeo& sg = (SAT_MODE == DPE_SAT_PER_TIME) ? geo_tab[(size_t)c * T + it] : geo_mid[c];
+            const double idx = code_index_fast(e, cc[c], sg, p, rel, sat + ((size_t)c * T + it) * 8, c, (double)S);
             const Bin b = make_bin(idx, c, S, W);
             pair_k[(size_t)c * G + j] = b.ok ? (int16_t)b.l : (int16_t)-1;
             pair_a[(size_t)c * G + j] = (float)b.wg;
@@ -452,12 +459,15 @@ int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     prof_begin(c, DPE_STAGE_BRUTE_BINS, s);
     const int nblk = (int)((c->G + kSortBlock - 1) / kSortBlock);
     const size_t hs_bytes = sizeof(int32_t) * nbuck;
-    if (sat_mode == DPE_SAT_PER_TIME)
+    if (sat_mode == DPE_SAT_PER_TIME) {
+        int rc = launch_sat_geo(c, s);
+        if (rc) return rc;
         k_pair_bins<DPE_SAT_PER_TIME><<<nblk, kSortBlock, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
-            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist);
-    else
+            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist,
+            reinterpret_cast<const SatGeo*>(c->sat_geo));
+    } else
         k_pair_bins<DPE_SAT_MIDDLE><<<nblk, kSortBlock, hs_bytes, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S,
-            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist);
+            c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist, nullptr);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     k_block_scan<<<nbuck, 256, 0, s>>>(c->blk_hist, nblk, c->hist, nbuck, c->group_base, c->bucket_base, c->n_groups,

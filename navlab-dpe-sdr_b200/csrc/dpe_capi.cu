@@ -163,6 +163,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     c->ep = reinterpret_cast<EpochDev*>(c->pkt + c->pkt_off_ep);
     c->sat = reinterpret_cast<double*>(c->pkt + c->pkt_off_sat);
     DPE_ALLOC(c->ca, DPE_MAX_CHAN * 1024);
+    DPE_ALLOC(c->sat_geo, C * c->T * 7);
     DPE_ALLOC(c->xw, C * S);
     DPE_ALLOC(c->rs, C * S);
     if (cfg->flags & DPE_FLAG_KEEP_CHIP_IDX) DPE_ALLOC(c->chip_idx, C * S);
@@ -235,7 +236,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     DevGuard guard(c->cfg.device);
     cudaDeviceSynchronize();
     if (c->comm) dpe_comm_destroy(c);
-    void* ptrs[] = {c->pkt, c->ca, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
+    void* ptrs[] = {c->pkt, c->ca, c->sat_geo, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
                     c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,

@@ -8,16 +8,21 @@
 namespace dpe {
 
 struct Cand { double px, py, pz, pt; };
+struct CandRel { double dx, dy, dz, d2; };      // candidate minus grid centre (ECEF), squared length
 
-// batchcorrmanifold.cu:1760-1763
-__device__ __forceinline__ Cand cand_ecef(const EpochDev& e, const double* __restrict__ g4) {
+// batchcorrmanifold.cu:1760-1763 (same operation order: the rotated offset first, the centre added last)
+__device__ __forceinline__ Cand cand_ecef(const EpochDev& e, const double* __restrict__ g4, CandRel* rel = nullptr) {
     const double2 a = *reinterpret_cast<const double2*>(g4);
     const double2 b = *reinterpret_cast<const double2*>(g4 + 2);
+    const double dx = e.R[0] * a.x + e.R[1] * a.y + e.R[2] * b.x;
+    const double dy = e.R[3] * a.x + e.R[4] * a.y + e.R[5] * b.x;
+    const double dz = e.R[6] * a.x + e.R[7] * a.y + e.R[8] * b.x;
     Cand p;
-    p.px = e.R[0] * a.x + e.R[1] * a.y + e.R[2] * b.x + e.center[0];
-    p.py = e.R[3] * a.x + e.R[4] * a.y + e.R[5] * b.x + e.center[1];
-    p.pz = e.R[6] * a.x + e.R[7] * a.y + e.R[8] * b.x + e.center[2];
+    p.px = dx + e.center[0];
+    p.py = dy + e.center[1];
+    p.pz = dz + e.center[2];
     p.pt = b.y + e.center[3];
+    if (rel) { rel->dx = dx; rel->dy = dy; rel->dz = dz; rel->d2 = dx * dx + dy * dy + dz * dz; }
     return p;
 }
 
@@ -47,6 +52,58 @@ __device__ __forceinline__ double code_index(const EpochDev& e, const ChanConst&
     const double rc0 = bc_rc - e.rc_end[c];
     return k.ratio * (-rc0) + S / 2.0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The same bin without the square root, the division and norm(): centre-relative geometry.
+//
+// With d0 = sat - centre, rho0 = |d0|, u = d0 / rho0 and the candidate offset D = p - centre,
+//     |sat - p| = rho0 - a + (b - a^2) / (2 rho0) * (1 + a / rho0) + O(b^2 / rho0^3),   a = u.D,  b = D.D
+// -- for |D| <= 1 km and rho0 >= 2e7 m the neglected terms are below 1e-11 m, so this range agrees with
+// the reference's norm(3, los) to FP64 rounding (a few 1e-9 m).  That alone would not keep the bins
+// bit-exact: the reference's  tx = rxTime - pr / c  rounds to the ulp of rxTime (5.8e-11 s = 1.7 cm of
+// pseudorange = 1.5e-4 samples of index) -- every later operation of the chain is exact or far finer.
+// So the fast path computes the SAME rounded tx whenever the exact difference is provably on the same
+// side of every rounding boundary (|rounding error of the subtraction| < half an ulp minus a margin of
+// 4e-16 s = 1.2e-7 m, 5x the error bound of the range above, the multiplication by 1/c included), and
+// from tx on it repeats the reference's operations one by one: the index, hence the bin, the lerp weights
+// and the score, are bit-identical to code_index().  When the margin is not met (probability ~1.4e-5 per
+// pair) the pair goes through code_index() itself.  Checked exhaustively against the FP64 chain:
+// tests/test_gpu_parity.py::test_code_phase_bins_bit_exact, test_fast_geometry_equals_the_reference_chain.
+// ---------------------------------------------------------------------------------------------
+struct SatGeo { double rho, ux, uy, uz, half_inv_rho, inv_rho, sat_dt; };
+
+__device__ __forceinline__ SatGeo make_sat_geo(const EpochDev& e, const double* __restrict__ sat) {
+    SatGeo g;
+    const double dx = sat[0] - e.center[0], dy = sat[1] - e.center[1], dz = sat[2] - e.center[2];
+    g.rho = sqrt(dx * dx + dy * dy + dz * dz);
+    g.inv_rho = 1.0 / g.rho;
+    g.ux = dx * g.inv_rho; g.uy = dy * g.inv_rho; g.uz = dz * g.inv_rho;
+    g.half_inv_rho = 0.5 * g.inv_rho;
+    g.sat_dt = sat[3];
+    return g;
+}
+
+constexpr double kTxMargin = 4.0e-16;           // seconds; see above
+
+__device__ __forceinline__ double code_index_fast(const EpochDev& e, const ChanConst& k, const SatGeo& g, const Cand& p,
+                                                  const CandRel& r, const double* __restrict__ sat, int c, double S) {
+    const double a = g.ux * r.dx + g.uy * r.dy + g.uz * r.dz;
+    const double range = (g.rho - a) + (fma(-a, a, r.d2) * g.half_inv_rho) * fma(a, g.inv_rho, 1.0);
+    const double pr = range - K_C * g.sat_dt + p.pt;
+    const double q = pr * (1.0 / K_C);
+    const double tx = e.rx_time - q;
+    const double err = (e.rx_time - tx) - q;                       // exact rounding error of the subtraction above
+    // half an ulp of tx: 2^(exponent - 53)
+    const double half_ulp = __longlong_as_double((__double_as_longlong(tx) & 0x7ff0000000000000ll) - (53ll << 52));
+    if (!(fabs(err) < half_ulp - kTxMargin)) return code_index(e, k, p, sat, c, S);   // too close to a rounding boundary
+    const double frac = tx - k.tow - k.cpd;
+    const double bc_rc = frac * K_F_CA;
+    const double rc0 = bc_rc - e.rc_end[c];
+    return k.ratio * (-rc0) + S / 2.0;
+}
+
+// (DPE_SAT_PER_TIME reads a per-(channel, time index) SatGeo table built by k_sat_geo, dpe_score.cu; the arg-max
+// kernels build the C entries of the middle time index per CTA instead)
 
 struct Bin { int64_t f; double wf, wg; int l; bool ok; };   // v = cs[l+1]*wg + cs[l]*wf
 

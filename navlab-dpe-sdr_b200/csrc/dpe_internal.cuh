@@ -95,6 +95,7 @@ struct dpe_ctx {
     int8_t* ca;
     dpe::EpochDev* ep;                 // = pkt + pkt_off_ep
     double* sat;                       // = pkt + pkt_off_sat, [C][T][8]
+    double* sat_geo;                   // dpe::SatGeo [C][T]: centre-relative geometry per satellite state (DPE_SAT_PER_TIME)
     float2* xw; int8_t* rs; int16_t* chip_idx;
     int32_t* idx_next; int32_t* no_flip;
     double2* cpart; double2* cs;
@@ -172,6 +173,7 @@ int launch_gen_ca(dpe_ctx* c, cudaStream_t s);
 int launch_prepare(dpe_ctx* c, cudaStream_t s);
 int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
+int launch_sat_geo(dpe_ctx* c, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_brute_corr(dpe_ctx* c, cudaStream_t s);
 int launch_brute_score(dpe_ctx* c, cudaStream_t s);

@@ -23,13 +23,16 @@ __global__ void __launch_bounds__(kReduceBlock, 6)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
                int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
-               unsigned int* __restrict__ ticket, double* __restrict__ partial) {
+               unsigned int* __restrict__ ticket, double* __restrict__ partial, const SatGeo* __restrict__ geo_tab) {
     __shared__ EpochDev e;
     __shared__ ChanConst cc[DPE_MAX_CHAN];
+    __shared__ SatGeo geo_mid[DPE_MAX_CHAN];
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
     __syncthreads();
     chan_consts(e, fs, cc);
+    if (SAT_MODE == DPE_SAT_MIDDLE)
+        for (int c = threadIdx.x; c < e.C; c += blockDim.x) geo_mid[c] = make_sat_geo(e, sat + ((size_t)c * T + T / 2) * 8);
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < G;
@@ -37,10 +40,13 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     int oow = 0;
     Cand p = {0, 0, 0, 0};
     if (active) {
-        p = cand_ecef(e, grid + 4 * j);
+        CandRel rel;
+        p = cand_ecef(e, grid + 4 * j, &rel);
         const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
+#pragma unroll 2
         for (int c = 0; c < e.C; ++c) {
-            const double idx = code_index(e, cc[c], p, sat + ((size_t)c * T + it) * 8, c, (double)S);
+            const SatGeo& sg = (SAT_MODE == DPE_SAT_PER_TIME) ? geo_tab[(size_t)c * T + it] : geo_mid[c];
+            const double idx = code_index_fast(e, cc[c], sg, p, rel, sat + ((size_t)c * T + it) * 8, c, (double)S);
             const Bin b = make_bin(idx, c, S, W);
             if (b.ok) {
                 const double2 lo = cs[(size_t)c * NL + b.l], hi = cs[(size_t)c * NL + b.l + 1];
@@ -57,8 +63,16 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
 }
 
-// Bins only (parity tests: "code-phase bins bit-exact").
-template <int SAT_MODE>
+__global__ void __launch_bounds__(128) k_sat_geo(const EpochDev* __restrict__ ep, const double* __restrict__ sat, int T,
+                                                 SatGeo* __restrict__ geo) {
+    const EpochDev& e = *ep;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.C * T; i += gridDim.x * blockDim.x)
+        geo[i] = make_sat_geo(e, sat + (size_t)i * 8);
+}
+
+// Bins only (parity tests: "code-phase bins bit-exact").  EXACT = 1: the reference's FP64 chain (code_index);
+// EXACT = 0: the centre-relative fast path the scoring kernels use (code_index_fast) -- the two must agree bit for bit.
+template <int SAT_MODE, int EXACT>
 __global__ void __launch_bounds__(256) k_debug_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
                              const double* __restrict__ sat, double fs, int S, int W, int T,
                              int64_t i0, int64_t n, int64_t grid_offset, int64_t* __restrict__ f_idx,
@@ -67,11 +81,14 @@ __global__ void __launch_bounds__(256) k_debug_bins(const double* __restrict__ g
     if (t >= n) return;
     const EpochDev& e = *ep;
     const int64_t j = i0 + t;
-    const Cand p = cand_ecef(e, grid + 4 * j);
+    CandRel rel;
+    const Cand p = cand_ecef(e, grid + 4 * j, &rel);
     const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
     for (int c = 0; c < e.C; ++c) {
         const ChanConst k = {fs / e.fc[c], (double)e.cp_ref_tow[c], (e.cp_end[c] - e.cp_ref[c]) * K_T_CA};
-        const double idx = code_index(e, k, p, sat + ((size_t)c * T + it) * 8, c, (double)S);
+        const double* s8 = sat + ((size_t)c * T + it) * 8;
+        const double idx = EXACT ? code_index(e, k, p, s8, c, (double)S)
+                                 : code_index_fast(e, k, make_sat_geo(e, s8), p, rel, s8, c, (double)S);
         const Bin b = make_bin(idx, c, S, W);
         f_idx[t * e.C + c] = b.f;
         alpha[t * e.C + c] = b.wg;
@@ -110,17 +127,26 @@ __global__ void k_finalize(const double* __restrict__ parts, int nranks, int est
 }
 
 // ---------------------------------------------------------------------------
+int launch_sat_geo(dpe_ctx* c, cudaStream_t s) {
+    k_sat_geo<<<(c->epoch_C * c->T + 127) / 128, 128, 0, s>>>(c->ep, c->sat, c->T, reinterpret_cast<SatGeo*>(c->sat_geo));
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
     prof_begin(c, DPE_STAGE_LOOKUP, s);
-    if (sat_mode == DPE_SAT_PER_TIME)
+    if (sat_mode == DPE_SAT_PER_TIME) {
+        int rc = launch_sat_geo(c, s);
+        if (rc) return rc;
         k_score_lookup<DPE_SAT_PER_TIME><<<nblk, kReduceBlock, 0, s>>>(
             c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
-            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
-    else
+            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, reinterpret_cast<const SatGeo*>(c->sat_geo));
+    } else
         k_score_lookup<DPE_SAT_MIDDLE><<<nblk, kReduceBlock, 0, s>>>(
             c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
-            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
+            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, nullptr);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
@@ -141,12 +167,14 @@ int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks
 
 int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStream_t s) {
     const int nb = (int)((n + 255) / 256);
-    if (sat_mode == DPE_SAT_PER_TIME)
-        k_debug_bins<DPE_SAT_PER_TIME><<<nb, 256, 0, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S, c->W,
-                                                         c->T, i0, n, c->cfg.grid_offset, c->dbg_f, c->dbg_alpha);
-    else
-        k_debug_bins<DPE_SAT_MIDDLE><<<nb, 256, 0, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S, c->W,
-                                                       c->T, i0, n, c->cfg.grid_offset, c->dbg_f, c->dbg_alpha);
+    const bool per_time = (sat_mode & 1) == DPE_SAT_PER_TIME, exact = (sat_mode & DPE_DEBUG_BINS_EXACT) != 0;
+#define DPE_DBG(SM, EX) k_debug_bins<SM, EX><<<nb, 256, 0, s>>>(c->grid, c->ep, c->sat, c->cfg.fs, (int)c->S, c->W, \
+                                                                 c->T, i0, n, c->cfg.grid_offset, c->dbg_f, c->dbg_alpha)
+    if (per_time && exact) DPE_DBG(DPE_SAT_PER_TIME, 1);
+    else if (per_time) DPE_DBG(DPE_SAT_PER_TIME, 0);
+    else if (exact) DPE_DBG(DPE_SAT_MIDDLE, 1);
+    else DPE_DBG(DPE_SAT_MIDDLE, 0);
+#undef DPE_DBG
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;

@@ -101,6 +101,45 @@ def test_code_phase_bins_bit_exact(capi, sat_mode):
     assert np.max(np.abs(a - (idxo - f_ref))) < 1e-9
 
 
+@pytest.mark.parametrize("case", ["demo25", "c4shard", "wide"])
+@pytest.mark.parametrize("sat_mode", [0, 1])
+def test_fast_geometry_equals_the_reference_chain(capi, case, sat_mode):
+    """The scoring kernels evaluate the code-phase index without norm(), sqrt and the division (centre-relative
+    range, dpe_geom.cuh::code_index_fast) but with the SAME rounded tx as the reference's FP64 chain
+    (batchcorrmanifold.cu:1779-1791), falling back to that chain next to a rounding boundary: floor index AND
+    lerp weight must be bit-identical for every (candidate, PRN) pair -- checked on the whole demo grid, a c4
+    shard (10 MHz, 12 PRNs, 2 m steps: many indices next to integers) and a grid 1 km wide (the Taylor bound)."""
+    if case == "demo25":
+        sc = H.scenario()
+        grid, tg = synth.spread_grid(), 6.0 * synth.spread_axis()
+        W = 16
+    elif case == "c4shard":
+        sc = H.scenario(10.0e6, synth.PRNS_12)
+        grid, tg = synth.uniform_grid(51, (2.0, 2.0, 2.0, 2.0))
+        grid = np.ascontiguousarray(grid[3 * 845651: 3 * 845651 + 400000])
+        W = 16
+    else:
+        sc = H.scenario()
+        grid, tg = synth.uniform_grid(15, (150.0, 150.0, 150.0, 150.0))
+        W = 40
+    n_diff = 0
+    for b, off in ((0, (4.0, -3.0, 2.0, 5.0)), (3, (-41.7, 12.3, 77.7, -95.1))):
+        center = sc.rx_state(sc.cfg.rx_time0 + (b + 1) * sc.cfg.T).copy()
+        center[:4] += off
+        ep = sc.epoch_inputs(b, center=center, time_grid=tg)
+        G = grid.shape[0]
+        ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=sc.C, G=G, time_dim=len(tg), lag_halfwidth=W)
+        ctx.grid_set(grid)
+        ctx.epoch_set(ep)
+        f0, a0 = ctx.debug_bins(0, G, sc.C, sat_mode=sat_mode, exact=True)
+        f1, a1 = ctx.debug_bins(0, G, sc.C, sat_mode=sat_mode)
+        assert np.array_equal(f0, f1)
+        assert np.array_equal(a0, a1)                                   # bit for bit, not "close"
+        n_diff += int(np.unique(f0).size)
+        ctx.close()
+    assert n_diff > 2
+
+
 @pytest.mark.parametrize("lpower", [1, 2, 3])
 def test_lookup_scores_argmax_and_fix(capi, lpower):
     sc, iq, grid, ep = H.epoch_case(n=9, center_offset=(10.0, -5.0, 5.0, 12.0))
