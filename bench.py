@@ -371,7 +371,7 @@ def side_kernel_report(capi):
         free = 65536 - alloc(rb) * 256
         rep["k_brute_regs"] = rb
         rep["free_regs_per_sm_beside_k_brute"] = free
-        side = {"k_prepare": 128, "k_corr_partial": 128, "k_corr_finalize": 256, "k_sample_planes": 256,
+        side = {"k_prep_corr": 128, "k_sample_planes": 256,
                 "k_replica_rd": 256, "k_pair_bins": 128, "k_block_scan": 256, "k_scatter": 128,
                 "k_score_pairs": 128, "k_score_lookup": 128, "k_finalize": 32}
         worst = 0

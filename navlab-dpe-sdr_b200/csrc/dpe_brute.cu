@@ -484,16 +484,19 @@ int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     return DPE_OK;
 }
 
+int brute_set_attributes(dpe_ctx* c) {     // per context: the attributes belong to the device the context lives on
+    DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // the whole unified L1 as shared memory: one carve-out for k_brute and the side kernels that share its SMs
+    DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    c->brute_attr_set = 1;
+    return DPE_OK;
+}
+
 // k_brute alone (the pair sort and the planes are in place)
 int launch_brute_corr(dpe_ctx* c, cudaStream_t s) {
     const size_t smem = brute_smem_bytes(c->H);
-    if (!c->brute_attr_set) {          // per context: the attributes belong to the device the context lives on
-        DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        // the whole unified L1 as shared memory: one carve-out for k_brute and the side kernels that share its SMs
-        DPE_CUDA(cudaFuncSetAttribute(k_brute, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        c->brute_attr_set = 1;
-    }
+    if (!c->brute_attr_set) { int rc = brute_set_attributes(c); if (rc) return rc; }
     prof_begin(c, DPE_STAGE_BRUTE_CORR, s);
     // With a communicator, k_brute leaves `comm_reserve_sms` SMs alone: an NCCL kernel needs a whole SM, and with
     // every SM under a persistent k_brute CTA the broadcast of the NEXT epoch (and the all-gather of the previous one)

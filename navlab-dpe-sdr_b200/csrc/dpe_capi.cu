@@ -164,6 +164,8 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     c->sat = reinterpret_cast<double*>(c->pkt + c->pkt_off_sat);
     DPE_ALLOC(c->ca, DPE_MAX_CHAN * 1024);
     DPE_ALLOC(c->sat_geo, C * c->T * 7);
+    DPE_ALLOC(c->tidx, S);
+    DPE_ALLOC(c->chan_ticket, DPE_MAX_CHAN);
     DPE_ALLOC(c->xw, C * S);
     DPE_ALLOC(c->rs, C * S);
     if (cfg->flags & DPE_FLAG_KEEP_CHIP_IDX) DPE_ALLOC(c->chip_idx, C * S);
@@ -223,8 +225,10 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    { const char* ng = getenv("DPE_NO_GRAPH"); c->use_graph = !(ng && ng[0] == '1'); }
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
+    if (!rc) rc = launch_gen_time(c, 0);
     if (rc) { dpe_ctx_destroy(c); return rc; }
     DPE_CREATE_CUDA(cudaDeviceSynchronize());
     *out = c;
@@ -236,7 +240,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     DevGuard guard(c->cfg.device);
     cudaDeviceSynchronize();
     if (c->comm) dpe_comm_destroy(c);
-    void* ptrs[] = {c->pkt, c->ca, c->sat_geo, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
+    void* ptrs[] = {c->pkt, c->ca, c->sat_geo, c->tidx, c->chan_ticket, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
                     c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
@@ -255,6 +259,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec);
     if (c->prof_ev) {
         for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
@@ -512,8 +517,10 @@ int dpe_brute_presort(dpe_ctx* c, int sat_mode, void* stream) {
     DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
     cudaStream_t s = (cudaStream_t)stream;
     DPE_CUDA(cudaStreamWaitEvent(s, c->ev_epoch, 0));          // the parameters this epoch's upload put in place
-    DPE_CUDA(cudaStreamWaitEvent(s, c->ev_grid, 0));           // ... and the grid, should it have been replaced since
-    if (c->sort_pending) DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
+    if (!c->capturing) {
+        DPE_CUDA(cudaStreamWaitEvent(s, c->ev_grid, 0));       // ... and the grid, should it have been replaced since
+        if (c->sort_pending) DPE_CUDA(cudaStreamWaitEvent(s, c->ev_sort, 0));
+    }
     int rc = launch_brute_sort(c, sat_mode, s);
     if (rc) return rc;
     DPE_CUDA(cudaEventRecord(c->ev_sort, s));
@@ -564,8 +571,8 @@ int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
 // [velocity manifold].  No host synchronisation; the pair sort of a brute-force epoch runs on the
 // context's second stream beside the sample pre-pass.
 // ---------------------------------------------------------------------------------------------
-static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
-                         int score_mode, int est_mode, int with_vel, cudaStream_t s) {
+static int upload_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                        int score_mode, int est_mode, int with_vel, cudaStream_t s, bool own_copy) {
     DPE_REQUIRE(ep, DPE_EINVAL, "epoch: null parameters");
     DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
     DPE_REQUIRE(score_mode == DPE_SCORE_LOOKUP || score_mode == DPE_SCORE_BRUTE, DPE_EINVAL, "bad score_mode %d", score_mode);
@@ -612,7 +619,7 @@ static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, con
         } else {
             DPE_CUDA(cudaMemcpyAsync(c->pkt + c->pkt_off_ep, c->pkt_pin + c->pkt_off_ep, used - c->pkt_off_ep,
                                      cudaMemcpyHostToDevice, s));
-            const bool in_place = !c->comm && at.device == c->cfg.device && (reinterpret_cast<uintptr_t>(iq) & 15) == 0;
+            const bool in_place = !own_copy && !c->comm && at.device == c->cfg.device && (reinterpret_cast<uintptr_t>(iq) & 15) == 0;
             if (in_place) {
                 c->iq = iq;                                   // zero copy
             } else {
@@ -625,10 +632,17 @@ static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, con
         c->iq = c->iq_own;
         c->ep_host.C = C;
     }
-    int rc;
-    if (c->comm && (rc = comm_broadcast(c, c->pkt, used, s))) return rc;
-    DPE_CUDA(cudaEventRecord(c->ev_epoch, s));
+    c->pkt_used = used;
     c->epoch_C = C;
+    return DPE_OK;
+}
+
+// the device work of one epoch after the upload: [broadcast] -> pre-pass + correlogram (|| pair sort on the second
+// stream) -> scoring -> [all-gather] -> estimate -> [velocity manifold].  Pure enqueue: this is what gets captured.
+static int compute_epoch(dpe_ctx* c, int score_mode, int est_mode, int with_vel, cudaStream_t s) {
+    int rc;
+    if (c->comm && (rc = comm_broadcast(c, c->pkt, c->pkt_used, s))) return rc;
+    DPE_CUDA(cudaEventRecord(c->ev_epoch, s));
     c->have_block = 1;
     c->have_epoch = DPE_PART_CHANNELS | DPE_PART_GEOMETRY;
     c->have_prepare = c->have_corr = c->have_scores = 0;
@@ -648,6 +662,60 @@ static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, con
         return rc;
     }
     if (with_vel && (rc = dpe_score_vel(c, s))) return rc;
+    return DPE_OK;
+}
+
+static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const double* sat_states,
+                         int score_mode, int est_mode, int with_vel, cudaStream_t s) {
+    int rc = upload_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s, false);
+    if (rc) return rc;
+    return compute_epoch(c, score_mode, est_mode, with_vel, s);
+}
+
+// dpe_epoch_submit's device work as ONE cudaGraphLaunch: the kernel chain of compute_epoch is captured once per
+// (scoring path, estimator, velocity, channel count, communicator) and replayed; every kernel argument of the chain is a
+// context-owned buffer (the block is always copied into the packet in this mode), so a replay needs no update.
+static int launch_epoch_graph(dpe_ctx* c, int score_mode, int est_mode, int with_vel, cudaStream_t s) {
+    const uint64_t key = 1u | (uint64_t)score_mode << 1 | (uint64_t)est_mode << 2 | (uint64_t)(with_vel != 0) << 3 |
+                         (uint64_t)c->epoch_C << 4 | (uint64_t)(c->comm != nullptr) << 12 | (uint64_t)c->pkt_used << 13;
+    if (!c->graph_exec || c->graph_key != key) {
+        if (c->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec); c->graph_exec = nullptr; }
+        if (!c->brute_attr_set && score_mode == DPE_SCORE_BRUTE) {      // function attributes cannot be set while capturing
+            int rc = brute_set_attributes(c);
+            if (rc) return rc;
+        }
+        // a grid upload on another stream must be visible before the graph; inside the capture only captured events may be waited on
+        DPE_CUDA(cudaStreamWaitEvent(s, c->ev_grid, 0));
+        const int64_t l0 = c->launches;
+        DPE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        c->capturing = 1;
+        int rc = compute_epoch(c, score_mode, est_mode, with_vel, s);
+        c->capturing = 0;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            if (!rc) { set_error("stream capture of the epoch failed: %s", cudaGetErrorString(e)); rc = DPE_ECUDA; }
+            cudaGetLastError();
+            return rc;
+        }
+        c->graph_launches = c->launches - l0;
+        c->launches = l0;
+        cudaGraphExec_t ex = nullptr;
+        e = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(e)); return DPE_ECUDA; }
+        c->graph_exec = ex;
+        c->graph_key = key;
+    }
+    DPE_CUDA(cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, s));
+    c->launches += c->graph_launches;
+    c->have_block = 1;
+    c->have_epoch = DPE_PART_CHANNELS | DPE_PART_GEOMETRY;
+    c->have_prepare = c->have_corr = c->have_scores = 1;
+    c->have_planes = (score_mode == DPE_SCORE_BRUTE);
+    c->sort_valid = 0;
+    c->sort_pending = 0;
     return DPE_OK;
 }
 
@@ -679,8 +747,13 @@ int dpe_epoch_submit(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const d
     DPE_REQUIRE(!c->inflight, DPE_ESTATE, "dpe_epoch_submit: collect the previous epoch first");
     DevGuard guard(c->cfg.device);
     cudaStream_t s = c->own_stream;
-    int rc = enqueue_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s);
-    if (rc) return rc;
+    int rc;
+    if (c->use_graph && !c->prof_on) {
+        if ((rc = upload_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s, true))) return rc;
+        if ((rc = launch_epoch_graph(c, score_mode, est_mode, with_vel, s))) return rc;
+    } else if ((rc = enqueue_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s))) {
+        return rc;
+    }
     DPE_CUDA(cudaMemcpyAsync(c->res_pin, c->result, sizeof(double) * 16, cudaMemcpyDeviceToHost, s));
     DPE_CUDA(cudaEventRecord(c->ev_done, s));
     c->inflight = 1;

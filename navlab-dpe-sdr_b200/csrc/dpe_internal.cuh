@@ -93,6 +93,8 @@ struct dpe_ctx {
     size_t pkt_off_ep, pkt_off_sat, pkt_bytes;
     int16_t* iq_own; const int16_t* iq;    // iq_own = pkt
     int8_t* ca;
+    double* tidx;                      // [S] time index t_n (BCS_GenTimeIdcs), built once
+    unsigned int* chan_ticket;         // [maxC] arrivals per channel in k_prep_corr (self-resetting)
     dpe::EpochDev* ep;                 // = pkt + pkt_off_ep
     double* sat;                       // = pkt + pkt_off_sat, [C][T][8]
     double* sat_geo;                   // dpe::SatGeo [C][T]: centre-relative geometry per satellite state (DPE_SAT_PER_TIME)
@@ -138,6 +140,12 @@ struct dpe_ctx {
     cudaEvent_t ev_done;
     double* res_pin;                   // page-locked mirror of `result` [16]
     int inflight;
+    size_t pkt_used;                   // bytes of the packet the current epoch uses (broadcast size)
+    // the device work of dpe_epoch_submit as one CUDA graph
+    int use_graph, capturing;
+    void* graph_exec;                  // cudaGraphExec_t
+    uint64_t graph_key;
+    int64_t graph_launches;
     // multi-GPU
     void* comm;                        // ncclComm_t
     int nranks, rank;
@@ -171,11 +179,13 @@ void prof_end(dpe_ctx* c, cudaStream_t s);
 // launchers (each returns DPE_OK / DPE_ECUDA and bumps ctx->launches)
 int launch_gen_ca(dpe_ctx* c, cudaStream_t s);
 int launch_prepare(dpe_ctx* c, cudaStream_t s);
+int launch_gen_time(dpe_ctx* c, cudaStream_t s);
 int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_sat_geo(dpe_ctx* c, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_brute_corr(dpe_ctx* c, cudaStream_t s);
+int brute_set_attributes(dpe_ctx* c);
 int launch_brute_score(dpe_ctx* c, cudaStream_t s);
 // cudaFuncGetAttributes of a kernel by name, one lookup per translation unit (1 = found)
 int kernel_attr_prepare(const char* name, cudaFuncAttributes* a);

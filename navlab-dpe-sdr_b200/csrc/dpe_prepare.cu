@@ -56,124 +56,103 @@ __device__ __forceinline__ int nav_edge_index(const EpochDev& e, int c, double f
 }
 
 // ---------------------------------------------------------------------------
-// k_prepare: one thread per (channel, sample).  16 B vector load of 4 I/Q pairs
-// per thread, FP64 time index / carrier phase / chip index (bit-exactness of
-// the chip index and of the wiped samples does not survive FP32: t*fc ~ 2e4
-// chips, fi*t ~ 1e2 cycles), FP32 results.
+// BCS_GenTimeIdcs (batchcorrscores.cu:185-196): t_n = round(n / fs * 1e9) / 1e9, once per context.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gen_time(double fs, int S, double* __restrict__ tidx) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= S) return;
+    double t = (double)n / fs;                                // :190-193
+    tidx[n] = round(t * 1.0e9) / 1.0e9;
+}
+
+// ---------------------------------------------------------------------------
+// k_prep_corr: the whole per-PRN pre-pass of a lookup epoch in ONE launch -- int16 unpack, carrier wipe-off,
+// C/A replica, windowed circular correlogram, flip / no-flip choice, fft-shifted CodeScores window.
+// (Round 1: k_prepare + k_corr_partial + k_corr_finalize, the wiped samples making a round trip through HBM.)
+//
+// One CTA per (chunk of 1024 samples, channel), 128 threads (a side kernel: shares an SM with k_brute).
+//   1. the CTA wipes its 1024 samples plus the circular halo of NLp + 8 the lag window needs, straight into
+//      the word-skewed shared tile the correlation reads.  Time index, carrier phase and chip index are FP64
+//      (t * fc ~ 2e4 chips, fi * t ~ 1e2 cycles do not survive FP32; the chip index is a bit-exact target);
+//      the phase is reduced to [0, 1) cycles in FP64 and only then handed to the FP32 sincospif -- the
+//      range-reduced FP32 NCO the north star asks for (phase error <= 6e-8 cycle per sample, incoherent).
+//   2. each thread owns an 8-sample x 8-lag register tile (64 complex MACs per 23 shared loads), FP32 inside
+//      the chunk, FP64 across chunks; part A = samples before the nav-bit edge, part B = from the edge on, so
+//      no-flip = A + B and flipped = A - B without a second pass.
+//   3. the CTA that takes the last ticket of its channel adds the chunk partials in chunk order (FP64,
+//      fixed order), decides flip / no-flip on lag 0 (BCS_ChooseCodeCorr, batchcorrscores.cu:499-543) and
+//      writes the window (BCS_cufftBatchShift, :554-584: cs[l] <-> shifted bin l - W + S/2).
+// xw / rs (and zw for the carrier branch) still go to HBM once: the brute-force planes and the velocity
+// manifold read them.
 // ---------------------------------------------------------------------------
 __global__ void DPE_SIDE128
-k_prepare(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca,
-          const EpochDev* __restrict__ ep, double fs, int S, int S_pad,
-          float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
-          int32_t* __restrict__ idx_next, const long long* __restrict__ dc, float2* __restrict__ zw) {
-    __shared__ int8_t code_s[1024];
+k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const double* __restrict__ tidx,
+            const EpochDev* __restrict__ ep, double fs, int S, int W, int NL, int NLp, int nchunk,
+            float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
+            int32_t* __restrict__ idx_next, const long long* __restrict__ dc, float2* __restrict__ zw,
+            double2* __restrict__ cpart, double2* __restrict__ cs, int32_t* __restrict__ no_flip,
+            unsigned int* __restrict__ chan_ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_edge;
+    __shared__ bool s_last;
+    __shared__ int s_keep;
     const int c = blockIdx.y;
     const EpochDev& e = *ep;
     if (c >= e.C) return;
-    const int prn = e.prn[c];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) code_s[i] = ca[(prn - 1) * 1024 + i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) idx_next[c] = nav_edge_index(e, c, fs);
-    __syncthreads();
-
-    const double fc = e.fc[c], rc = e.rc_start[c], fi = e.fi[c], ri = e.ri_start[c];
-    const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (n0 >= S_pad) return;
-    int16_t v[8];
-    if (n0 + 4 <= S) {
-        *reinterpret_cast<int4*>(v) = *reinterpret_cast<const int4*>(iq + 2 * (size_t)n0);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            bool in = (n0 + q) < S;
-            v[2 * q] = in ? iq[2 * (size_t)(n0 + q)] : (int16_t)0;
-            v[2 * q + 1] = in ? iq[2 * (size_t)(n0 + q) + 1] : (int16_t)0;
-        }
-    }
-    // DC mean for the carrier branch: sum / (float)S (ComplexDivide, batchcorrscores.cu:1065,1210-1216)
-    const double inv = 1.0 / (double)(float)S;
-    const double mr = dc ? (double)dc[0] * inv : 0.0, mi = dc ? (double)dc[1] * inv : 0.0;
-    float xr[4], xi[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int n = n0 + q;
-        xr[q] = 0.f; xi[q] = 0.f;
-        if (n < S) {
-            double t = (double)n / fs;                        // BCS_GenTimeIdcs :190-193
-            t = round(t * 1.0e9) / 1.0e9;
-            double sn, cs;
-            sincos(2 * K_PI * (fi * t + ri), &sn, &cs);       // :293
-            const double I = (double)v[2 * q], Q = (double)v[2 * q + 1];
-            // x * conj(exp(j phi)) (cuCmul, :385-407)
-            xr[q] = (float)(I * cs + Q * sn);
-            xi[q] = (float)(Q * cs - I * sn);
-            int chip = (int)floor(t * fc + rc);               // :347-348
-            chip = ((chip % K_L_CA) + K_L_CA) % K_L_CA;
-            rs[(size_t)c * S + n] = code_s[chip];
-            if (chip_idx) chip_idx[(size_t)c * S + n] = (int16_t)chip;
-            xw[(size_t)c * S + n] = make_float2(xr[q], xi[q]);
-            if (zw)   // (x - mean) * conj(carrier), BCS_SubtractDCOffset :470-485
-                zw[(size_t)c * S + n] = make_float2((float)((I - mr) * cs + (Q - mi) * sn),
-                                                    (float)((Q - mi) * cs - (I - mr) * sn));
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Planes of the brute-force kernel (dpe_brute.cu).  The kernel walks the replica
-// position p; a pair with lag k multiplies replica position p with sample
-// (p + k) mod S.  k_sample_planes writes the wiped samples 8 times, copy s shifted
-// by s samples, each with a circular halo of H elements, so that lag k = 8 q + s is
-// copy s read at element offset 8 q: 16-byte aligned for the TMA bulk copy and in
-// phase with the float4 skew for every lag.  One thread per element pair.
-// ---------------------------------------------------------------------------
-__global__ void DPE_SIDE256
-k_sample_planes(const float2* __restrict__ xw, const EpochDev* __restrict__ ep, int S, int n_elem, int H,
-                float* __restrict__ bx, int64_t bx_stride) {
-    const int c = blockIdx.y, s = blockIdx.z;
-    if (c >= ep->C) return;
-    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // element = p + H
-    if (e >= n_elem) return;
-    int n0 = (e - H + s) % S; if (n0 < 0) n0 += S;
-    int n1 = n0 + 1; if (n1 == S) n1 = 0;
-    const float2 a = xw[(size_t)c * S + n0], b = xw[(size_t)c * S + n1];
-    *reinterpret_cast<float4*>(bx + ((size_t)c * 8 + s) * bx_stride + skewX(e)) = make_float4(a.x, a.y, b.x, b.y);
-}
-
-// ---------------------------------------------------------------------------
-// k_corr_partial: one CTA per (chunk of 1024 samples, channel).  The chunk of xw
-// (with a +-W halo, circular) and of r is staged in shared memory in a
-// word-skewed layout (x + x/8) so that lanes holding runs of 8 contiguous samples
-// read conflict-free; each thread owns an 8-sample x 8-lag register tile
-// (64 complex MACs per 23 shared loads), FP32 inside the chunk, FP64 across chunks.
-// Part A = samples before the nav-bit edge, part B = from the edge on, so that
-// no-flip = A + B and flipped = A - B without a second pass.
-// ---------------------------------------------------------------------------
-__global__ void DPE_SIDE128
-k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
-               const int32_t* __restrict__ idx_next, const EpochDev* __restrict__ ep,
-               int S, int W, int NLp, int nchunk, double2* __restrict__ cpart) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = blockIdx.y;
-    if (c >= ep->C) return;
     const int chunk = blockIdx.x;
     const int n0 = chunk * kCorrChunk;
     const int nx = kCorrChunk + NLp + 8;             // halo: lags -W .. -W+NLp-1 (+7 slack)
     float2* xs = reinterpret_cast<float2*>(smem_raw);                 // [skew(nx)]
     float* r_s = reinterpret_cast<float*>(xs + (nx + (nx >> 3) + 1)); // [skew(1024)]
+    int8_t* code_s = reinterpret_cast<int8_t*>(r_s + (kCorrChunk + (kCorrChunk >> 3) + 1));   // [1024]
 
-    const float2* xc = xw + (size_t)c * S;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-        int n = n0 - W + i;
-        n %= S; if (n < 0) n += S;
-        xs[i + (i >> 3)] = xc[n];
-    }
-    for (int i = threadIdx.x; i < kCorrChunk; i += blockDim.x) {
-        int n = n0 + i;
-        r_s[i + (i >> 3)] = (n < S) ? (float)rs[(size_t)c * S + n] : 0.f;
+    const int prn = e.prn[c];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        reinterpret_cast<int32_t*>(code_s)[i] = reinterpret_cast<const int32_t*>(ca + (prn - 1) * 1024)[i];
+    if (threadIdx.x == 0) {
+        const int en = nav_edge_index(e, c, fs);
+        s_edge = en;
+        if (chunk == 0) idx_next[c] = en;
     }
     __syncthreads();
 
-    int edge = idx_next[c];
+    const double fc = e.fc[c], rc = e.rc_start[c], fi = e.fi[c], ri = e.ri_start[c];
+    // DC mean for the carrier branch: sum / (float)S (ComplexDivide, batchcorrscores.cu:1065,1210-1216)
+    const double inv = 1.0 / (double)(float)S;
+    const float mr = dc ? (float)((double)dc[0] * inv) : 0.f, mi = dc ? (float)((double)dc[1] * inv) : 0.f;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        int n = n0 - W + i;
+        n %= S; if (n < 0) n += S;
+        const double t = tidx[n];
+        const short2 v = reinterpret_cast<const short2*>(iq)[n];
+        const double ph = fi * t + ri;                        // cycles (:293)
+        const float fr = (float)(ph - floor(ph));             // [0, 1): range reduction in FP64, NCO in FP32
+        float sn, cn;
+        sincospif(2.0f * fr, &sn, &cn);
+        const float I = (float)v.x, Q = (float)v.y;
+        const float2 x = make_float2(fmaf(I, cn, Q * sn), fmaf(Q, cn, -I * sn));   // x * conj(exp(j phi)) (cuCmul, :385-407)
+        xs[i + (i >> 3)] = x;
+        const int m = i - W;                                  // sample of the chunk's own 1024
+        if (m >= 0 && m < kCorrChunk) {
+            float r = 0.f;
+            if (n0 + m < S) {                                 // n == n0 + m here (no wrap inside the block)
+                int chip = (int)floor(t * fc + rc);           // :347-348
+                chip = ((chip % K_L_CA) + K_L_CA) % K_L_CA;
+                const int8_t rv = code_s[chip];
+                r = (float)rv;
+                const size_t o = (size_t)c * S + n;
+                rs[o] = rv;
+                if (chip_idx) chip_idx[o] = (int16_t)chip;
+                xw[o] = x;
+                if (zw)   // (x - mean) * conj(carrier), BCS_SubtractDCOffset :470-485
+                    zw[o] = make_float2(fmaf(I - mr, cn, (Q - mi) * sn), fmaf(Q - mi, cn, -(I - mr) * sn));
+            }
+            r_s[m + (m >> 3)] = r;
+        }
+    }
+    __syncthreads();
+
+    int edge = s_edge;
     if (!(edge > 0 && edge < S)) edge = S;           // no edge in block: everything is part A
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_lag_runs = NLp / kLagTile;
@@ -186,11 +165,11 @@ k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
             const int m = sr * 8;                     // local sample of the run
             float r[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) r[s] = r_s[m + s + sr];        // skew: (m+s) + (m+s)/8
+            for (int s_ = 0; s_ < 8; ++s_) r[s_] = r_s[m + s_ + sr];        // skew: (m+s) + (m+s)/8
             float2 x[15];
             const int xb = m + lr * kLagTile;         // xs index of (sample m, lag lr*8)
 #pragma unroll
-            for (int s = 0; s < 15; ++s) { int i = xb + s; x[s] = xs[i + (i >> 3)]; }
+            for (int s_ = 0; s_ < 15; ++s_) { int i = xb + s_; x[s_] = xs[i + (i >> 3)]; }
             const int nabs = n0 + m;
             const bool allA = (nabs + 8 <= edge), allB = (nabs >= edge);
             if (allA || allB) {
@@ -198,18 +177,18 @@ k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
 #pragma unroll
                 for (int l = 0; l < kLagTile; ++l)
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        acc[l].x = fmaf(x[s + l].x, r[s], acc[l].x);
-                        acc[l].y = fmaf(x[s + l].y, r[s], acc[l].y);
+                    for (int s_ = 0; s_ < 8; ++s_) {
+                        acc[l].x = fmaf(x[s_ + l].x, r[s_], acc[l].x);
+                        acc[l].y = fmaf(x[s_ + l].y, r[s_], acc[l].y);
                     }
             } else {
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const bool a = (nabs + s) < edge;
+                for (int s_ = 0; s_ < 8; ++s_) {
+                    const bool a = (nabs + s_) < edge;
 #pragma unroll
                     for (int l = 0; l < kLagTile; ++l) {
-                        if (a) { accA[l].x = fmaf(x[s + l].x, r[s], accA[l].x); accA[l].y = fmaf(x[s + l].y, r[s], accA[l].y); }
-                        else   { accB[l].x = fmaf(x[s + l].x, r[s], accB[l].x); accB[l].y = fmaf(x[s + l].y, r[s], accB[l].y); }
+                        if (a) { accA[l].x = fmaf(x[s_ + l].x, r[s_], accA[l].x); accA[l].y = fmaf(x[s_ + l].y, r[s_], accA[l].y); }
+                        else   { accB[l].x = fmaf(x[s_ + l].x, r[s_], accB[l].x); accB[l].y = fmaf(x[s_ + l].y, r[s_], accB[l].y); }
                     }
                 }
             }
@@ -233,49 +212,63 @@ k_corr_partial(const float2* __restrict__ xw, const int8_t* __restrict__ rs,
             }
         }
     }
-}
 
-// k_corr_finalize: fixed-order FP64 sum of the chunk partials, flip / no-flip
-// choice on lag 0 (BCS_ChooseCodeCorr, batchcorrscores.cu:499-543), fft-shifted
-// window out (BCS_cufftBatchShift, :554-584: cs[l] <-> shifted bin l - W + S/2).
-// One warp per lag (lanes stride the chunks, xor-tree: a fixed summation order); every warp also
-// sums lag 0 so the decision needs no cross-CTA exchange.
-__device__ __forceinline__ void sum_chunks(const double2* __restrict__ cpart, int c, int l, int NLp, int nchunk,
-                                           int lane, double (&r)[4]) {
-    r[0] = r[1] = r[2] = r[3] = 0.0;
-    for (int ch = lane; ch < nchunk; ch += 32) {
-        const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + l;
-        r[0] += p[0].x; r[1] += p[0].y; r[2] += p[NLp].x; r[3] += p[NLp].y;
+    // ---- last CTA of this channel: chunk partials -> CodeScores window ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&chan_ticket[c], 1u);
+        s_last = (t == (unsigned int)nchunk - 1);
+        if (s_last) chan_ticket[c] = 0;               // self-resetting for the next launch
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const bool has_edge = (s_edge > 0) && (s_edge < S);
+    if (threadIdx.x == 0) {                           // lag 0 decides (:512)
+        double ax = 0, ay = 0, bx_ = 0, by = 0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + W;
+            const double2 a = __ldcg(p), b2 = __ldcg(p + NLp);
+            ax += a.x; ay += a.y; bx_ += b2.x; by += b2.y;
+        }
+        const int keep = !has_edge || (hypot(ax + bx_, ay + by) > hypot(ax - bx_, ay - by));
+        s_keep = keep;
+        no_flip[c] = keep;
+    }
+    __syncthreads();
+    const bool keep = s_keep != 0;
+    for (int l = threadIdx.x; l < NL; l += blockDim.x) {
+        double ax = 0, ay = 0, bx_ = 0, by = 0;
+        for (int ch = 0; ch < nchunk; ++ch) {         // chunk order: a fixed summation order
+            const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + l;
+            const double2 a = __ldcg(p), b2 = __ldcg(p + NLp);
+            ax += a.x; ay += a.y; bx_ += b2.x; by += b2.y;
+        }
+        cs[(size_t)c * NL + l] = keep ? make_double2(ax + bx_, ay + by)     // no-flip = A + B
+                                      : make_double2(ax - bx_, ay - by);    // flipped = A - B (only chosen when an edge exists)
+    }
 }
 
+// ---------------------------------------------------------------------------
+// Planes of the brute-force kernel (dpe_brute.cu).  The kernel walks the replica
+// position p; a pair with lag k multiplies replica position p with sample
+// (p + k) mod S.  k_sample_planes writes the wiped samples 8 times, copy s shifted
+// by s samples, each with a circular halo of H elements, so that lag k = 8 q + s is
+// copy s read at element offset 8 q: 16-byte aligned for the TMA bulk copy and in
+// phase with the float4 skew for every lag.  One thread per element pair.
+// ---------------------------------------------------------------------------
 __global__ void DPE_SIDE256
-k_corr_finalize(const double2* __restrict__ cpart, const int32_t* __restrict__ idx_next,
-                const EpochDev* __restrict__ ep, int S, int W, int NL, int NLp,
-                int nchunk, double2* __restrict__ cs, int32_t* __restrict__ no_flip) {
-    const int c = blockIdx.x;
+k_sample_planes(const float2* __restrict__ xw, const EpochDev* __restrict__ ep, int S, int n_elem, int H,
+                float* __restrict__ bx, int64_t bx_stride) {
+    const int c = blockIdx.y, s = blockIdx.z;
     if (c >= ep->C) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l = blockIdx.y * 8 + warp;
-    const int edge_raw = idx_next[c];
-    const bool edge = (edge_raw > 0) && (edge_raw < S);
-    double z[4];
-    sum_chunks(cpart, c, W, NLp, nchunk, lane, z);                // lag 0
-    const bool keep = !edge || (hypot(z[0] + z[2], z[1] + z[3]) > hypot(z[0] - z[2], z[1] - z[3]));
-    if (blockIdx.y == 0 && threadIdx.x == 0) no_flip[c] = keep ? 1 : 0;
-    if (l >= NL) return;
-    double r[4];
-    sum_chunks(cpart, c, l, NLp, nchunk, lane, r);
-    if (lane == 0) {
-        double2 v;
-        if (keep) v = make_double2(r[0] + r[2], r[1] + r[3]);     // no-flip = A + B
-        else v = make_double2(r[0] - r[2], r[1] - r[3]);          // flipped = A - B (only chosen when an edge exists)
-        cs[(size_t)c * NL + l] = v;
-    }
+    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // element = p + H
+    if (e >= n_elem) return;
+    int n0 = (e - H + s) % S; if (n0 < 0) n0 += S;
+    int n1 = n0 + 1; if (n1 == S) n1 = 0;
+    const float2 a = xw[(size_t)c * S + n0], b = xw[(size_t)c * S + n1];
+    *reinterpret_cast<float4*>(bx + ((size_t)c * 8 + s) * bx_stride + skewX(e)) = make_float4(a.x, a.y, b.x, b.y);
 }
 
 // k_replica_rd: chosen replica (flip applied) by position pair for the brute-force kernel:
@@ -315,39 +308,33 @@ int launch_gen_ca(dpe_ctx* c, cudaStream_t s) {
     return DPE_OK;
 }
 
+int launch_gen_time(dpe_ctx* c, cudaStream_t s) {
+    k_gen_time<<<(int)((c->S + 255) / 256), 256, 0, s>>>(c->cfg.fs, (int)c->S, c->tidx);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
+// pre-pass + correlogram: one launch (k_prep_corr)
 int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S;
-    const int S4 = ((S + 3) / 4) * 4;
-    dim3 grid((S4 / 4 + 127) / 128, c->epoch_C);
+    const int nx = kCorrChunk + c->NLp + 8;
+    const size_t smem = (size_t)(nx + (nx >> 3) + 1) * sizeof(float2) +
+                        (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float) + 1024;
+    dim3 grid(c->nchunk, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
     if (c->Gv > 0) { int rc = launch_dc_sum(c, s); if (rc) return rc; }
-    k_prepare<<<grid, 128, 0, s>>>(c->iq, c->ca, c->ep, c->cfg.fs, S, S4, c->xw, c->rs, c->chip_idx, c->idx_next,
-                                   c->Gv > 0 ? c->dc_sum : nullptr, c->Gv > 0 ? c->bb : nullptr);
+    k_prep_corr<<<grid, 128, smem, s>>>(c->iq, c->ca, c->tidx, c->ep, c->cfg.fs, S, c->W, c->NL, c->NLp, c->nchunk,
+                                        c->xw, c->rs, c->chip_idx, c->idx_next, c->Gv > 0 ? c->dc_sum : nullptr,
+                                        c->Gv > 0 ? c->bb : nullptr, c->cpart, c->cs, c->no_flip, c->chan_ticket);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     prof_end(c, s);
     return DPE_OK;
 }
 
-int launch_correlogram(dpe_ctx* c, cudaStream_t s) {
-    const int S = (int)c->S;
-    const int nx = kCorrChunk + c->NLp + 8;
-    const size_t smem = (size_t)(nx + (nx >> 3) + 1) * sizeof(float2) +
-                        (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float);
-    dim3 grid(c->nchunk, c->epoch_C);
-    prof_begin(c, DPE_STAGE_CORRELOGRAM, s);
-    k_corr_partial<<<grid, 128, smem, s>>>(c->xw, c->rs, c->idx_next, c->ep, S, c->W, c->NLp,
-                                           c->nchunk, c->cpart);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
-    dim3 gf(c->epoch_C, (c->NL + 7) / 8);
-    k_corr_finalize<<<gf, 256, 0, s>>>(c->cpart, c->idx_next, c->ep, S, c->W, c->NL, c->NLp, c->nchunk, c->cs,
-                                       c->no_flip);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
-    prof_end(c, s);
-    return DPE_OK;
-}
+// the correlogram is finished by the last CTA of every channel inside k_prep_corr: nothing left to launch
+int launch_correlogram(dpe_ctx*, cudaStream_t) { return DPE_OK; }
 
 // The planes k_brute streams (built on the first brute-force scoring of an epoch, so that a
 // context which only looks up pays nothing for them).
@@ -367,10 +354,9 @@ int launch_brute_planes(dpe_ctx* c, cudaStream_t s) {
 
 int kernel_attr_prepare(const char* name, cudaFuncAttributes* a) {
     DPE_KATTR("k_gen_ca", k_gen_ca);
-    DPE_KATTR("k_prepare", k_prepare);
+    DPE_KATTR("k_prep_corr", k_prep_corr);
+    DPE_KATTR("k_gen_time", k_gen_time);
     DPE_KATTR("k_sample_planes", k_sample_planes);
-    DPE_KATTR("k_corr_partial", k_corr_partial);
-    DPE_KATTR("k_corr_finalize", k_corr_finalize);
     DPE_KATTR("k_replica_rd", k_replica_rd);
     return 0;
 }

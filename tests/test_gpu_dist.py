@@ -89,7 +89,7 @@ def test_side_kernels_fit_beside_k_brute(capi):
     """The overlap of two epochs relies on every side kernel fitting on an SM next to a k_brute CTA."""
     rb, _, tb = capi.kernel_attr("k_brute")
     free = 65536 - ((rb + 7) // 8 * 8) * 256
-    for k, thr in (("k_prepare", 128), ("k_corr_partial", 128), ("k_corr_finalize", 256), ("k_sample_planes", 256),
+    for k, thr in (("k_prep_corr", 128), ("k_sample_planes", 256),
                    ("k_replica_rd", 256), ("k_pair_bins", 128), ("k_block_scan", 256), ("k_scatter", 128),
                    ("k_score_pairs", 128), ("k_score_lookup", 128)):
         r, _, _ = capi.kernel_attr(k)

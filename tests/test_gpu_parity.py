@@ -64,8 +64,8 @@ def test_wiped_samples_match_oracle(capi):
     for c in range(C):
         ref = x * orc.doppler_wipeoff(ep["fi"][c], ep["ri_start"][c], t)
         got = xw[c, :, 0].astype(np.float64) + 1j * xw[c, :, 1]
-        # FP32 storage of an FP64 product: half an ulp of the sample magnitude
-        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1.5e-7
+        # FP32 NCO on a phase range-reduced in FP64 (<= 6e-8 cycle = 3.8e-7 rad) + FP32 products
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1.0e-6
 
 
 @pytest.mark.parametrize("fs,prns,W_", [(2.5e6, synth.PRNS_8, 32), (2.5e6, synth.PRNS_8, 5),
