@@ -748,7 +748,8 @@ int dpe_epoch_submit(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, const d
     DevGuard guard(c->cfg.device);
     cudaStream_t s = c->own_stream;
     int rc;
-    if (c->use_graph && !c->prof_on) {
+    // (a context with a communicator enqueues kernel by kernel: NCCL refuses thread-local stream capture)
+    if (c->use_graph && !c->prof_on && !c->comm) {
         if ((rc = upload_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s, true))) return rc;
         if ((rc = launch_epoch_graph(c, score_mode, est_mode, with_vel, s))) return rc;
     } else if ((rc = enqueue_epoch(c, iq, ep, sat_states, score_mode, est_mode, with_vel, s))) {
