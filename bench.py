@@ -373,7 +373,7 @@ def side_kernel_report(capi):
         rep["free_regs_per_sm_beside_k_brute"] = free
         side = {"k_prep_corr": 128, "k_sample_planes": 256,
                 "k_replica_rd": 256, "k_pair_bins": 128, "k_block_scan": 256, "k_scatter": 128,
-                "k_score_pairs": 128, "k_score_lookup": 128, "k_finalize": 32}
+                "k_score_pairs": 128, "k_finalize": 32}
         worst = 0
         for k, thr in side.items():
             r, _, _ = capi.kernel_attr(k)

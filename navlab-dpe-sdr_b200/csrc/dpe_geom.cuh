@@ -85,21 +85,29 @@ __device__ __forceinline__ SatGeo make_sat_geo(const EpochDev& e, const double* 
 
 constexpr double kTxMargin = 4.0e-16;           // seconds; see above
 
-__device__ __forceinline__ double code_index_fast(const EpochDev& e, const ChanConst& k, const SatGeo& g, const Cand& p,
-                                                  const CandRel& r, const double* __restrict__ sat, int c, double S) {
+// returns false when the pair must take the exact chain (too close to a rounding boundary of tx)
+__device__ __forceinline__ bool code_index_fast_core(double rx_time, const ChanConst& k, const SatGeo& g, double pt,
+                                                     const CandRel& r, double rc_end, double S, double* idx) {
     const double a = g.ux * r.dx + g.uy * r.dy + g.uz * r.dz;
     const double range = (g.rho - a) + (fma(-a, a, r.d2) * g.half_inv_rho) * fma(a, g.inv_rho, 1.0);
-    const double pr = range - K_C * g.sat_dt + p.pt;
+    const double pr = range - K_C * g.sat_dt + pt;
     const double q = pr * (1.0 / K_C);
-    const double tx = e.rx_time - q;
-    const double err = (e.rx_time - tx) - q;                       // exact rounding error of the subtraction above
+    const double tx = rx_time - q;
+    const double err = (rx_time - tx) - q;                         // exact rounding error of the subtraction above
     // half an ulp of tx: 2^(exponent - 53)
     const double half_ulp = __longlong_as_double((__double_as_longlong(tx) & 0x7ff0000000000000ll) - (53ll << 52));
-    if (!(fabs(err) < half_ulp - kTxMargin)) return code_index(e, k, p, sat, c, S);   // too close to a rounding boundary
     const double frac = tx - k.tow - k.cpd;
     const double bc_rc = frac * K_F_CA;
-    const double rc0 = bc_rc - e.rc_end[c];
-    return k.ratio * (-rc0) + S / 2.0;
+    const double rc0 = bc_rc - rc_end;
+    *idx = k.ratio * (-rc0) + S / 2.0;
+    return fabs(err) < half_ulp - kTxMargin;
+}
+
+__device__ __forceinline__ double code_index_fast(const EpochDev& e, const ChanConst& k, const SatGeo& g, const Cand& p,
+                                                  const CandRel& r, const double* __restrict__ sat, int c, double S) {
+    double idx;
+    if (code_index_fast_core(e.rx_time, k, g, p.pt, r, e.rc_end[c], S, &idx)) return idx;
+    return code_index(e, k, p, sat, c, S);
 }
 
 // (DPE_SAT_PER_TIME reads a per-(channel, time index) SatGeo table built by k_sat_geo, dpe_score.cu; the arg-max
@@ -132,19 +140,31 @@ __device__ __forceinline__ double mag_pow(double re, double im, int L) {
 // Block-level reduction of (score-weighted sums, sum, max/argmax, out-of-window)
 // with warp shuffles + shared memory, fixed order => bit-reproducible.
 // out[0..3]=sum s*p, [4]=sum s, [5]=max, [6]=global argmax (lowest on ties), [7]=oow
+// NSUM = 5: score-weighted sums + sum of scores; NSUM = 1: the sum of scores only (arg-max estimate): v[4] alone is reduced
+template <int NSUM>
+__device__ __forceinline__ void block_reduce_store_vals(double (&v)[5], double mx, double mi, double oo,
+                                                        double* __restrict__ out);
+
 __device__ __forceinline__ void block_reduce_store(double score, int64_t gidx, const Cand& p, bool active,
                                                    int oow, double* __restrict__ out) {
-    __shared__ double sh[kReduceBlock / 32][8];
     double v[5] = {0, 0, 0, 0, 0};
-    double mx = -1.0, mi = 9.0e18, oo = (double)oow;
+    double mx = -1.0, mi = 9.0e18;
     if (active) {
         v[0] = score * p.px; v[1] = score * p.py; v[2] = score * p.pz; v[3] = score * p.pt; v[4] = score;
         mx = score; mi = (double)gidx;
     }
+    block_reduce_store_vals<5>(v, mx, mi, (double)oow, out);
+}
+
+template <int NSUM>
+__device__ __forceinline__ void block_reduce_store_vals(double (&v)[5], double mx, double mi, double oo,
+                                                        double* __restrict__ out) {
+    __shared__ double sh[kReduceBlock / 32][8];
+    constexpr int K0 = (NSUM == 5) ? 0 : 4;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        for (int k = K0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
         oo += __shfl_xor_sync(0xffffffffu, oo, o);
         const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
         const double omi = __shfl_xor_sync(0xffffffffu, mi, o);
@@ -180,9 +200,12 @@ __device__ __forceinline__ void block_reduce_store(double score, int64_t gidx, c
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool take_last_ticket(unsigned int* counter) {
     __shared__ bool s_last;
-    __threadfence();                                   // this CTA's partial is visible device-wide
     __syncthreads();
     if (threadIdx.x == 0) {
+        // thread 0 wrote this CTA's partial (block_reduce_store / the bucket total): its fence makes it visible
+        // device-wide before the ticket.  (A fence in EVERY thread, as in round 1, stalled each warp on its own
+        // score store: "membar" was 0.7 stalled warps per issue in k_score_lookup.)
+        __threadfence();
         const unsigned int t = atomicAdd(counter, 1u);
         s_last = (t == gridDim.x - 1);
         if (s_last) *counter = 0;

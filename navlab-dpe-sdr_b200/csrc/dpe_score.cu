@@ -14,12 +14,18 @@
 namespace dpe {
 
 // ---------------------------------------------------------------------------
-// k_score_lookup: one thread per candidate (the reference's BCM_PosMeasML with
-// the arg-max / weighted accumulation fused in).  sat_mode: middle time-grid
-// state (:1773-1775) or per-time-index state (:865-873).
+// k_score_lookup: the reference's BCM_PosMeasML with the arg-max / weighted accumulation fused in.
+// sat_mode: middle time-grid state (:1773-1775) or per-time-index state (:865-873).
+// Every thread scores kLkCand candidates (coalesced: j = base + tid + 128 k): the per-PRN constants are read
+// from shared memory once per 4 pairs and the four FP64 chains are independent (round 1, one candidate per
+// thread: 169 issued instructions per pair, 13 of them LDS, "wait" + "long scoreboard" 5.5 stalled warps per
+// issue -- a latency-bound kernel at 4 % of its HBM roofline).
+// WITH_SUMS = 0 (arg-max estimate): only the sum of scores is reduced, not sum s*x.
 // ---------------------------------------------------------------------------
-template <int SAT_MODE>
-__global__ void __launch_bounds__(kReduceBlock, 6)
+constexpr int kLkCand = 4;
+
+template <int SAT_MODE, int WITH_SUMS>
+__global__ void __launch_bounds__(kReduceBlock, 4)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
                int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
@@ -34,32 +40,71 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     if (SAT_MODE == DPE_SAT_MIDDLE)
         for (int c = threadIdx.x; c < e.C; c += blockDim.x) geo_mid[c] = make_sat_geo(e, sat + ((size_t)c * T + T / 2) * 8);
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = j < G;
-    double score = 0.0;
+    const int64_t base = (int64_t)blockIdx.x * (kReduceBlock * kLkCand) + threadIdx.x;
+    CandRel rel[kLkCand];
+    double pt[kLkCand], score[kLkCand];
+    int it[kLkCand];
+    bool act[kLkCand];
+#pragma unroll
+    for (int k = 0; k < kLkCand; ++k) {
+        const int64_t j = base + (int64_t)k * kReduceBlock;
+        act[k] = j < G;
+        score[k] = 0.0;
+        it[k] = T / 2;
+        pt[k] = 0.0;
+        rel[k].dx = rel[k].dy = rel[k].dz = rel[k].d2 = 0.0;
+        if (act[k]) {
+            const Cand p = cand_ecef(e, grid + 4 * j, &rel[k]);
+            pt[k] = p.pt;
+            if (SAT_MODE == DPE_SAT_PER_TIME) it[k] = (int)((j + grid_offset) % T);
+        }
+    }
     int oow = 0;
-    Cand p = {0, 0, 0, 0};
-    if (active) {
-        CandRel rel;
-        p = cand_ecef(e, grid + 4 * j, &rel);
-        const int it = (SAT_MODE == DPE_SAT_PER_TIME) ? (int)((j + grid_offset) % T) : T / 2;
-#pragma unroll 2
-        for (int c = 0; c < e.C; ++c) {
-            const SatGeo& sg = (SAT_MODE == DPE_SAT_PER_TIME) ? geo_tab[(size_t)c * T + it] : geo_mid[c];
-            const double idx = code_index_fast(e, cc[c], sg, p, rel, sat + ((size_t)c * T + it) * 8, c, (double)S);
+    const double rx_time = e.rx_time, Sd = (double)S;
+    for (int c = 0; c < e.C; ++c) {
+        const ChanConst kc = cc[c];
+        const double rc_end = e.rc_end[c];
+        SatGeo sg;
+        if (SAT_MODE == DPE_SAT_MIDDLE) sg = geo_mid[c];
+        const double2* __restrict__ csc = cs + (size_t)c * NL;
+#pragma unroll
+        for (int k = 0; k < kLkCand; ++k) {
+            if (!act[k]) continue;
+            if (SAT_MODE == DPE_SAT_PER_TIME) sg = geo_tab[(size_t)c * T + it[k]];
+            double idx;
+            if (!code_index_fast_core(rx_time, kc, sg, pt[k], rel[k], rc_end, Sd, &idx)) {
+                // next to a rounding boundary of tx: the reference's chain itself, on the same candidate state
+                const Cand p = {rel[k].dx + e.center[0], rel[k].dy + e.center[1], rel[k].dz + e.center[2], pt[k]};
+                idx = code_index(e, kc, p, sat + ((size_t)c * T + it[k]) * 8, c, Sd);
+            }
             const Bin b = make_bin(idx, c, S, W);
             if (b.ok) {
-                const double2 lo = cs[(size_t)c * NL + b.l], hi = cs[(size_t)c * NL + b.l + 1];
+                const double2 lo = csc[b.l], hi = csc[b.l + 1];
                 const double re = hi.x * b.wg + lo.x * b.wf;     // :1808-1812
                 const double im = hi.y * b.wg + lo.y * b.wf;
-                score += mag_pow(re, im, lpower);                // :1816
+                score[k] += mag_pow(re, im, lpower);             // :1816
             } else {
                 ++oow;
             }
         }
-        scores[j] = score;
     }
-    block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
+    // this thread's candidates in increasing index order: strict > keeps the lowest index on ties
+    double v[5] = {0, 0, 0, 0, 0}, mx = -1.0, mi = 9.0e18;
+#pragma unroll
+    for (int k = 0; k < kLkCand; ++k) {
+        if (!act[k]) continue;
+        const int64_t j = base + (int64_t)k * kReduceBlock;
+        scores[j] = score[k];
+        if (WITH_SUMS) {
+            v[0] += score[k] * (rel[k].dx + e.center[0]);
+            v[1] += score[k] * (rel[k].dy + e.center[1]);
+            v[2] += score[k] * (rel[k].dz + e.center[2]);
+            v[3] += score[k] * pt[k];
+        }
+        v[4] += score[k];
+        if (score[k] > mx) { mx = score[k]; mi = (double)(j + grid_offset); }
+    }
+    block_reduce_store_vals<WITH_SUMS ? 5 : 1>(v, mx, mi, (double)oow, blk_partial);
     if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
 }
 
@@ -135,18 +180,21 @@ int launch_sat_geo(dpe_ctx* c, cudaStream_t s) {
 }
 
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
-    const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
+    const int per = kReduceBlock * kLkCand;
+    const int nblk = (int)((c->G + per - 1) / per);
     prof_begin(c, DPE_STAGE_LOOKUP, s);
+    const SatGeo* tab = nullptr;
     if (sat_mode == DPE_SAT_PER_TIME) {
         int rc = launch_sat_geo(c, s);
         if (rc) return rc;
-        k_score_lookup<DPE_SAT_PER_TIME><<<nblk, kReduceBlock, 0, s>>>(
-            c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
-            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, reinterpret_cast<const SatGeo*>(c->sat_geo));
-    } else
-        k_score_lookup<DPE_SAT_MIDDLE><<<nblk, kReduceBlock, 0, s>>>(
-            c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,
-            c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, nullptr);
+        tab = reinterpret_cast<const SatGeo*>(c->sat_geo);
+    }
+#define DPE_LK(SM, WS) k_score_lookup<SM, WS><<<nblk, kReduceBlock, 0, s>>>(                                        \
+        c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,              \
+        c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab)
+    if (sat_mode == DPE_SAT_PER_TIME) { if (c->want_sums) DPE_LK(DPE_SAT_PER_TIME, 1); else DPE_LK(DPE_SAT_PER_TIME, 0); }
+    else { if (c->want_sums) DPE_LK(DPE_SAT_MIDDLE, 1); else DPE_LK(DPE_SAT_MIDDLE, 0); }
+#undef DPE_LK
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
@@ -181,7 +229,7 @@ int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStrea
 }
 
 int kernel_attr_score(const char* name, cudaFuncAttributes* a) {
-    DPE_KATTR("k_score_lookup", k_score_lookup<DPE_SAT_MIDDLE>);
+    DPE_KATTR("k_score_lookup", (k_score_lookup<DPE_SAT_MIDDLE, 0>));
     DPE_KATTR("k_finalize", k_finalize);
     return 0;
 }

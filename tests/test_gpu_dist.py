@@ -86,12 +86,13 @@ def test_two_contexts_in_flight_match_one_at_a_time(capi, mode):
 
 
 def test_side_kernels_fit_beside_k_brute(capi):
-    """The overlap of two epochs relies on every side kernel fitting on an SM next to a k_brute CTA."""
+    """The overlap of two epochs relies on every kernel of a brute-force epoch except k_brute itself fitting on an SM
+    next to a k_brute CTA (k_score_lookup only runs in lookup epochs, where there is no k_brute to share with)."""
     rb, _, tb = capi.kernel_attr("k_brute")
     free = 65536 - ((rb + 7) // 8 * 8) * 256
     for k, thr in (("k_prep_corr", 128), ("k_sample_planes", 256),
                    ("k_replica_rd", 256), ("k_pair_bins", 128), ("k_block_scan", 256), ("k_scatter", 128),
-                   ("k_score_pairs", 128), ("k_score_lookup", 128)):
+                   ("k_score_pairs", 128), ("k_finalize", 32)):
         r, _, _ = capi.kernel_attr(k)
         assert ((r + 7) // 8 * 8) * thr <= free, (k, r, thr, free)
 
