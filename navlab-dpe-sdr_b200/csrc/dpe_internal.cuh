@@ -134,6 +134,7 @@ struct dpe_ctx {
     cudaEvent_t ev_epoch, ev_grid, ev_sort;   // epoch upload done / grid upload done / presort done
     cudaStream_t aux_stream;           // dpe_epoch_run's own presort stream (created on first use)
     int64_t launches;
+    int lk_cand_forced;                // DPE_LK_CAND = 3 | 4 | 6: candidates per thread of k_score_lookup (0 = chosen per launch)
     int want_sums;                     // k_score_pairs accumulates sum s*x (0 only inside an arg-max dpe_epoch_submit)
     // asynchronous epochs (dpe_epoch_submit / dpe_epoch_collect)
     cudaStream_t own_stream;

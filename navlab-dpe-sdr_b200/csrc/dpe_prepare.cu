@@ -120,34 +120,52 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     // DC mean for the carrier branch: sum / (float)S (ComplexDivide, batchcorrscores.cu:1065,1210-1216)
     const double inv = 1.0 / (double)(float)S;
     const float mr = dc ? (float)((double)dc[0] * inv) : 0.f, mi = dc ? (float)((double)dc[1] * inv) : 0.f;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-        int n = n0 - W + i;
-        n %= S; if (n < 0) n += S;
-        const double t = tidx[n];
-        const short2 v = reinterpret_cast<const short2*>(iq)[n];
-        const double ph = fi * t + ri;                        // cycles (:293)
-        const float fr = (float)(ph - floor(ph));             // [0, 1): range reduction in FP64, NCO in FP32
-        float sn, cn;
-        sincospif(2.0f * fr, &sn, &cn);
-        const float I = (float)v.x, Q = (float)v.y;
-        const float2 x = make_float2(fmaf(I, cn, Q * sn), fmaf(Q, cn, -I * sn));   // x * conj(exp(j phi)) (cuCmul, :385-407)
-        xs[i + (i >> 3)] = x;
-        const int m = i - W;                                  // sample of the chunk's own 1024
-        if (m >= 0 && m < kCorrChunk) {
-            float r = 0.f;
-            if (n0 + m < S) {                                 // n == n0 + m here (no wrap inside the block)
-                int chip = (int)floor(t * fc + rc);           // :347-348
-                chip = ((chip % K_L_CA) + K_L_CA) % K_L_CA;
-                const int8_t rv = code_s[chip];
-                r = (float)rv;
-                const size_t o = (size_t)c * S + n;
-                rs[o] = rv;
-                if (chip_idx) chip_idx[o] = (int16_t)chip;
-                xw[o] = x;
-                if (zw)   // (x - mean) * conj(carrier), BCS_SubtractDCOffset :470-485
-                    zw[o] = make_float2(fmaf(I - mr, cn, (Q - mi) * sn), fmaf(Q - mi, cn, -(I - mr) * sn));
+    // batches of 4 samples per thread: the 8 global loads of a batch are in flight together (one sample at a time the
+    // kernel sat in "long scoreboard": 3.3 stalled warps per issue at 16 % occupancy)
+    for (int i0 = threadIdx.x; i0 < nx; i0 += 4 * blockDim.x) {
+        double tq[4];
+        short2 vq[4];
+        int nq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * blockDim.x;
+            int n = n0 - W + i;
+            n %= S; if (n < 0) n += S;
+            nq[q] = n;
+            tq[q] = (i < nx) ? __ldg(tidx + n) : 0.0;
+            vq[q] = (i < nx) ? __ldg(reinterpret_cast<const short2*>(iq) + n) : make_short2(0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * blockDim.x;
+            if (i >= nx) break;
+            const int n = nq[q];
+            const double t = tq[q];
+            const short2 v = vq[q];
+            const double ph = fi * t + ri;                        // cycles (:293)
+            const float fr = (float)(ph - floor(ph));             // [0, 1): range reduction in FP64, NCO in FP32
+            float sn, cn;
+            sincospif(2.0f * fr, &sn, &cn);
+            const float I = (float)v.x, Q = (float)v.y;
+            const float2 x = make_float2(fmaf(I, cn, Q * sn), fmaf(Q, cn, -I * sn));   // x * conj(exp(j phi)) (cuCmul, :385-407)
+            xs[i + (i >> 3)] = x;
+            const int m = i - W;                                  // sample of the chunk's own 1024
+            if (m >= 0 && m < kCorrChunk) {
+                float r = 0.f;
+                if (n0 + m < S) {                                 // n == n0 + m here (no wrap inside the block)
+                    int chip = (int)floor(t * fc + rc);           // :347-348
+                    chip = ((chip % K_L_CA) + K_L_CA) % K_L_CA;
+                    const int8_t rv = code_s[chip];
+                    r = (float)rv;
+                    const size_t o = (size_t)c * S + n;
+                    rs[o] = rv;
+                    if (chip_idx) chip_idx[o] = (int16_t)chip;
+                    xw[o] = x;
+                    if (zw)   // (x - mean) * conj(carrier), BCS_SubtractDCOffset :470-485
+                        zw[o] = make_float2(fmaf(I - mr, cn, (Q - mi) * sn), fmaf(Q - mi, cn, -(I - mr) * sn));
+                }
+                r_s[m + (m >> 3)] = r;
             }
-            r_s[m + (m >> 3)] = r;
         }
     }
     __syncthreads();

@@ -22,10 +22,11 @@ namespace dpe {
 // issue -- a latency-bound kernel at 4 % of its HBM roofline).
 // WITH_SUMS = 0 (arg-max estimate): only the sum of scores is reduced, not sum s*x.
 // ---------------------------------------------------------------------------
-constexpr int kLkCand = 4;
-
-template <int SAT_MODE, int WITH_SUMS>
-__global__ void __launch_bounds__(kReduceBlock, 4)
+// kLkCand candidates per thread: 3 (<= 64 registers, 8 CTAs per SM), 4 or 6 (<= 128 registers, 4 CTAs per SM).  The
+// launcher picks the one whose CTA count fills whole waves best: at the demo size (390 625 candidates) 4 per thread is
+// 763 CTAs on 592 slots -- 1.29 waves, the second one 29 % full -- while 6 per thread is 509 CTAs: one wave.
+template <int SAT_MODE, int WITH_SUMS, int kLkCand>
+__global__ void __launch_bounds__(kReduceBlock, (kLkCand == 3) ? 8 : 4)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
                int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
@@ -67,25 +68,34 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         SatGeo sg;
         if (SAT_MODE == DPE_SAT_MIDDLE) sg = geo_mid[c];
         const double2* __restrict__ csc = cs + (size_t)c * NL;
+        // straight-line code over the kLkCand candidates (no branch inside: the four FP64 chains interleave)
+        double idx[kLkCand];
+        bool fast = true;
 #pragma unroll
         for (int k = 0; k < kLkCand; ++k) {
-            if (!act[k]) continue;
             if (SAT_MODE == DPE_SAT_PER_TIME) sg = geo_tab[(size_t)c * T + it[k]];
-            double idx;
-            if (!code_index_fast_core(rx_time, kc, sg, pt[k], rel[k], rc_end, Sd, &idx)) {
-                // next to a rounding boundary of tx: the reference's chain itself, on the same candidate state
+            fast &= code_index_fast_core(rx_time, kc, sg, pt[k], rel[k], rc_end, Sd, &idx[k]);
+        }
+        if (__builtin_expect(!fast, 0)) {
+            // a pair of this thread sits next to a rounding boundary of tx (probability ~1e-5): redo the thread's pairs
+            // of this channel through the reference's chain itself, on the same candidate states
+#pragma unroll
+            for (int k = 0; k < kLkCand; ++k) {
                 const Cand p = {rel[k].dx + e.center[0], rel[k].dy + e.center[1], rel[k].dz + e.center[2], pt[k]};
-                idx = code_index(e, kc, p, sat + ((size_t)c * T + it[k]) * 8, c, Sd);
+                idx[k] = code_index(e, kc, p, sat + ((size_t)c * T + it[k]) * 8, c, Sd);
             }
-            const Bin b = make_bin(idx, c, S, W);
-            if (b.ok) {
-                const double2 lo = csc[b.l], hi = csc[b.l + 1];
-                const double re = hi.x * b.wg + lo.x * b.wf;     // :1808-1812
-                const double im = hi.y * b.wg + lo.y * b.wf;
-                score[k] += mag_pow(re, im, lpower);             // :1816
-            } else {
-                ++oow;
-            }
+        }
+#pragma unroll
+        for (int k = 0; k < kLkCand; ++k) {
+            const Bin b = make_bin(idx[k], c, S, W);
+            const int l = min(max(b.l, 0), NL - 2);              // clamped: the loads are unconditional
+            const double2 lo = csc[l], hi = csc[l + 1];
+            const double re = hi.x * b.wg + lo.x * b.wf;         // :1808-1812
+            const double im = hi.y * b.wg + lo.y * b.wf;
+            const double m = mag_pow(re, im, lpower);            // :1816
+            const bool use = b.ok && act[k];
+            score[k] += use ? m : 0.0;
+            oow += (act[k] && !b.ok) ? 1 : 0;
         }
     }
     // this thread's candidates in increasing index order: strict > keeps the lowest index on ties
@@ -180,7 +190,20 @@ int launch_sat_geo(dpe_ctx* c, cudaStream_t s) {
 }
 
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
-    const int per = kReduceBlock * kLkCand;
+    // candidates per thread: the choice that wastes the least of its last wave (ties: more per thread)
+    static const int kNc[3] = {3, 4, 6}, kOcc[3] = {8, 4, 4};
+    int nc = 4;
+    if (c->lk_cand_forced) nc = c->lk_cand_forced;
+    else {
+        double best = -1.0;
+        for (int i = 0; i < 3; ++i) {
+            const double ctas = (double)((c->G + kReduceBlock * kNc[i] - 1) / (kReduceBlock * kNc[i]));
+            const double waves = ctas / ((double)c->sm_count * kOcc[i]);
+            const double eff = waves / ceil(waves) * (kNc[i] == 3 ? 0.9 : 1.0);      // 3 per thread: less ILP per warp
+            if (eff >= best - 1e-9) { best = eff; nc = kNc[i]; }
+        }
+    }
+    const int per = kReduceBlock * nc;
     const int nblk = (int)((c->G + per - 1) / per);
     prof_begin(c, DPE_STAGE_LOOKUP, s);
     const SatGeo* tab = nullptr;
@@ -189,11 +212,13 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
         if (rc) return rc;
         tab = reinterpret_cast<const SatGeo*>(c->sat_geo);
     }
-#define DPE_LK(SM, WS) k_score_lookup<SM, WS><<<nblk, kReduceBlock, 0, s>>>(                                        \
+#define DPE_LK(SM, WS, NC) k_score_lookup<SM, WS, NC><<<nblk, kReduceBlock, 0, s>>>(                                \
         c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,              \
         c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab)
-    if (sat_mode == DPE_SAT_PER_TIME) { if (c->want_sums) DPE_LK(DPE_SAT_PER_TIME, 1); else DPE_LK(DPE_SAT_PER_TIME, 0); }
-    else { if (c->want_sums) DPE_LK(DPE_SAT_MIDDLE, 1); else DPE_LK(DPE_SAT_MIDDLE, 0); }
+#define DPE_LK_NC(SM, WS) do { if (nc == 3) DPE_LK(SM, WS, 3); else if (nc == 6) DPE_LK(SM, WS, 6); else DPE_LK(SM, WS, 4); } while (0)
+    if (sat_mode == DPE_SAT_PER_TIME) { if (c->want_sums) DPE_LK_NC(DPE_SAT_PER_TIME, 1); else DPE_LK_NC(DPE_SAT_PER_TIME, 0); }
+    else { if (c->want_sums) DPE_LK_NC(DPE_SAT_MIDDLE, 1); else DPE_LK_NC(DPE_SAT_MIDDLE, 0); }
+#undef DPE_LK_NC
 #undef DPE_LK
     c->launches++;
     DPE_CUDA(cudaGetLastError());
@@ -229,7 +254,9 @@ int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStrea
 }
 
 int kernel_attr_score(const char* name, cudaFuncAttributes* a) {
-    DPE_KATTR("k_score_lookup", (k_score_lookup<DPE_SAT_MIDDLE, 0>));
+    DPE_KATTR("k_score_lookup", (k_score_lookup<DPE_SAT_MIDDLE, 0, 4>));
+    DPE_KATTR("k_score_lookup_3", (k_score_lookup<DPE_SAT_MIDDLE, 0, 3>));
+    DPE_KATTR("k_score_lookup_6", (k_score_lookup<DPE_SAT_MIDDLE, 0, 6>));
     DPE_KATTR("k_finalize", k_finalize);
     return 0;
 }
