@@ -392,10 +392,15 @@ def roofline_of(m, S, clocks, peaks, fp32_peak):
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
         nominal = 148 * 128 * 2 * mhz * 1e6 / 1e12
         step_frac = kb["flop"] / (m["ms_per_step"] * 1e-3) / 1e12 / fp32_peak if WORKLOADS[m["workload"]].get("streams") is None else None
+        traffic, traffic_note = None, "no ncu capture committed for this workload / GPU count"
+        try:                                                       # DRAM bytes of one launch, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_k_brute_traffic.json")))
+            if tr.get("workload") == m["workload"] and int(os.environ.get("WORLD_SIZE", "1")) == tr.get("n_gpus"):
+                traffic, traffic_note = tr["dram_bytes_per_launch"], tr["source"]
+        except Exception:
+            pass
         return dict(bound="fp32", kernel="k_brute", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
-                    frac=achieved / fp32_peak, traffic=None,
-                    traffic_note="not measured in this run (ncu --set full capture of the same command: profiles/); "
-                                 "k_brute streams its planes from L2, DRAM traffic is ~60 MB per launch",
+                    frac=achieved / fp32_peak, traffic=traffic, traffic_note=traffic_note,
                     peak_source="FFMA2 issue-limit micro-benchmark in this run (dpe_microbench_fp32: scalar multiplier, "
                                 "shared pair); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                     algorithmic="6 FLOP x S x valid (candidate,PRN) pairs per launch (this rank's shard)",
