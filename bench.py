@@ -256,12 +256,12 @@ def measure(rig, args, workload, steps, warmup, with_latency=True, with_e2e=True
         return res
 
     def timed(K, Wm, host, score=None):
-        run_steps(Wm, host, score)
+        run_steps(max(Wm, depth), host, score)                      # every context (and its communicator) has run once
         rig.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        res = run_steps(K, host, score, first=Wm)
+        res = run_steps(K, host, score, first=max(Wm, depth))
         e1.record()
         rig.barrier()
         wall = time.perf_counter() - t0

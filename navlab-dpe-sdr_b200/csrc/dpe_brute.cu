@@ -343,13 +343,15 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
             // software pipeline over the 4 chunks of the tile: the shared-memory operands of chunk
             // ch+1 are in flight while chunk ch is computed (2 warps per scheduler are not enough to
             // hide the LDS latency otherwise: they run in lock step)
-            BruteChunk cur, nxt;
-            cur.load(px, 0);
+            if (n_valid > 0) {             // a padding group (bucket rounded up to a whole slot) only keeps the barriers going
+                BruteChunk cur, nxt;
+                cur.load(px, 0);
 #pragma unroll
-            for (int ch = 0; ch < kBfTile / kBfChunk; ++ch) {
-                if (ch + 1 < kBfTile / kBfChunk) nxt.load(px, ch + 1);
-                cur.accumulate(al, acc);
-                cur = nxt;
+                for (int ch = 0; ch < kBfTile / kBfChunk; ++ch) {
+                    if (ch + 1 < kBfTile / kBfChunk) nxt.load(px, ch + 1);
+                    cur.accumulate(al, acc);
+                    cur = nxt;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_u(empty0 + 8 * stg);

@@ -20,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*GetVersion)(int*) = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;   // optional (>= 2.14)
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -60,6 +61,7 @@ const char* nccl_load() {
         snprintf(why, sizeof(why), "libnccl.so.2 lacks a required symbol");
         return why;
     }
+    sym(h, "ncclCommInitRankConfig", &a.CommInitRankConfig);
     a.ok = true;
     g_nccl = a;
     return nullptr;
@@ -117,7 +119,18 @@ int dpe_comm_init(dpe_ctx* c, int nranks, int rank, const void* id) {
     ncclUniqueId u;
     memcpy(&u, id, sizeof(u));
     ncclComm_t comm = nullptr;
-    DPE_NCCL(g_nccl.CommInitRank(&comm, nranks, u, rank));
+    // one CTA per collective: the packet (200 kB - 800 kB) and the 128-byte partials need no more, and a collective
+    // must fit on the single SM k_brute leaves free (comm_reserve_sms below) to run UNDER it
+    const char* mc = getenv("DPE_COMM_MAX_CTAS");
+    const int max_ctas = mc ? atoi(mc) : 1;
+    if (g_nccl.CommInitRankConfig && max_ctas > 0) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = max_ctas;
+        DPE_NCCL(g_nccl.CommInitRankConfig(&comm, nranks, u, rank, &cfg));
+    } else {
+        DPE_NCCL(g_nccl.CommInitRank(&comm, nranks, u, rank));
+    }
     double* gathered = nullptr;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&gathered), sizeof(double) * dpe::kPartialLen * nranks);
     if (e != cudaSuccess) {
