@@ -201,6 +201,10 @@ def measure(rig, args, workload, steps, warmup, with_latency=True, with_e2e=True
         per = (G_total + world - 1) // world
         lo, hi = min(rank * per, G_total), min((rank + 1) * per, G_total)
         my_streams = [0]
+        fake = int(os.environ.get("DPE_BENCH_SHARD_OF", "0"))       # tuning aid: one GPU holding what rank 3 of `fake` would
+        if fake > 1 and world == 1:
+            per = (G_total + fake - 1) // fake
+            lo, hi = min(3 * per, G_total), min(4 * per, G_total)
     shard = np.ascontiguousarray(grid[lo:hi])
     score_mode = capi.SCORE_LOOKUP if args.path == "lookup" else capi.SCORE_BRUTE
     est_mode = capi.EST_WEIGHTED if args.estimate == "weighted" else capi.EST_ARGMAX

@@ -263,7 +263,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
         int64_t bx_stride, int64_t brd_stride, const int4* __restrict__ hdr,
         const int32_t* __restrict__ ent_j, const float* __restrict__ ent_a,
         const int32_t* __restrict__ n_groups, float2* __restrict__ pair_v, int64_t G, int S_pad,
-        int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket) {
+        int H, int W, float2* __restrict__ tail_part, unsigned int* __restrict__ tail_ticket, int skip_pad) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * kBfStages];  // full[s] = bars[s], empty[s] = bars[stages + s]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -343,7 +343,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
             // software pipeline over the 4 chunks of the tile: the shared-memory operands of chunk
             // ch+1 are in flight while chunk ch is computed (2 warps per scheduler are not enough to
             // hide the LDS latency otherwise: they run in lock step)
-            if (n_valid > 0) {             // a padding group (bucket rounded up to a whole slot) only keeps the barriers going
+            if (n_valid > 0 || !skip_pad) {   // a padding group (bucket rounded up to a whole slot) only keeps the barriers going
                 BruteChunk cur, nxt;
                 cur.load(px, 0);
 #pragma unroll
@@ -507,7 +507,7 @@ int launch_brute_corr(dpe_ctx* c, cudaStream_t s) {
     k_brute<<<n_cta > 0 ? n_cta : 1, kBfWarps * 32, smem, s>>>(
         c->bx, c->brd, c->bx_stride, c->brd_stride, reinterpret_cast<const int4*>(c->hdr),
         reinterpret_cast<const int32_t*>(c->ent_j), c->ent_a, c->n_groups, c->pair_v, c->G, (int)c->S_pad,
-        c->H, c->W, c->tail_part, c->tail_ticket);
+        c->H, c->W, c->tail_part, c->tail_ticket, c->brute_skip_pad);
     prof_end(c, s);
     c->launches++;
     DPE_CUDA(cudaGetLastError());

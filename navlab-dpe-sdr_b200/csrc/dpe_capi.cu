@@ -226,6 +226,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     { const char* ng = getenv("DPE_NO_GRAPH"); c->use_graph = !(ng && ng[0] == '1'); }
+    { const char* sp = getenv("DPE_BRUTE_SKIP_PAD"); c->brute_skip_pad = !(sp && sp[0] == '0'); }
     { const char* lk = getenv("DPE_LK_CAND"); const int v = lk ? atoi(lk) : 0; c->lk_cand_forced = (v == 3 || v == 4 || v == 6) ? v : 0; }
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);

@@ -128,6 +128,7 @@ struct dpe_ctx {
     int have_block, have_epoch, have_prepare, have_corr, have_scores;
     int epoch_C;
     int brute_attr_set;
+    int brute_skip_pad;                // padding groups skip their FFMA work (DPE_BRUTE_SKIP_PAD, default 1)
     int have_planes;                   // brute-force planes match the current prepare + correlogram
     int sort_valid;                    // 0, or 1 + sat_mode the brute-force work lists were built for (this epoch)
     int sort_pending;                  // a presort on another stream has not been waited for yet
