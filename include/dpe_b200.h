@@ -349,6 +349,12 @@ int dpe_stream_destroy(void* stream);
 int dpe_stream_sync(void* stream);
 int dpe_host_alloc(void** ptr, size_t bytes);
 int dpe_host_free(void* ptr);
+/* the device side of SampleBlock's ring (cudaMalloc + the reader thread's cudaMemcpyAsync on its own stream,
+ * sampleblock.cu:221,403): dpe_stream_create_on / dpe_device_alloc bind `device` for the call only           */
+int dpe_stream_create_on(void** stream, int device);
+int dpe_device_alloc(void** ptr, size_t bytes, int device);
+int dpe_device_free(void* ptr, int device);
+int dpe_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream, int device);
 int dpe_device_count(void);
 
 /* ---- per-stage device timing (bench.py's roofline.achieved) --------------------

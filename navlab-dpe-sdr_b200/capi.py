@@ -42,7 +42,8 @@ EXPORTS = (
     "dpe_host_free", "dpe_device_count", "dpe_microbench_fp32",
     "dpe_microbench_hbm", "dpe_epoch_submit", "dpe_epoch_collect", "dpe_epoch_pending", "dpe_epoch_run_dist",
     "dpe_comm_get_unique_id", "dpe_comm_init", "dpe_comm_destroy", "dpe_comm_info", "dpe_ctx_stream",
-    "dpe_kernel_attr", "dpe_epoch_set_device")
+    "dpe_kernel_attr", "dpe_epoch_set_device", "dpe_stream_create_on", "dpe_device_alloc",
+    "dpe_device_free", "dpe_copy_h2d")
 
 
 class DpeCfg(C.Structure):

@@ -885,6 +885,31 @@ int dpe_host_free(void* ptr) {
     if (ptr) DPE_CUDA(cudaFreeHost(ptr));
     return DPE_OK;
 }
+int dpe_stream_create_on(void** stream, int device) {
+    DPE_REQUIRE(stream, DPE_EINVAL, "null argument");
+    DevGuard guard(device);
+    cudaStream_t s;
+    DPE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return DPE_OK;
+}
+int dpe_device_alloc(void** ptr, size_t bytes, int device) {
+    DPE_REQUIRE(ptr && bytes, DPE_EINVAL, "bad argument");
+    DevGuard guard(device);
+    DPE_CUDA(cudaMalloc(ptr, bytes));
+    return DPE_OK;
+}
+int dpe_device_free(void* ptr, int device) {
+    DevGuard guard(device);
+    if (ptr) DPE_CUDA(cudaFree(ptr));
+    return DPE_OK;
+}
+int dpe_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream, int device) {
+    DPE_REQUIRE(dst_device && src_host, DPE_EINVAL, "null argument");
+    DevGuard guard(device);
+    DPE_CUDA(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return DPE_OK;
+}
 int dpe_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -82,6 +82,9 @@ class SampleBlock : public Module {
     char InputSourceType = 0;
     int64_t BlockLength = 0;                       // samples per block (64-bit: 10 MHz works)
     std::vector<int16_t*> Blocks;                  // pinned host ring
+    std::vector<int16_t*> DevBlocks;               // device ring: the reader thread uploads on its own stream (sampleblock.cu:221,403)
+    void* readerStream = nullptr;
+    int Device = 0;
     int fd = -1;                                   // capture file or connected TCP socket
     int OpenSource();
     std::thread reader;

@@ -97,7 +97,7 @@ SampleBlock::SampleBlock() {
     AllocateOutputs(3);
     // the reference hands over a device pointer filled by its reader thread; here the block stays in
     // page-locked host memory and BatchCorrScores stages it with dpe_block_stage on the flow stream
-    ConfigOutput(0, "Samples", UNDEFINED_t, VALUE_CMPX, HOST, 2, nullptr, 0);
+    ConfigOutput(0, "Samples", UNDEFINED_t, VALUE_CMPX, CUDA_DEVICE, 2, nullptr, 0);      // a device block, like the reference's
     ConfigOutput(1, "SamplingFrequency", DOUBLE_t, FREQUENCY_HZ, HOST, 1, &SamplingFrequency, 0);
     ConfigOutput(2, "SampleLength", DOUBLE_t, VALUE, HOST, 1, &SampleLength, 0);
     InsertParam("Filename", Filename, CHAR_t, kNameCap, 0);
@@ -107,6 +107,7 @@ SampleBlock::SampleBlock() {
     InsertParam("SampleLength", &SampleLength, DOUBLE_t, sizeof(double), sizeof(double));
     InsertParam("RunLive", &RunLive, BOOL_t, sizeof(bool), sizeof(bool));
     InsertParam("InputSourceType", &InputSourceType, CHAR_t, sizeof(char), sizeof(char));
+    InsertParam("Device", &Device, INT_t, sizeof(int), sizeof(int));           // CUDA ordinal of the device ring
 }
 
 SampleBlock::~SampleBlock() { Stop(); }
@@ -163,11 +164,17 @@ int SampleBlock::Start(void*) {
     if (OpenSource()) return -1;
     BlockLength = (int64_t)(SamplingFrequency * SampleLength + 0.5);
     Blocks.assign(kNumBlocks, nullptr);
+    DevBlocks.assign(kNumBlocks, nullptr);
     for (int i = 0; i < kNumBlocks; ++i)
-        if (dpe_host_alloc((void**)&Blocks[i], sizeof(int16_t) * 2 * (size_t)BlockLength)) {
+        if (dpe_host_alloc((void**)&Blocks[i], sizeof(int16_t) * 2 * (size_t)BlockLength) ||
+            dpe_device_alloc((void**)&DevBlocks[i], sizeof(int16_t) * 2 * (size_t)BlockLength, Device)) {
             std::cerr << "[SampleBlock] Unable to allocate sample buffers: " << dpe_last_error() << std::endl;
             return -1;
         }
+    if (dpe_stream_create_on(&readerStream, Device)) {
+        std::cerr << "[SampleBlock] Unable to create the upload stream: " << dpe_last_error() << std::endl;
+        return -1;
+    }
     UpdateOutput(0, BlockLength, nullptr, 0);
     filled = 0; freeSlots = kNumBlocks; loadIdx = 0; procIdx = -1; eof = false; firstUpdate = true;
     KeepRunning = true;
@@ -201,6 +208,14 @@ void SampleBlock::ReaderThread() {
             std::clog << "[SampleBlock] Reached EOF." << std::endl << "[SampleBlock] blockCnt = " << blockCnt << std::endl;
             break;
         }
+        // H2D ahead of time on the reader's own stream (sampleblock.cu:403): the flow thread gets a resident block
+        if (dpe_copy_h2d(DevBlocks[loadIdx], Blocks[loadIdx], bytes, readerStream, Device) || dpe_stream_sync(readerStream)) {
+            std::cerr << "[SampleBlock] upload failed: " << dpe_last_error() << std::endl;
+            std::lock_guard<std::mutex> lk(mu);
+            eof = true;
+            cv.notify_all();
+            break;
+        }
         ++blockCnt;
         loadIdx = (loadIdx + 1) % kNumBlocks;
         std::lock_guard<std::mutex> lk(mu);
@@ -224,7 +239,7 @@ int SampleBlock::Update(void*) {
     if (filled == 0) return -1;                    // EOF: ends the flow
     --filled;
     procIdx = (procIdx + 1) % kNumBlocks;
-    outputs[0].Data = Blocks[procIdx];
+    outputs[0].Data = DevBlocks[procIdx];
     return 0;
 }
 
@@ -238,6 +253,9 @@ int SampleBlock::Stop() {
     if (reader.joinable()) reader.join();
     for (size_t i = 0; i < Blocks.size(); ++i) dpe_host_free(Blocks[i]);
     Blocks.clear();
+    for (size_t i = 0; i < DevBlocks.size(); ++i) dpe_device_free(DevBlocks[i], Device);
+    DevBlocks.clear();
+    if (readerStream) { dpe_stream_destroy(readerStream); readerStream = nullptr; }
     if (fd >= 0) { ::close(fd); fd = -1; }
     Started = false;
     return 0;
