@@ -366,6 +366,50 @@ def measure(rig, args, workload, steps, warmup, with_latency=True, with_e2e=True
     return out
 
 
+def velocity_brute_leg(rig, args, fp32_peak):
+    """SURVEY 8 a', last sentence: the velocity / clock-drift manifold with every (velocity candidate, PRN) pair
+    correlating the whole block against its own blended carrier (k_brute_vel), beside the lookup formulation
+    (k_score_vel) on the same 25^4 velocity grid -- the grid the console flow uses."""
+    torch, capi = rig.torch, rig.capi
+    import dpe_pkg
+    synth = dpe_pkg.submodule("synth")
+    sc, grid, tg = build_workload("demo")
+    vgrid, _ = synth.uniform_grid(25, (0.5, 0.5, 0.5, 0.25))
+    C, S = sc.C, sc.S
+    small = np.ascontiguousarray(grid[:4096])
+    ctx = capi.Context(fs=sc.cfg.fs, S=S, max_chan=C, G=small.shape[0], time_dim=len(tg), lag_halfwidth=args.lag_halfwidth,
+                       Gv=vgrid.shape[0], dopp_halfwidth=64, flags=capi.FLAG_BRUTE_VEL, device=rig.local)
+    ctx.grid_set(small)
+    ctx.vel_grid_set(vgrid)
+    out = {}
+    for mode, name in ((1, "lookup"), (2, "brute")):
+        iqs = [sc.block(b) for b in range(3)]
+        eps = [epoch_for_block(sc, b, tg) for b in range(3)]
+        res = ctx.epoch_run_dist(iqs[0], eps[0], None, capi.SCORE_LOOKUP, capi.EST_ARGMAX, mode)      # warm-up (graph capture)
+        ctx.profile_enable(True)
+        K = 3
+        for i in range(K):
+            rig.flush.zero_()
+            torch.cuda.synchronize()
+            res = ctx.epoch_run_dist(iqs[i % 3], eps[i % 3], None, capi.SCORE_LOOKUP, capi.EST_ARGMAX, mode)
+        stage_ms, stage_cnt = ctx.profile_read()
+        ctx.profile_enable(False)
+        ms = float(stage_ms[capi.STAGE_VELOCITY] / max(int(stage_cnt[capi.STAGE_VELOCITY]), 1))
+        pairs = vgrid.shape[0] * C - res.vel_out_of_window
+        rec = dict(stage_ms=ms, valid_pairs=int(pairs), vel_fix=[res.z[i] for i in range(4, 8)], vel_argmax=res.vel_argmax)
+        if mode == 2:
+            flop = 12.0 * S * pairs
+            rec.update(flop=flop, achieved_tflops=flop / (ms * 1e-3) / 1e12, frac=flop / (ms * 1e-3) / 1e12 / fp32_peak,
+                       algorithmic="12 FLOP x S x valid (velocity candidate, PRN) pairs: 1 FFMA2 blends the complex carrier, "
+                                   "2 FFMA2 do the complex MAC; the stage time includes the plane, the pair sort and the "
+                                   "reduction (5 side launches)")
+        out[name] = rec
+    ctx.close()
+    out["same_fix"] = out["lookup"]["vel_argmax"] == out["brute"]["vel_argmax"]
+    out["config"] = dict(velocity_candidates=int(vgrid.shape[0]), prns=C, S=S, doppler_halfwidth_bins=64)
+    return out
+
+
 def side_kernel_report(capi):
     """Registers x threads of every kernel: do the side kernels fit on an SM beside a k_brute CTA?"""
     rep = {}
@@ -442,6 +486,7 @@ def run_ours(args):
     if rig.rank != 0:
         rig.close()
         return
+    vel_brute = None
 
     peaks = {}
     try:
@@ -452,6 +497,11 @@ def run_ours(args):
     cfg = config_for(args)
     S = cfg["S"]
     roofline = roofline_of(main, S, main["clocks"], peaks, fp32_peak)
+    if rig.world == 1 and args.workload == "demo" and args.vel_brute:
+        try:
+            vel_brute = velocity_brute_leg(rig, args, fp32_peak)
+        except Exception as exc:
+            vel_brute = dict(error=repr(exc))
     configs = {}
     for n, m in subs.items():
         if "error" in m:
@@ -506,7 +556,7 @@ def run_ours(args):
                 gpu_launches_per_epoch=int(main["launches_per_epoch"]),
                 latency=main.get("latency"), roofline=roofline, cpu_baseline=cpu, like_for_like=like,
                 reference_gpu=ref_gpu, clocks=main["clocks"], other_path=main.get("other_path"), flow=flow,
-                configs=configs, side_kernels=main.get("side_kernels"), wall_s=main["wall_s"], fix=main["fix"])
+                configs=configs, velocity_brute=vel_brute, side_kernels=main.get("side_kernels"), wall_s=main["wall_s"], fix=main["fix"])
     print(json.dumps(line))
     rig.close()
 
@@ -684,6 +734,8 @@ def main():
     ap.add_argument("--both", action="store_true", default=True, help="also time the other scoring path")
     ap.add_argument("--no-both", dest="both", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vel-brute", dest="vel_brute", action="store_false", default=True,
+                    help="skip the brute-force velocity manifold leg (1 GPU, demo)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--cpu-procs", type=int, default=64)
     ap.add_argument("--flow-epochs", type=int, default=100,

@@ -90,6 +90,7 @@ enum {
 #define DPE_FLAG_KEEP_CHIP_IDX 1u   /* store chip indices (parity tests)          */
 #define DPE_FLAG_BRUTE_TILES   2u   /* allocate + emit the brute-force tiles      */
 #define DPE_FLAG_KEEP_BINS     4u   /* store per-(candidate,PRN) bins (parity)    */
+#define DPE_FLAG_BRUTE_VEL     8u   /* allocate the work lists of the brute-force velocity manifold (needs Gv > 0) */
 
 typedef struct dpe_ctx dpe_ctx;
 
@@ -266,6 +267,11 @@ int dpe_estimate(dpe_ctx* ctx, int est_mode, const double* gathered, int nranks,
  * BCM_VelMeasML + BCM_MakeVelMeas (batchcorrscores.cu:1158-1180,
  * batchcorrmanifold.cu:1861-1963,2030-2068).  Fills zVal[4:8].                   */
 int dpe_score_vel(dpe_ctx* ctx, void* stream);
+/* dpe_score_vel_brute: the same fix with every (velocity candidate, PRN) pair correlating the whole block against its
+ * own BLENDED carrier (1 - a) exp(-j 2 pi n m / N_c) + a exp(-j 2 pi n (m+1) / N_c) -- SURVEY.md section 8 a', last
+ * sentence; by linearity equal to the lerp of two CarrScores bins (batchcorrmanifold.cu:1950-1958) to rounding.
+ * Needs DPE_FLAG_BRUTE_VEL.  In dpe_epoch_run / dpe_epoch_submit: with_vel = 2.                                   */
+int dpe_score_vel_brute(dpe_ctx* ctx, void* stream);
 
 /* dpe_result_fetch: D2H of the result block; synchronises the stream.           */
 int dpe_result_fetch(dpe_ctx* ctx, dpe_result* out, void* stream);

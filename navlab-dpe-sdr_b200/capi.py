@@ -26,7 +26,7 @@ SAT_MIDDLE, SAT_PER_TIME = 0, 1
 (PTR_SAMPLES, PTR_CODE_SCORES, PTR_POS_SCORES, PTR_ZVAL, PTR_RVAL, PTR_GRID, PTR_PARTIAL,
  PTR_CHIP_IDX, PTR_XW, PTR_CARR_SCORES, PTR_VEL_SCORES, PTR_VEL_GRID, PTR_REPLICA_SIGN,
  PTR_CA_TABLE) = range(14)
-FLAG_KEEP_CHIP_IDX, FLAG_BRUTE_TILES, FLAG_KEEP_BINS = 1, 2, 4
+FLAG_KEEP_CHIP_IDX, FLAG_BRUTE_TILES, FLAG_KEEP_BINS, FLAG_BRUTE_VEL = 1, 2, 4, 8
 PART_CHANNELS, PART_GEOMETRY = 1, 2
 DEBUG_BINS_EXACT = 16
 (STAGE_PREPARE, STAGE_CORRELOGRAM, STAGE_LOOKUP, STAGE_BRUTE_BINS, STAGE_BRUTE_CORR, STAGE_BRUTE_SCORE,
@@ -43,7 +43,7 @@ EXPORTS = (
     "dpe_microbench_hbm", "dpe_epoch_submit", "dpe_epoch_collect", "dpe_epoch_pending", "dpe_epoch_run_dist",
     "dpe_comm_get_unique_id", "dpe_comm_init", "dpe_comm_destroy", "dpe_comm_info", "dpe_ctx_stream",
     "dpe_kernel_attr", "dpe_epoch_set_device", "dpe_stream_create_on", "dpe_device_alloc",
-    "dpe_device_free", "dpe_copy_h2d")
+    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute")
 
 
 class DpeCfg(C.Structure):
@@ -105,6 +105,7 @@ def load_library(path: str | None = None):
     lib.dpe_brute_presort.argtypes = [vp, i32, vp]
     lib.dpe_estimate.argtypes = [vp, i32, vp, i32, vp]
     lib.dpe_score_vel.argtypes = [vp, vp]
+    lib.dpe_score_vel_brute.argtypes = [vp, vp]
     lib.dpe_result_fetch.argtypes = [vp, C.POINTER(DpeResult), vp]
     lib.dpe_epoch_run.argtypes = [vp, vp, C.POINTER(DpeEpoch), vp, i32, i32, i32, C.POINTER(DpeResult), vp]
     lib.dpe_dev_ptr.argtypes = [vp, i32]
@@ -217,6 +218,9 @@ class Context:
 
     def score_vel(self, stream=0):
         _check(self.lib, self.lib.dpe_score_vel(self.h, C.c_void_p(stream)))
+
+    def score_vel_brute(self, stream=0):
+        _check(self.lib, self.lib.dpe_score_vel_brute(self.h, C.c_void_p(stream)))
 
     def block_stage(self, iq, stream=0):
         if isinstance(iq, np.ndarray):

@@ -454,6 +454,24 @@ size_t brute_smem_bytes(int) {
     return (size_t)kBfStages * 2 * kXTileF * sizeof(float);
 }
 
+// second and third launch of the pair sort (per-bucket scan of the per-CTA counts + bucket layout; headers + scatter),
+// shared by the position pairs (buckets = PRN x lag) and the velocity pairs (PRN x Doppler bin, dpe_vel.cu)
+int launch_sort_tail(dpe_ctx* c, const SortLists& L, int64_t G, int W, int C, unsigned int* ticket, cudaStream_t s) {
+    const int NB = 2 * W + 1, nbuck = C * NB;
+    const int nblk = (int)((G + kSortBlock - 1) / kSortBlock);
+    k_block_scan<<<nbuck, 256, 0, s>>>(L.blk_hist, nblk, L.hist, nbuck, L.group_base, L.bucket_base, L.n_groups,
+                                       L.max_groups, ticket);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    dim3 gs(nblk, C);
+    k_scatter<<<gs, kSortBlock, sizeof(int32_t) * ((kSortBlock / 32) * NB + nbuck + 1), s>>>(
+        L.pair_k, L.pair_a, G, W, nbuck, L.hist, L.group_base, L.bucket_base, L.blk_hist,
+        reinterpret_cast<int32_t*>(L.ent_j), L.ent_a, reinterpret_cast<int4*>(L.hdr), L.max_groups);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
+}
+
 // bins + stable counting sort of the pairs into (PRN, lag) buckets / groups / slots; needs the epoch
 // parameters only (dpe_brute_presort may run it on another stream than the sample pre-pass)
 int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s) {
@@ -472,16 +490,10 @@ int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s) {
             c->W, c->T, c->G, c->cfg.grid_offset, c->pair_k, c->pair_a, c->pair_v, c->blk_hist, nullptr);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
-    k_block_scan<<<nbuck, 256, 0, s>>>(c->blk_hist, nblk, c->hist, nbuck, c->group_base, c->bucket_base, c->n_groups,
-                                       c->max_groups, c->ticket + 1);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
-    dim3 gs(nblk, C);
-    k_scatter<<<gs, kSortBlock, sizeof(int32_t) * ((kSortBlock / 32) * NB + nbuck + 1), s>>>(
-        c->pair_k, c->pair_a, c->G, c->W, nbuck, c->hist, c->group_base, c->bucket_base, c->blk_hist,
-        reinterpret_cast<int32_t*>(c->ent_j), c->ent_a, reinterpret_cast<int4*>(c->hdr), c->max_groups);
-    c->launches++;
-    DPE_CUDA(cudaGetLastError());
+    SortLists L = {c->pair_k, c->pair_a, c->blk_hist, c->hist, c->group_base, c->bucket_base, c->n_groups, c->hdr, c->ent_j,
+                   c->ent_a, c->max_groups};
+    int rc = launch_sort_tail(c, L, c->G, c->W, C, c->ticket + 1, s);
+    if (rc) return rc;
     prof_end(c, s);
     return DPE_OK;
 }

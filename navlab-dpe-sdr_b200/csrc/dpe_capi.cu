@@ -122,6 +122,9 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
                     "8*2^ceil(log2 S) limits S to 2^21)", (long long)nf);
         Wd = cfg->dopp_halfwidth > 0 ? cfg->dopp_halfwidth : 64;
         DPE_REQUIRE(2 * Wd + 2 < nf, DPE_EINVAL, "Doppler window wider than the spectrum");
+        DPE_REQUIRE(!(cfg->flags & DPE_FLAG_BRUTE_VEL) ||
+                    sizeof(int32_t) * ((size_t)cfg->max_chan * (2 * Wd + 1) + 1 + 4 * (2 * Wd + 1)) <= 48 * 1024, DPE_EINVAL,
+                    "max_chan * (2 Wd + 1) too large for the velocity pair sort");
     }
     DevGuard guard(cfg->device >= 0 ? cfg->device : 0);
     int ndev = 0;
@@ -213,6 +216,23 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->bb, C * S);
         DPE_ALLOC(c->vpart, C * c->nchunk * c->NBd);
         DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
+        if (cfg->flags & DPE_FLAG_BRUTE_VEL) {
+            const size_t NBv = 2 * c->Wd + 1, Gv = (size_t)cfg->Gv;
+            c->vS_pad = ((c->S + 1023) / 1024) * 1024;
+            c->vmax_groups = (int64_t)(C * ((Gv + kBfNC - 1) / kBfNC + NBv * kBfWarps));
+            DPE_ALLOC(c->vbb, C * c->vS_pad);
+            DPE_ALLOC(c->vpair_k, C * Gv);
+            DPE_ALLOC(c->vpair_a, C * Gv);
+            DPE_ALLOC(c->vpair_v, C * Gv);
+            DPE_ALLOC(c->vhist, C * NBv);
+            DPE_ALLOC(c->vblk_hist, C * NBv * ((Gv + kSortBlock - 1) / kSortBlock));
+            DPE_ALLOC(c->vbucket_base, C * NBv);
+            DPE_ALLOC(c->vgroup_base, C * NBv + 1);
+            DPE_ALLOC(c->vhdr, c->vmax_groups * 4);
+            DPE_ALLOC(c->vent_j, c->vmax_groups * kBfNC);
+            DPE_ALLOC(c->vent_a, c->vmax_groups * kBfNC);
+            DPE_ALLOC(c->vn_groups, 1);
+        }
     }
     DPE_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->ep_pin), sizeof(EpochDev) * kPinSlots));
     DPE_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->sat_pin), sizeof(double) * c->sat_cap * kPinSlots));
@@ -246,7 +266,9 @@ int dpe_ctx_destroy(dpe_ctx* c) {
                     c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
-                    c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial, c->gathered};
+                    c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial, c->gathered,
+                    c->vbb, c->vpair_k, c->vpair_a, c->vpair_v, c->vhist, c->vblk_hist, c->vbucket_base, c->vgroup_base,
+                    c->vhdr, c->vent_j, c->vent_a, c->vn_groups};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->ep_pin) cudaFreeHost(c->ep_pin);
@@ -549,6 +571,16 @@ int dpe_score_vel(dpe_ctx* c, void* stream) {
     return launch_score_vel(c, (cudaStream_t)stream);
 }
 
+int dpe_score_vel_brute(dpe_ctx* c, void* stream) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DevGuard guard(c->cfg.device);
+    DPE_REQUIRE(c->Gv > 0 && c->have_vgrid, DPE_ESTATE, "score_vel_brute without a velocity grid");
+    DPE_REQUIRE(c->vbb, DPE_ESTATE, "context created without DPE_FLAG_BRUTE_VEL");
+    DPE_REQUIRE(c->have_prepare && c->have_corr, DPE_ESTATE, "score_vel_brute before replica_prepare / correlogram");
+    DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_vel_brute before the geometry part of epoch_set");
+    return launch_score_vel_brute(c, (cudaStream_t)stream);
+}
+
 int dpe_result_fetch(dpe_ctx* c, dpe_result* out, void* stream) {
     DPE_REQUIRE(c && out, DPE_EINVAL, "null argument");
     DevGuard guard(c->cfg.device);
@@ -582,6 +614,7 @@ static int upload_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, cons
     DPE_REQUIRE(score_mode != DPE_SCORE_BRUTE || (c->cfg.flags & DPE_FLAG_BRUTE_TILES), DPE_ESTATE,
                 "context created without DPE_FLAG_BRUTE_TILES");
     DPE_REQUIRE(!with_vel || (c->Gv > 0 && c->have_vgrid), DPE_ESTATE, "velocity manifold requested without a velocity grid");
+    DPE_REQUIRE(with_vel >= 0 && with_vel <= 2, DPE_EINVAL, "with_vel: 0 none, 1 lookup, 2 brute force");
     const bool root = !c->comm || c->rank == 0;
     const int C = ep->C;
     const size_t sat_bytes = sizeof(double) * 8 * (size_t)C * c->T;
@@ -663,7 +696,8 @@ static int compute_epoch(dpe_ctx* c, int score_mode, int est_mode, int with_vel,
     } else if ((rc = launch_estimate(c, est_mode, nullptr, 1, s))) {
         return rc;
     }
-    if (with_vel && (rc = dpe_score_vel(c, s))) return rc;
+    if (with_vel == 2) { if ((rc = dpe_score_vel_brute(c, s))) return rc; }
+    else if (with_vel && (rc = dpe_score_vel(c, s))) return rc;
     return DPE_OK;
 }
 
@@ -678,12 +712,16 @@ static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, con
 // (scoring path, estimator, velocity, channel count, communicator) and replayed; every kernel argument of the chain is a
 // context-owned buffer (the block is always copied into the packet in this mode), so a replay needs no update.
 static int launch_epoch_graph(dpe_ctx* c, int score_mode, int est_mode, int with_vel, cudaStream_t s) {
-    const uint64_t key = 1u | (uint64_t)score_mode << 1 | (uint64_t)est_mode << 2 | (uint64_t)(with_vel != 0) << 3 |
+    const uint64_t key = 1u | (uint64_t)score_mode << 1 | (uint64_t)est_mode << 2 | (uint64_t)(with_vel & 3) << 40 |
                          (uint64_t)c->epoch_C << 4 | (uint64_t)(c->comm != nullptr) << 12 | (uint64_t)c->pkt_used << 13;
     if (!c->graph_exec || c->graph_key != key) {
         if (c->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec); c->graph_exec = nullptr; }
         if (!c->brute_attr_set && score_mode == DPE_SCORE_BRUTE) {      // function attributes cannot be set while capturing
             int rc = brute_set_attributes(c);
+            if (rc) return rc;
+        }
+        if (!c->vel_attr_set && with_vel == 2) {
+            int rc = vel_brute_set_attributes(c);
             if (rc) return rc;
         }
         // a grid upload on another stream must be visible before the graph; inside the capture only captured events may be waited on

@@ -123,6 +123,11 @@ struct dpe_ctx {
     // velocity (section 8 f-1)
     double* vgrid; double* vscores; double2* carr;       // [Gv][4], [Gv], [C][NBd]
     long long* dc_sum; float2* bb; double2* vpart; double* vblk_partial;
+    // brute-force velocity manifold (DPE_FLAG_BRUTE_VEL): baseband plane with the chosen replica applied + pair lists
+    float2* vbb; int64_t vS_pad;
+    int16_t* vpair_k; float* vpair_a; float2* vpair_v;
+    int32_t *vhist, *vblk_hist, *vgroup_base, *vhdr, *vent_j, *vn_groups; int64_t* vbucket_base; float* vent_a;
+    int64_t vmax_groups; int vel_attr_set;
     int32_t Wd, NBd, n_fft; int have_vgrid;
     // state
     int have_block, have_epoch, have_prepare, have_corr, have_scores;
@@ -186,6 +191,13 @@ int launch_correlogram(dpe_ctx* c, cudaStream_t s);
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_sat_geo(dpe_ctx* c, cudaStream_t s);
 int launch_score_brute(dpe_ctx* c, int sat_mode, cudaStream_t s);
+struct SortLists {                 // one set of pair-sort work lists (position pairs, or velocity pairs)
+    int16_t* pair_k; float* pair_a; int32_t* blk_hist; int32_t* hist; int32_t* group_base; int64_t* bucket_base;
+    int32_t* n_groups; int32_t* hdr; int32_t* ent_j; float* ent_a; int64_t max_groups;
+};
+int launch_sort_tail(dpe_ctx* c, const SortLists& L, int64_t G, int W, int C, unsigned int* ticket, cudaStream_t s);
+int launch_score_vel_brute(dpe_ctx* c, cudaStream_t s);
+int vel_brute_set_attributes(dpe_ctx* c);
 int launch_brute_corr(dpe_ctx* c, cudaStream_t s);
 int brute_set_attributes(dpe_ctx* c);
 int launch_brute_score(dpe_ctx* c, cudaStream_t s);

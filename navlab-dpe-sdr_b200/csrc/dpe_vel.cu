@@ -113,6 +113,56 @@ k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ 
     if (lane == 0) carr[(size_t)c * NBd + l] = make_double2(re, im);
 }
 
+// arg-max over all block partials + BCM_MakeVelMeas (all threads of the last CTA)
+__device__ __forceinline__ void finish_velocity(const double* __restrict__ blk_partial, int n_blk, const EpochDev& e,
+                                                const double* __restrict__ vgrid_all, double* __restrict__ zval,
+                                                double* __restrict__ rval, double* __restrict__ res) {
+    double r[8];
+    reduce_all_partials(blk_partial, n_blk, r);
+    if (threadIdx.x == 0) {
+        const int64_t jm = (int64_t)r[6];
+        const double* g = vgrid_all + 4 * jm;
+        const double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
+                             e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
+                             e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
+        for (int k = 0; k < 4; ++k) { zval[4 + k] = z[k]; res[4 + k] = z[k]; }
+        for (int rr = 4; rr < 8; ++rr)
+            for (int k = 0; k < 8; ++k) rval[rr * 8 + k] = (rr == k) ? 1.0 : 0.0;
+        res[12] = r[5]; res[13] = (double)jm; res[14] = r[7];
+    }
+}
+
+// unit line of sight to the grid CENTRE + satellite velocity / clock drift of every channel (batchcorrmanifold.cu:1917-1921)
+__device__ __forceinline__ void vel_los(const EpochDev& e, const double* __restrict__ sat, int T, double (*los_s)[8]) {
+    if (threadIdx.x < e.C) {
+        const int c = threadIdx.x;
+        const double* s = sat + ((size_t)c * T + T / 2) * 8;
+        double los[3] = {s[0] - e.center[0], s[1] - e.center[1], s[2] - e.center[2]};
+        const double range = norm(3, los);
+        los_s[c][0] = los[0] / range; los_s[c][1] = los[1] / range; los_s[c][2] = los[2] / range;
+        los_s[c][3] = s[4]; los_s[c][4] = s[5]; los_s[c][5] = s[6]; los_s[c][6] = s[7];
+    }
+}
+
+// Doppler bin of one (velocity candidate, channel) pair (batchcorrmanifold.cu:1932-1950): window entry l (bin l - Wd
+// relative to 0 Hz), lerp weight of entry l + 1; false when the pair falls outside the window / the spectrum
+struct VelCand { double ex, ey, ez, pt; };
+__device__ __forceinline__ bool vel_bin(const EpochDev& e, const double* __restrict__ u, const VelCand& v, int c, double fs,
+                                        int n_fft, int Wd, int NBd, int64_t* l_out, double* wg, double* wf) {
+    const double rate = (u[0] * (v.ex - u[3])) + (u[1] * (v.ey - u[4])) + (u[2] * (v.ez - u[5]));
+    const double bc_fi = K_F_L1 * ((rate - v.pt) / K_C + u[6]) / e.doppler_sign;
+    const double fi0 = bc_fi - e.fi[c];
+    const double idx_base = (n_fft / fs) * fi0 + n_fft / 2.0;
+    const bool valid = (idx_base < n_fft) && (idx_base > 0);
+    const double idxo = idx_base + (double)((int64_t)n_fft * c);
+    const double f = floor(idxo), gg = floor(idxo + 1.0);
+    const int64_t l = (int64_t)f - (int64_t)n_fft * c - n_fft / 2 + Wd;
+    *l_out = l;
+    *wg = idxo - f;
+    *wf = gg - idxo;
+    return valid && l >= 0 && l + 1 < NBd;
+}
+
 // BCM_VelMeasML with the arg-max fused (batchcorrmanifold.cu:1896-1962); partial layout as the
 // position kernels' (sum s*v, sum s, max, argmax, out-of-window).
 __global__ void __launch_bounds__(kReduceBlock, 6)
@@ -127,14 +177,7 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
     __syncthreads();
     // the line of sight goes to the grid CENTRE (batchcorrmanifold.cu:1917-1921): one per channel, not per candidate
-    if (threadIdx.x < e.C) {
-        const int c = threadIdx.x;
-        const double* s = sat + ((size_t)c * T + T / 2) * 8;
-        double los[3] = {s[0] - e.center[0], s[1] - e.center[1], s[2] - e.center[2]};
-        const double range = norm(3, los);
-        los_s[c][0] = los[0] / range; los_s[c][1] = los[1] / range; los_s[c][2] = los[2] / range;
-        los_s[c][3] = s[4]; los_s[c][4] = s[5]; los_s[c][5] = s[6]; los_s[c][6] = s[7];
-    }
+    vel_los(e, sat, T, los_s);
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < Gv;
@@ -147,20 +190,12 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
         v.py = e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5];
         v.pz = e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6];
         v.pt = g[3] + e.center[7];
-        const double ex = v.px - K_OEDOT * e.center[1], ey = v.py + K_OEDOT * e.center[0], ez = v.pz;
+        const VelCand vc = {v.px - K_OEDOT * e.center[1], v.py + K_OEDOT * e.center[0], v.pz, v.pt};
         for (int c = 0; c < e.C; ++c) {
-            const double* u = los_s[c];                          // unit LOS to the centre + satellite velocity / drift
-            const double rate = (u[0] * (ex - u[3])) + (u[1] * (ey - u[4])) + (u[2] * (ez - u[5]));
-            const double bc_fi = K_F_L1 * ((rate - v.pt) / K_C + u[6]) / e.doppler_sign;
-            const double fi0 = bc_fi - e.fi[c];
-            const double idx_base = (n_fft / fs) * fi0 + n_fft / 2.0;
-            const bool valid = (idx_base < n_fft) && (idx_base > 0);
-            const double idxo = idx_base + (double)((int64_t)n_fft * c);
-            const double f = floor(idxo), gg = floor(idxo + 1.0);
-            const int64_t l = (int64_t)f - (int64_t)n_fft * c - n_fft / 2 + Wd;
-            if (valid && l >= 0 && l + 1 < NBd) {
+            int64_t l;
+            double wg, wf;
+            if (vel_bin(e, los_s[c], vc, c, fs, n_fft, Wd, NBd, &l, &wg, &wf)) {
                 const double2 lo = carr[(size_t)c * NBd + l], hi = carr[(size_t)c * NBd + l + 1];
-                const double wg = idxo - f, wf = gg - idxo;
                 score += mag_pow(hi.x * wg + lo.x * wf, hi.y * wg + lo.y * wf, lpower);
             } else {
                 ++oow;
@@ -170,21 +205,233 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
     }
     block_reduce_store(score, j, v, active, oow, blk_partial);
     // last CTA: arg-max over all candidates + BCM_MakeVelMeas (zVal[4:8], RVal rows 4-7, batchcorrmanifold.cu:2030-2068)
-    if (take_last_ticket(ticket)) {
-        double r[8];
-        reduce_all_partials(blk_partial, gridDim.x, r);
-        if (threadIdx.x == 0) {
-            const int64_t jm = (int64_t)r[6];
-            const double* g = vgrid_all + 4 * jm;
-            const double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
-                                 e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
-                                 e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
-            for (int k = 0; k < 4; ++k) { zval[4 + k] = z[k]; res[4 + k] = z[k]; }
-            for (int rr = 4; rr < 8; ++rr)
-                for (int k = 0; k < 8; ++k) rval[rr * 8 + k] = (rr == k) ? 1.0 : 0.0;
-            res[12] = r[5]; res[13] = (double)jm; res[14] = r[7];
+    if (take_last_ticket(ticket)) finish_velocity(blk_partial, gridDim.x, e, vgrid_all, zval, rval, res);
+}
+
+// =============================================================================================
+// Brute-force velocity manifold (SURVEY.md section 8 a', last sentence).  By linearity the reference's lerp of two
+// carrier-spectrum bins (batchcorrmanifold.cu:1950-1958) is a full-length correlation against a BLENDED carrier,
+//     v(j, c) = sum_n bb_c[n] * ( (1 - a) w_m[n] + a w_{m+1}[n] ),   w_m[n] = exp(-j 2 pi n m / N_c),
+// with the bin m and fraction a from the candidate's own Doppler geometry -- nothing is looked up, every
+// (velocity candidate, PRN) pair runs all S samples, the same way k_brute does on the position grid.
+//   k_vel_plane      bb = (x - mean) conj(carrier) * chosen replica, zero-padded to whole tiles
+//   k_vel_pair_bins  bins of every pair + per-CTA (PRN, bin) histograms; then the shared sort tail
+//                    (k_block_scan, k_scatter: dpe_brute.cu)
+//   k_brute_vel      one warp = 32 pairs of one (PRN, bin) bucket in registers, lanes stride the samples of a
+//                    shared 1024-sample tile; per candidate-sample 1 FFMA2 blends the carrier (alpha scalar,
+//                    the (d, w) pair shared by all candidates) and 2 FFMA2 do the complex MAC (blended re / im
+//                    as scalar operands, the sample pairs (re, im) and (-im, re) shared): 12 FLOP
+//   k_score_vpairs   sum_prn |v|^L, arg-max, BCM_MakeVelMeas
+// =============================================================================================
+constexpr int kVelTile = 1024;
+constexpr size_t kVelSmem = 2 * 2 * kVelTile * sizeof(float4);   // 64 KB: two buffers of (A, B)
+
+__global__ void DPE_SIDE256
+k_vel_plane(const float2* __restrict__ zw, const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
+            const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int64_t S_pad,
+            float2* __restrict__ vbb) {
+    const int c = blockIdx.y;
+    if (c >= ep->C) return;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= S_pad) return;
+    float2 v = make_float2(0.f, 0.f);
+    if (n < S) {
+        v = zw[(size_t)c * S + n];
+        float r = (float)rs[(size_t)c * S + n];
+        if (!no_flip[c] && n >= idx_next[c]) r = -r;
+        v.x *= r; v.y *= r;
+    }
+    vbb[(size_t)c * S_pad + n] = v;
+}
+
+__global__ void DPE_SIDE128
+k_vel_pair_bins(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
+                double fs, int n_fft, int Wd, int NBd, int T, int64_t Gv, int16_t* __restrict__ pair_k,
+                float* __restrict__ pair_a, float2* __restrict__ pair_v, int32_t* __restrict__ blk_hist) {
+    extern __shared__ int32_t hs[];
+    __shared__ EpochDev e;
+    __shared__ double los_s[DPE_MAX_CHAN][8];
+    for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
+    __syncthreads();
+    const int NB = 2 * Wd + 1, nbuck = e.C * NB;
+    for (int i = threadIdx.x; i < nbuck; i += blockDim.x) hs[i] = 0;
+    vel_los(e, sat, T, los_s);
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < Gv) {
+        const double* g = vgrid + 4 * j;
+        const double vx = e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4];
+        const double vy = e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5];
+        const double vz = e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6];
+        const VelCand vc = {vx - K_OEDOT * e.center[1], vy + K_OEDOT * e.center[0], vz, g[3] + e.center[7]};
+        for (int c = 0; c < e.C; ++c) {
+            int64_t l;
+            double wg, wf;
+            const bool ok = vel_bin(e, los_s[c], vc, c, fs, n_fft, Wd, NBd, &l, &wg, &wf);
+            pair_k[(size_t)c * Gv + j] = ok ? (int16_t)l : (int16_t)-1;
+            pair_a[(size_t)c * Gv + j] = (float)wg;
+            if (ok) atomicAdd(&hs[c * NB + (int)l], 1);
+            else pair_v[(size_t)c * Gv + j] = make_float2(__int_as_float(0x7fc00000), 0.f);   // NaN: "not scored"
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbuck; i += blockDim.x) blk_hist[(size_t)i * gridDim.x + blockIdx.x] = hs[i];
+}
+
+// One CTA slot = kBfWarps groups of ONE (PRN, Doppler bin) bucket, so the two carriers of the bucket -- and their
+// difference -- are the same for every pair of the CTA: the threads build them once per 1024-sample tile into shared
+// memory next to the samples (thread i: samples i, i+256, i+512, i+768 -- the first from the exact integer phase
+// n m mod N_c, the others by the exact 256-sample rotation), double-buffered, one __syncthreads per tile.  The inner
+// loop is then 2 LDS.128 per sample and lane against 96 FFMA2.
+//   A[n] = (w.re, w.im, d.re, d.im)   w = exp(-j theta_m[n]),  d = exp(-j theta_{m+1}[n]) - w
+//   B[n] = (x.re, x.im, -x.im, x.re)  the sample and j times the sample
+__global__ void __launch_bounds__(kBfWarps * 32, 1)
+k_brute_vel(const float2* __restrict__ vbb, int64_t S_pad, const int4* __restrict__ hdr, const int32_t* __restrict__ ent_j,
+            const float* __restrict__ ent_a, const int32_t* __restrict__ n_groups, float2* __restrict__ pair_v, int64_t Gv,
+            int Wd, int n_fft) {
+    extern __shared__ __align__(16) float4 vsm[];              // [2 buffers][A | B][kVelTile]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slots = *n_groups / kBfWarps;
+    const unsigned mask = (unsigned)n_fft - 1u;                 // n_fft is a power of two
+    const float scale = 2.0f / (float)n_fft;
+    const int ntiles = (int)(S_pad / kVelTile);
+    constexpr int kPer = kVelTile / (kBfWarps * 32);            // samples per thread and tile
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        const int g = slot * kBfWarps + warp;
+        const int4 h = hdr[g];                               // {channel, window entry, valid pairs}: one bucket per slot
+        const int c = h.x, n_valid = h.z;
+        const int m = h.y - Wd;                              // bin relative to 0 Hz; the pair blends bins m and m + 1
+        const float a_mine = (lane < n_valid) ? ent_a[(size_t)g * kBfNC + lane] : 0.f;
+        float al[kBfNC];
+#pragma unroll
+        for (int j = 0; j < kBfNC; ++j) al[j] = __shfl_sync(0xffffffffu, a_mine, j);
+        float2 acc[kBfNC];
+#pragma unroll
+        for (int j = 0; j < kBfNC; ++j) acc[j] = make_float2(0.f, 0.f);
+        float r0s, r0c, r1s, r1c;                            // rotation of 256 samples for bins m, m + 1
+        sincospif((float)((256u * (unsigned)m) & mask) * scale, &r0s, &r0c);
+        sincospif((float)((256u * (unsigned)(m + 1)) & mask) * scale, &r1s, &r1c);
+        const float2* __restrict__ src = vbb + (size_t)c * S_pad;
+        auto stage_tile = [&](int t, int buf) {
+            float4* A = vsm + (size_t)buf * 2 * kVelTile;
+            float4* B = A + kVelTile;
+            const unsigned n = (unsigned)(t * kVelTile) + threadIdx.x;
+            float2 x[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) x[k] = __ldg(src + (size_t)t * kVelTile + threadIdx.x + 256 * k);
+            float s0, c0, s1, c1;                            // exact from the integer phase
+            sincospif((float)((n * (unsigned)m) & mask) * scale, &s0, &c0);
+            sincospif((float)((n * (unsigned)(m + 1)) & mask) * scale, &s1, &c1);
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                A[threadIdx.x + 256 * k] = make_float4(c0, -s0, c1 - c0, s0 - s1);
+                B[threadIdx.x + 256 * k] = make_float4(x[k].x, x[k].y, -x[k].y, x[k].x);
+                const float nc0 = c0 * r0c - s0 * r0s, ns0 = s0 * r0c + c0 * r0s;
+                const float nc1 = c1 * r1c - s1 * r1s, ns1 = s1 * r1c + c1 * r1s;
+                c0 = nc0; s0 = ns0; c1 = nc1; s1 = ns1;
+            }
+        };
+        __syncthreads();                                     // the previous slot is done with both buffers
+        stage_tile(0, 0);
+        __syncthreads();
+        for (int t = 0; t < ntiles; ++t) {
+            if (t + 1 < ntiles) stage_tile(t + 1, (t + 1) & 1);
+            if (n_valid > 0) {
+                const float4* A = vsm + (size_t)(t & 1) * 2 * kVelTile + lane;
+                const float4* B = A + kVelTile;
+#pragma unroll 2
+                for (int i = 0; i < kVelTile / 32; ++i) {
+                    const float4 wd = A[32 * i], xx = B[32 * i];
+                    const float2 w = make_float2(wd.x, wd.y), d = make_float2(wd.z, wd.w);
+                    const float2 xa = make_float2(xx.x, xx.y), xb = make_float2(xx.z, xx.w);
+#pragma unroll
+                    for (int j = 0; j < kBfNC; ++j) {
+                        const float2 b = __ffma2_rn(make_float2(al[j], al[j]), d, w);   // w + alpha d
+                        acc[j] = __ffma2_rn(make_float2(b.x, b.x), xa, acc[j]);          // x * b, real part of b
+                        acc[j] = __ffma2_rn(make_float2(b.y, b.y), xb, acc[j]);          // ... imaginary part
+                    }
+                }
+            }
+            __syncthreads();                                 // tile t + 1 is staged, tile t is free
+        }
+        // lane partials -> one candidate per lane (halving butterfly, as in k_brute)
+#pragma unroll
+        for (int o = 16, nn = kBfNC / 2; o > 0; o >>= 1, nn >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < nn; ++j) {
+                const float2 keep = up ? acc[j + nn] : acc[j];
+                const float2 send = up ? acc[j] : acc[j + nn];
+                acc[j].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, o);
+                acc[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, o);
+            }
+        }
+        if (lane < n_valid) {
+            const int64_t j = ent_j[(size_t)g * kBfNC + lane];
+            pair_v[(size_t)c * Gv + j] = acc[0];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kReduceBlock, 6)
+k_score_vpairs(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const float2* __restrict__ pair_v,
+               int lpower, int64_t Gv, double* __restrict__ vscores, double* __restrict__ blk_partial,
+               unsigned int* __restrict__ ticket, double* __restrict__ zval, double* __restrict__ rval,
+               double* __restrict__ res) {
+    const EpochDev& e = *ep;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < Gv;
+    double score = 0.0;
+    int oow = 0;
+    if (active) {
+        for (int c = 0; c < e.C; ++c) {
+            const float2 v = __ldcs(&pair_v[(size_t)c * Gv + j]);
+            if (v.x == v.x) score += mag_pow((double)v.x, (double)v.y, lpower);
+            else ++oow;
+        }
+        vscores[j] = score;
+    }
+    double v5[5] = {0, 0, 0, 0, active ? score : 0.0};
+    block_reduce_store_vals<1>(v5, active ? score : -1.0, active ? (double)j : 9.0e18, (double)oow, blk_partial);
+    if (take_last_ticket(ticket)) finish_velocity(blk_partial, gridDim.x, e, vgrid, zval, rval, res);
+}
+
+int vel_brute_set_attributes(dpe_ctx* c) {   // per context (device); not while a stream capture is open
+    DPE_CUDA(cudaFuncSetAttribute(k_brute_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVelSmem));
+    c->vel_attr_set = 1;
+    return DPE_OK;
+}
+
+int launch_score_vel_brute(dpe_ctx* c, cudaStream_t s) {
+    const int S = (int)c->S, C = c->epoch_C;
+    const int NB = 2 * c->Wd + 1, nbuck = C * NB;
+    prof_begin(c, DPE_STAGE_VELOCITY, s);
+    dim3 gp((unsigned)((c->vS_pad + 255) / 256), C);
+    k_vel_plane<<<gp, 256, 0, s>>>(c->bb, c->rs, c->idx_next, c->no_flip, c->ep, S, c->vS_pad, c->vbb);
+    c->launches++;
+    const int nblk = (int)((c->Gv + kSortBlock - 1) / kSortBlock);
+    k_vel_pair_bins<<<nblk, kSortBlock, sizeof(int32_t) * nbuck, s>>>(c->vgrid, c->ep, c->sat, c->cfg.fs, c->n_fft, c->Wd,
+                                                                     c->NBd, c->T, c->Gv, c->vpair_k, c->vpair_a, c->vpair_v,
+                                                                     c->vblk_hist);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    SortLists L = {c->vpair_k, c->vpair_a, c->vblk_hist, c->vhist, c->vgroup_base, c->vbucket_base, c->vn_groups, c->vhdr,
+                   c->vent_j, c->vent_a, c->vmax_groups};
+    int rc = launch_sort_tail(c, L, c->Gv, c->Wd, C, c->ticket + 2, s);
+    if (rc) return rc;
+    if (!c->vel_attr_set) { int rc2 = vel_brute_set_attributes(c); if (rc2) return rc2; }
+    k_brute_vel<<<c->sm_count, kBfWarps * 32, kVelSmem, s>>>(c->vbb, c->vS_pad, reinterpret_cast<const int4*>(c->vhdr), c->vent_j,
+                                                      c->vent_a, c->vn_groups, c->vpair_v, c->Gv, c->Wd, c->n_fft);
+    c->launches++;
+    DPE_CUDA(cudaGetLastError());
+    const int nb2 = (int)((c->Gv + kReduceBlock - 1) / kReduceBlock);
+    k_score_vpairs<<<nb2, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->vpair_v, c->cfg.lpower, c->Gv, c->vscores,
+                                                c->vblk_partial, c->ticket, c->zval, c->rval, c->result);
+    c->launches++;
+    prof_end(c, s);
+    DPE_CUDA(cudaGetLastError());
+    return DPE_OK;
 }
 
 // DC sum of the block; runs before k_prepare when a velocity grid exists (k_prepare then also
@@ -220,6 +467,10 @@ int kernel_attr_vel(const char* name, cudaFuncAttributes* a) {
     DPE_KATTR("k_carr_partial", k_carr_partial);
     DPE_KATTR("k_carr_finalize", k_carr_finalize);
     DPE_KATTR("k_score_vel", k_score_vel);
+    DPE_KATTR("k_brute_vel", k_brute_vel);
+    DPE_KATTR("k_vel_pair_bins", k_vel_pair_bins);
+    DPE_KATTR("k_vel_plane", k_vel_plane);
+    DPE_KATTR("k_score_vpairs", k_score_vpairs);
     return 0;
 }
 

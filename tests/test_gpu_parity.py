@@ -339,6 +339,98 @@ def test_velocity_manifold_matches_oracle(capi, fs, prns):
     ctx.close()
 
 
+# ---- brute-force velocity manifold (SURVEY.md 8 a', last sentence: the blended-carrier identity) ----
+@pytest.mark.parametrize("fs,prns", [(2.5e6, synth.PRNS_8), (10.0e6, synth.PRNS_12)])
+def test_brute_force_velocity_manifold_matches_oracle_and_lookup(capi, fs, prns):
+    """Every (velocity candidate, PRN) pair correlates the whole block against its own blended carrier
+    (batchcorrmanifold.cu:1950-1958 by linearity): scores <= 1e-5 of the oracle's and of the lookup kernel's,
+    identical arg-max and fix; the one-call and the CUDA-graph (submit / collect) paths agree bit for bit."""
+    sc = H.scenario(fs, prns)
+    grid, tg = synth.uniform_grid(5, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(9, (0.5, 0.5, 0.5, 0.25))
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[4:] += (1.0, -0.5, 0.5, 0.3)
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    C, S, Wd = len(prns), ep["S"], 64
+    bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"], want_carrier=True)
+    ref = orc.vel_meas_ml(bcs["carr_scores"], vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"], ep["time_dim"],
+                          ep["fi"], ep["doppler_sign"], ep["fs"], bcs["n_fft"])
+    ctx = capi.Context(fs=fs, S=S, max_chan=C, G=grid.shape[0], time_dim=len(tg), lag_halfwidth=16,
+                       Gv=vgrid.shape[0], dopp_halfwidth=Wd, flags=capi.FLAG_BRUTE_VEL)
+    ctx.grid_set(grid)
+    ctx.vel_grid_set(vgrid)
+    r_look = ctx.epoch_run(iq, ep, with_vel=1)
+    vs_look = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    r_brute = ctx.epoch_run(iq, ep, with_vel=2)
+    vs = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    assert np.max(np.abs(vs - ref["scores"]) / ref["scores"]) < SCORE_RTOL
+    assert np.max(np.abs(vs - vs_look) / vs_look) < SCORE_RTOL
+    assert r_brute.vel_argmax == ref["argmax"] == r_look.vel_argmax and r_brute.vel_out_of_window == 0
+    assert np.max(np.abs(np.array(r_brute.z[4:8]) - ref["z"])) < 1e-9
+    assert np.array_equal(np.array(r_brute.z[:4]), np.array(r_look.z[:4]))      # the position fix is untouched
+    rval = ctx.copy_out(capi.PTR_RVAL, np.float64, 64).reshape(8, 8)
+    assert np.array_equal(rval, np.eye(8))
+    r_graph = ctx.epoch_run_dist(iq, ep, with_vel=2)
+    vs_graph = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    assert np.array_equal(vs_graph, vs) and r_graph.vel_argmax == r_brute.vel_argmax
+    assert r_graph.vel_max_score == r_brute.vel_max_score
+    ctx.close()
+
+
+def test_brute_force_velocity_wide_grid_ragged_buckets_and_window_edge(capi):
+    """13^4 velocity candidates spread over many Doppler bins (ragged (PRN, bin) buckets, several slots per
+    bucket) with a Doppler window so narrow that part of the grid falls outside: those pairs are counted, not
+    scored, exactly as the lookup kernel counts them."""
+    fs, prns = 2.5e6, synth.PRNS_8
+    sc = H.scenario(fs, prns)
+    grid, tg = synth.uniform_grid(3, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(13, (1.1, 0.9, 1.3, 0.7))
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[4:] += (2.0, -1.5, 0.7, -0.9)
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    C, S, Wd = len(prns), ep["S"], 6
+    ctx = capi.Context(fs=fs, S=S, max_chan=C, G=grid.shape[0], time_dim=len(tg), lag_halfwidth=16,
+                       Gv=vgrid.shape[0], dopp_halfwidth=Wd, flags=capi.FLAG_BRUTE_VEL)
+    ctx.grid_set(grid)
+    ctx.vel_grid_set(vgrid)
+    r_look = ctx.epoch_run(iq, ep, with_vel=1)
+    vs_look = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    r_brute = ctx.epoch_run(iq, ep, with_vel=2)
+    vs = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    assert 0 < r_look.vel_out_of_window < C * vgrid.shape[0]
+    assert r_brute.vel_out_of_window == r_look.vel_out_of_window
+    ok = vs_look > 0
+    assert np.array_equal(ok, vs > 0)
+    assert np.max(np.abs(vs[ok] - vs_look[ok]) / vs_look[ok]) < SCORE_RTOL
+    assert r_brute.vel_argmax == r_look.vel_argmax
+    assert np.array_equal(np.array(r_brute.z[4:8]), np.array(r_look.z[4:8]))
+    bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"], want_carrier=True)
+    ref = orc.vel_meas_ml(bcs["carr_scores"], vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"], ep["time_dim"],
+                          ep["fi"], ep["doppler_sign"], ep["fs"], bcs["n_fft"])
+    n_fft = bcs["n_fft"]
+    l = ref["f_idx"] - n_fft * np.arange(C)[None, :] - n_fft // 2 + Wd
+    pair_in = ref["valid"] & (l >= 0) & (l + 1 < 2 * Wd + 2)
+    assert r_look.vel_out_of_window == int((~pair_in).sum())
+    inside = pair_in.all(axis=1)                                   # candidates with every PRN inside the narrow window
+    assert inside.sum() > vgrid.shape[0] // 20
+    assert np.max(np.abs(vs[inside] - ref["scores"][inside]) / ref["scores"][inside]) < SCORE_RTOL
+    ctx.close()
+
+
+def test_brute_force_velocity_needs_its_flag(capi):
+    ctx = capi.Context(fs=2.5e6, S=5000, max_chan=2, G=16, time_dim=1, lag_halfwidth=16, Gv=16, dopp_halfwidth=8)
+    ctx.grid_set(np.zeros((16, 4)))
+    ctx.vel_grid_set(np.zeros((16, 4)))
+    with pytest.raises(capi.DpeError) as e:
+        ctx.score_vel_brute()
+    assert e.value.code == capi.DPE_ESTATE
+    ctx.close()
+
+
 def test_velocity_needs_its_grid(capi):
     ctx = _ctx(capi, 5000, 2, 16, 1, 2.5e6)
     with pytest.raises(capi.DpeError) as e:
