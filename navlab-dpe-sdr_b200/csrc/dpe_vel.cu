@@ -313,46 +313,56 @@ k_brute_vel(const float2* __restrict__ vbb, int64_t S_pad, const int4* __restric
         sincospif((float)((256u * (unsigned)m) & mask) * scale, &r0s, &r0c);
         sincospif((float)((256u * (unsigned)(m + 1)) & mask) * scale, &r1s, &r1c);
         const float2* __restrict__ src = vbb + (size_t)c * S_pad;
-        auto stage_tile = [&](int t, int buf) {
+        // staging of tile t, in two parts so that the global-load latency hides under the FFMA2 stream of the tile
+        // before: the samples are loaded before the first half of tile t - 1 is computed, the carriers are built and
+        // everything is stored between its two halves
+        float2 xr[kPer];
+        auto stage_load = [&](int t) {
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) xr[k] = __ldg(src + (size_t)t * kVelTile + threadIdx.x + 256 * k);
+        };
+        auto stage_store = [&](int t, int buf) {
             float4* A = vsm + (size_t)buf * 2 * kVelTile;
             float4* B = A + kVelTile;
             const unsigned n = (unsigned)(t * kVelTile) + threadIdx.x;
-            float2 x[kPer];
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) x[k] = __ldg(src + (size_t)t * kVelTile + threadIdx.x + 256 * k);
             float s0, c0, s1, c1;                            // exact from the integer phase
             sincospif((float)((n * (unsigned)m) & mask) * scale, &s0, &c0);
             sincospif((float)((n * (unsigned)(m + 1)) & mask) * scale, &s1, &c1);
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
                 A[threadIdx.x + 256 * k] = make_float4(c0, -s0, c1 - c0, s0 - s1);
-                B[threadIdx.x + 256 * k] = make_float4(x[k].x, x[k].y, -x[k].y, x[k].x);
+                B[threadIdx.x + 256 * k] = make_float4(xr[k].x, xr[k].y, -xr[k].y, xr[k].x);
                 const float nc0 = c0 * r0c - s0 * r0s, ns0 = s0 * r0c + c0 * r0s;
                 const float nc1 = c1 * r1c - s1 * r1s, ns1 = s1 * r1c + c1 * r1s;
                 c0 = nc0; s0 = ns0; c1 = nc1; s1 = ns1;
             }
         };
-        __syncthreads();                                     // the previous slot is done with both buffers
-        stage_tile(0, 0);
-        __syncthreads();
-        for (int t = 0; t < ntiles; ++t) {
-            if (t + 1 < ntiles) stage_tile(t + 1, (t + 1) & 1);
-            if (n_valid > 0) {
-                const float4* A = vsm + (size_t)(t & 1) * 2 * kVelTile + lane;
-                const float4* B = A + kVelTile;
-#pragma unroll 2
-                for (int i = 0; i < kVelTile / 32; ++i) {
-                    const float4 wd = A[32 * i], xx = B[32 * i];
-                    const float2 w = make_float2(wd.x, wd.y), d = make_float2(wd.z, wd.w);
-                    const float2 xa = make_float2(xx.x, xx.y), xb = make_float2(xx.z, xx.w);
+        auto compute_half = [&](int t, int half) {
+            const float4* A = vsm + (size_t)(t & 1) * 2 * kVelTile + lane + half * (kVelTile / 2);
+            const float4* B = A + kVelTile;
+#pragma unroll 4
+            for (int i = 0; i < kVelTile / 64; ++i) {
+                const float4 wd = A[32 * i], xx = B[32 * i];
+                const float2 w = make_float2(wd.x, wd.y), d = make_float2(wd.z, wd.w);
+                const float2 xa = make_float2(xx.x, xx.y), xb = make_float2(xx.z, xx.w);
 #pragma unroll
-                    for (int j = 0; j < kBfNC; ++j) {
-                        const float2 b = __ffma2_rn(make_float2(al[j], al[j]), d, w);   // w + alpha d
-                        acc[j] = __ffma2_rn(make_float2(b.x, b.x), xa, acc[j]);          // x * b, real part of b
-                        acc[j] = __ffma2_rn(make_float2(b.y, b.y), xb, acc[j]);          // ... imaginary part
-                    }
+                for (int j = 0; j < kBfNC; ++j) {
+                    const float2 b = __ffma2_rn(make_float2(al[j], al[j]), d, w);   // w + alpha d
+                    acc[j] = __ffma2_rn(make_float2(b.x, b.x), xa, acc[j]);          // x * b, real part of b
+                    acc[j] = __ffma2_rn(make_float2(b.y, b.y), xb, acc[j]);          // ... imaginary part
                 }
             }
+        };
+        __syncthreads();                                     // the previous slot is done with both buffers
+        stage_load(0);
+        stage_store(0, 0);
+        __syncthreads();
+        for (int t = 0; t < ntiles; ++t) {
+            const bool more = t + 1 < ntiles;
+            if (more) stage_load(t + 1);
+            if (n_valid > 0) compute_half(t, 0);
+            if (more) stage_store(t + 1, (t + 1) & 1);
+            if (n_valid > 0) compute_half(t, 1);
             __syncthreads();                                 // tile t + 1 is staged, tile t is free
         }
         // lane partials -> one candidate per lane (halving butterfly, as in k_brute)
