@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kReduceBlock, 6)
 k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
               const float2* __restrict__ pair_v, int lpower,
               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
-              unsigned int* __restrict__ ticket, double* __restrict__ partial) {
+              unsigned int* __restrict__ ticket, double* __restrict__ partial, const FoldEst fold) {
     const EpochDev& e = *ep;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < G;
@@ -447,7 +447,7 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         __stcs(&scores[j], score);
     }
     block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
-    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
+    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial, fold);
 }
 
 size_t brute_smem_bytes(int) {
@@ -528,13 +528,14 @@ int launch_brute_corr(dpe_ctx* c, cudaStream_t s) {
 
 int launch_brute_score(dpe_ctx* c, cudaStream_t s) {
     prof_begin(c, DPE_STAGE_BRUTE_SCORE, s);
+    const FoldEst fold = {c->fold_est_mode, c->zval, c->rval, c->result};
     const int nblk = (int)((c->G + kReduceBlock - 1) / kReduceBlock);
     if (c->want_sums)
         k_score_pairs<1><<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_v, c->cfg.lpower, c->G,
-                                                       c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
+                                                       c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, fold);
     else
         k_score_pairs<0><<<nblk, kReduceBlock, 0, s>>>(c->grid, c->ep, c->pair_v, c->cfg.lpower, c->G,
-                                                       c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial);
+                                                       c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, fold);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;

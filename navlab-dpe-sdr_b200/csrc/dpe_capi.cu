@@ -154,6 +154,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     c->T = cfg->time_dim > 0 ? cfg->time_dim : 1;
     c->nranks = 1;
     c->want_sums = 1;
+    c->fold_est_mode = -1;
     const size_t C = c->maxC, S = c->S, G = c->G;
 
     // epoch packet {iq | EpochDev | sat}: device copy + page-locked staging copy
@@ -212,7 +213,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->vgrid, (size_t)cfg->Gv * 4);
         DPE_ALLOC(c->vscores, (size_t)cfg->Gv);
         DPE_ALLOC(c->carr, C * c->NBd);
-        DPE_ALLOC(c->dc_sum, 2);
+        DPE_ALLOC(c->dc_part, 2 * c->nchunk);
         DPE_ALLOC(c->bb, C * S);
         DPE_ALLOC(c->vpart, C * c->nchunk * c->NBd);
         DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
@@ -245,8 +246,16 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    if (cfg->Gv > 0) {
+        DPE_CREATE_CUDA(cudaStreamCreateWithFlags(&c->vel_stream, cudaStreamNonBlocking));
+        DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        DPE_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_vel, cudaEventDisableTiming));
+        const char* vf = getenv("DPE_VEL_FORK");
+        c->vel_fork = !(vf && vf[0] == '0');
+    }
     { const char* ng = getenv("DPE_NO_GRAPH"); c->use_graph = !(ng && ng[0] == '1'); }
     { const char* sp = getenv("DPE_BRUTE_SKIP_PAD"); c->brute_skip_pad = !(sp && sp[0] == '0'); }
+    { const char* cd = getenv("DPE_CARR_DIRECT"); c->carr_direct = (cd && cd[0] == '1'); }
     { const char* lk = getenv("DPE_LK_CAND"); const int v = lk ? atoi(lk) : 0; c->lk_cand_forced = (v == 3 || v == 4 || v == 6) ? v : 0; }
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
@@ -266,7 +275,7 @@ int dpe_ctx_destroy(dpe_ctx* c) {
                     c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
-                    c->vgrid, c->vscores, c->carr, c->dc_sum, c->bb, c->vpart, c->vblk_partial, c->gathered,
+                    c->vgrid, c->vscores, c->carr, c->dc_part, c->bb, c->vpart, c->vblk_partial, c->gathered,
                     c->vbb, c->vpair_k, c->vpair_a, c->vpair_v, c->vhist, c->vblk_hist, c->vbucket_base, c->vgroup_base,
                     c->vhdr, c->vent_j, c->vent_a, c->vn_groups};
     for (void* p : ptrs)
@@ -282,6 +291,9 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     if (c->ev_sort) cudaEventDestroy(c->ev_sort);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->vel_stream) cudaStreamDestroy(c->vel_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_vel) cudaEventDestroy(c->ev_vel);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec);
     if (c->prof_ev) {
@@ -312,6 +324,7 @@ int dpe_grid_set(dpe_ctx* c, const double* enu_dt, int64_t G, void* stream) {
 int dpe_vel_grid_set(dpe_ctx* c, const double* venu_ddt, int64_t Gv, void* stream) {
     DPE_REQUIRE(c && venu_ddt, DPE_EINVAL, "dpe_vel_grid_set: null argument");
     DevGuard guard(c->cfg.device);
+    c->fork_valid = 0;
     DPE_REQUIRE(c->Gv > 0, DPE_ESTATE, "context created without a velocity grid (cfg.Gv = 0)");
     DPE_REQUIRE(Gv == c->Gv, DPE_EINVAL, "dpe_vel_grid_set: Gv=%lld, context holds %lld", (long long)Gv,
                 (long long)c->Gv);
@@ -327,6 +340,7 @@ int dpe_vel_grid_set(dpe_ctx* c, const double* venu_ddt, int64_t Gv, void* strea
 int dpe_block_stage(dpe_ctx* c, const int16_t* iq, int64_t S, void* stream) {
     DPE_REQUIRE(c && iq, DPE_EINVAL, "dpe_block_stage: null argument");
     DevGuard guard(c->cfg.device);
+    c->fork_valid = 0;
     DPE_REQUIRE(S == c->S, DPE_EINVAL, "block of %lld samples, context built for %lld", (long long)S,
                 (long long)c->S);
     cudaPointerAttributes at;
@@ -349,6 +363,7 @@ int dpe_epoch_set_part(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states
                        void* stream) {
     DPE_REQUIRE(c && ep, DPE_EINVAL, "dpe_epoch_set: null argument");
     DevGuard guard(c->cfg.device);
+    c->fork_valid = 0;
     DPE_REQUIRE(parts && !(parts & ~(DPE_PART_CHANNELS | DPE_PART_GEOMETRY)), DPE_EINVAL, "bad parts mask %u", parts);
     DPE_REQUIRE(ep->C >= 1 && ep->C <= c->maxC, DPE_EINVAL, "C=%d, context built for <= %d", ep->C, c->maxC);
     DPE_REQUIRE(!(parts & DPE_PART_GEOMETRY) || sat_states, DPE_EINVAL, "geometry part without sat_states");
@@ -475,6 +490,7 @@ int dpe_epoch_set(dpe_ctx* c, const dpe_epoch* ep, const double* sat_states, voi
 int dpe_replica_prepare(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
     DevGuard guard(c->cfg.device);
+    c->fork_valid = 0;
     DPE_REQUIRE(c->have_block && (c->have_epoch & DPE_PART_CHANNELS), DPE_ESTATE,
                 "replica_prepare before block_stage / the channel part of epoch_set");
     int rc = launch_prepare(c, (cudaStream_t)stream);
@@ -488,6 +504,7 @@ int dpe_replica_prepare(dpe_ctx* c, void* stream) {
 int dpe_correlogram(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
     DevGuard guard(c->cfg.device);
+    c->fork_valid = 0;
     DPE_REQUIRE(c->have_prepare, DPE_ESTATE, "correlogram before replica_prepare");
     int rc = launch_correlogram(c, (cudaStream_t)stream);
     if (rc) return rc;
@@ -499,6 +516,7 @@ int dpe_correlogram(dpe_ctx* c, void* stream) {
 int dpe_code_scores_set(dpe_ctx* c, const double* cs, int C, void* stream) {
     DPE_REQUIRE(c && cs, DPE_EINVAL, "null argument");
     DevGuard guard(c->cfg.device);
+    c->fork_valid = 0;
     DPE_REQUIRE(c->have_epoch, DPE_ESTATE, "code_scores_set before epoch_set");
     DPE_REQUIRE(C == c->epoch_C, DPE_EINVAL, "C=%d, epoch has %d channels", C, c->epoch_C);
     DPE_CUDA(cudaMemcpyAsync(c->cs, cs, sizeof(double2) * (size_t)C * c->NL, cudaMemcpyDefault,
@@ -515,6 +533,10 @@ int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
     DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_pos before the geometry part of epoch_set");
     DPE_REQUIRE(sat_mode == DPE_SAT_MIDDLE || sat_mode == DPE_SAT_PER_TIME, DPE_EINVAL, "bad sat_mode");
     int rc;
+    if (c->vel_stream && c->vel_fork) {           // everything the velocity manifold reads is in place at this point of the stream
+        DPE_CUDA(cudaEventRecord(c->ev_fork, (cudaStream_t)stream));
+        c->fork_valid = 1;
+    }
     if (score_mode == DPE_SCORE_LOOKUP) {
         rc = launch_score_lookup(c, sat_mode, (cudaStream_t)stream);
     } else if (score_mode == DPE_SCORE_BRUTE) {
@@ -568,7 +590,15 @@ int dpe_score_vel(dpe_ctx* c, void* stream) {
     DPE_REQUIRE(c->Gv > 0 && c->have_vgrid, DPE_ESTATE, "score_vel without a velocity grid");
     DPE_REQUIRE(c->have_prepare && c->have_corr, DPE_ESTATE, "score_vel before replica_prepare / correlogram");
     DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_vel before the geometry part of epoch_set");
-    return launch_score_vel(c, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c->fork_valid) return launch_score_vel(c, s);
+    // beside the position scoring that dpe_score_pos put on `s`: fork behind the point it recorded, join `s` again
+    c->fork_valid = 0;
+    DPE_CUDA(cudaStreamWaitEvent(c->vel_stream, c->ev_fork, 0));
+    int rc = launch_score_vel(c, c->vel_stream);
+    DPE_CUDA(cudaEventRecord(c->ev_vel, c->vel_stream));
+    DPE_CUDA(cudaStreamWaitEvent(s, c->ev_vel, 0));
+    return rc;
 }
 
 int dpe_score_vel_brute(dpe_ctx* c, void* stream) {
@@ -682,19 +712,20 @@ static int compute_epoch(dpe_ctx* c, int score_mode, int est_mode, int with_vel,
     c->have_epoch = DPE_PART_CHANNELS | DPE_PART_GEOMETRY;
     c->have_prepare = c->have_corr = c->have_scores = 0;
     c->sort_valid = 0;
+    c->fork_valid = 0;
     const int sat_mode = (est_mode == DPE_EST_WEIGHTED) ? DPE_SAT_PER_TIME : DPE_SAT_MIDDLE;
     if (score_mode == DPE_SCORE_BRUTE && (rc = dpe_brute_presort(c, sat_mode, c->aux_stream))) return rc;
     if ((rc = dpe_replica_prepare(c, s))) return rc;
     if ((rc = dpe_correlogram(c, s))) return rc;
     c->want_sums = (est_mode == DPE_EST_WEIGHTED);     // an arg-max epoch needs no per-candidate sum s*x
+    c->fold_est_mode = c->comm ? -1 : est_mode;        // one GPU: the estimate is the tail of the scoring kernel
     rc = dpe_score_pos(c, score_mode, sat_mode, s);
     c->want_sums = 1;
+    c->fold_est_mode = -1;
     if (rc) return rc;
     if (c->comm) {
         if ((rc = comm_allgather(c, c->partial, c->gathered, kPartialLen, s))) return rc;
         if ((rc = launch_estimate(c, est_mode, c->gathered, c->nranks, s))) return rc;
-    } else if ((rc = launch_estimate(c, est_mode, nullptr, 1, s))) {
-        return rc;
     }
     if (with_vel == 2) { if ((rc = dpe_score_vel_brute(c, s))) return rc; }
     else if (with_vel && (rc = dpe_score_vel(c, s))) return rc;

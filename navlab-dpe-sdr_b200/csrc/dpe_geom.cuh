@@ -130,8 +130,19 @@ __device__ __forceinline__ Bin make_bin(double idx_base, int c, int S, int W) {
     return b;
 }
 
+// sqrt(s) from the FP32 reciprocal square root (MUFU.RSQ) and ONE FP64 Newton step: the seed is good to 1.2e-7, the
+// step squares that -- 2e-14 relative, against 1.1e-16 for the IEEE sqrt (7 more FP64 instructions and a branch per
+// pair on a part whose FP64 pipe is what bounds the scoring kernels).  Outside the FP32 range: the IEEE sqrt.
+__device__ __forceinline__ double sqrt_newton(double s) {
+    const float sf = (float)s;
+    if (__builtin_expect(!(sf > 1.0e-30f && sf < 1.0e37f), 0)) return sqrt(s);
+    const double y = (double)rsqrtf(sf);
+    const double m = s * y;
+    return fma(0.5 * y, fma(-m, m, s), m);
+}
+
 __device__ __forceinline__ double mag_pow(double re, double im, int L) {
-    const double m = sqrt(re * re + im * im);
+    const double m = sqrt_newton(re * re + im * im);
     if (L == 1) return m;
     if (L == 2) return m * m;
     return pow(m, (double)L);
@@ -181,7 +192,7 @@ __device__ __forceinline__ void block_reduce_store_vals(double (&v)[5], double m
         double r[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) r[k] = sh[0][k];
-        for (int w = 1; w < kReduceBlock / 32; ++w) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) r[k] += sh[w][k];
             r[7] += sh[w][7];
@@ -215,11 +226,12 @@ __device__ __forceinline__ bool take_last_ticket(unsigned int* counter) {
     return s_last;
 }
 
-// all kReduceBlock threads of one CTA: r[0..4] sums, r[5]/r[6] max / arg-max (lowest index on ties), r[7] sum;
+// all threads of one CTA (a power of two, <= kReduceBlock): r[0..4] sums, r[5]/r[6] max / arg-max (lowest index on ties), r[7] sum;
 // valid in thread 0 on return
 __device__ __forceinline__ void reduce_all_partials(const double* __restrict__ blk, int n_blk, double (&r)[8]) {
     __shared__ double shr[kReduceBlock][8];
     r[0] = r[1] = r[2] = r[3] = r[4] = 0.0; r[5] = -1.0; r[6] = 9.0e18; r[7] = 0.0;
+#pragma unroll 4
     for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
         const double* q = blk + (size_t)b * 8;
         double v[8];
@@ -233,7 +245,7 @@ __device__ __forceinline__ void reduce_all_partials(const double* __restrict__ b
 #pragma unroll
     for (int k = 0; k < 8; ++k) shr[threadIdx.x][k] = r[k];
     __syncthreads();
-    for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
+    for (int s = (int)(blockDim.x >> 1); s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             double* a = shr[threadIdx.x];
             const double* b = shr[threadIdx.x + s];
@@ -248,11 +260,42 @@ __device__ __forceinline__ void reduce_all_partials(const double* __restrict__ b
     for (int k = 0; k < 8; ++k) r[k] = shr[0][k];
 }
 
+// Estimate from per-rank partials (rank order = ascending grid offset, so "first maximum" = lowest global index, like
+// thrust::max_element / np.argmax).  partial[0..7] as block partials, [8..11] = ECEF / clock of the rank's arg-max
+// candidate.  result layout mirrors dpe_result (doubles; indices exact below 2^53).  One thread.
+__device__ __forceinline__ void finalize_estimate(const double* __restrict__ parts, int nranks, int est_mode,
+                                                  double* __restrict__ zval, double* __restrict__ rval,
+                                                  double* __restrict__ res) {
+    double sum[5] = {0, 0, 0, 0, 0}, oow = 0, mx = -1.0, mi = 9.0e18;
+    int best = -1;
+    for (int r = 0; r < nranks; ++r) {
+        const double* q = parts + (size_t)r * kPartialLen;
+        for (int k = 0; k < 5; ++k) sum[k] += q[k];
+        oow += q[7];
+        if (q[5] > mx || (q[5] == mx && q[6] < mi)) { mx = q[5]; mi = q[6]; best = r; }
+    }
+    double z[4] = {0, 0, 0, 0};
+    if (est_mode == DPE_EST_WEIGHTED) {                       // BCM_ReduceAndPosMeas :1497-1500
+        for (int k = 0; k < 4; ++k) z[k] = sum[k] / sum[4];
+    } else if (best >= 0) {                                   // BCM_MakePosMeas
+        for (int k = 0; k < 4; ++k) z[k] = parts[(size_t)best * kPartialLen + 8 + k];
+    }
+    for (int k = 0; k < 4; ++k) zval[k] = z[k];
+    for (int r = 0; r < 4; ++r)                               // RVal rows 0-3 <- identity (:2008-2014)
+        for (int k = 0; k < 8; ++k) rval[r * 8 + k] = (r == k) ? 1.0 : 0.0;
+    res[0] = z[0]; res[1] = z[1]; res[2] = z[2]; res[3] = z[3];
+    res[8] = mx; res[9] = sum[4]; res[10] = mi; res[11] = oow;
+}
+
+// The single-rank estimate folded into the tail of a scoring kernel (est_mode < 0: not folded, k_finalize follows).
+struct FoldEst { int est_mode; double* zval; double* rval; double* res; };
+
 // per-rank partial of the position manifold: sums, max / arg-max, and the arg-max candidate's state
 // (BCM_MakePosMeas, batchcorrmanifold.cu:1990-2000)
 __device__ __forceinline__ void finish_position_partial(const double* __restrict__ blk, int n_blk,
                                                         const double* __restrict__ grid, const EpochDev& e,
-                                                        int64_t grid_offset, double* __restrict__ partial) {
+                                                        int64_t grid_offset, double* __restrict__ partial,
+                                                        const FoldEst& fold) {
     double r[8];
     reduce_all_partials(blk, n_blk, r);
     if (threadIdx.x == 0) {
@@ -263,6 +306,7 @@ __device__ __forceinline__ void finish_position_partial(const double* __restrict
             const Cand p = cand_ecef(e, grid + 4 * ((int64_t)r[6] - grid_offset));
             partial[8] = p.px; partial[9] = p.py; partial[10] = p.pz; partial[11] = p.pt;
         }
+        if (fold.est_mode >= 0) finalize_estimate(partial, 1, fold.est_mode, fold.zval, fold.rval, fold.res);
     }
 }
 

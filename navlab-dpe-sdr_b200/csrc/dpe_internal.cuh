@@ -105,7 +105,7 @@ struct dpe_ctx {
     int64_t bx_stride, brd_stride;     // floats per sample-plane copy (8 copies per channel) / per replica plane
     double* grid; double* scores;
     double* blk_partial; int32_t n_blk_partial;
-    unsigned int* ticket;              // last-CTA ticket counter of the scoring kernels (self-resetting)
+    unsigned int* ticket;              // last-CTA ticket counters (self-resetting): [0] position scoring, [1] pair sort, [2] velocity pair sort, [3] velocity scoring
     double* partial; double* zval; double* rval; double* result;  // result: device mirror of dpe_result
     // brute-force work lists
     int16_t* pair_k; float* pair_a; float2* pair_v;    // [C][G]
@@ -122,12 +122,14 @@ struct dpe_ctx {
     int64_t* dbg_f; double* dbg_alpha;
     // velocity (section 8 f-1)
     double* vgrid; double* vscores; double2* carr;       // [Gv][4], [Gv], [C][NBd]
-    long long* dc_sum; float2* bb; double2* vpart; double* vblk_partial;
+    long long* dc_part; float2* bb; double2* vpart; double* vblk_partial;   // [nchunk][2] DC sums per chunk; bb = conj(carrier) plane [C][S]
     // brute-force velocity manifold (DPE_FLAG_BRUTE_VEL): baseband plane with the chosen replica applied + pair lists
     float2* vbb; int64_t vS_pad;
     int16_t* vpair_k; float* vpair_a; float2* vpair_v;
     int32_t *vhist, *vblk_hist, *vgroup_base, *vhdr, *vent_j, *vn_groups; int64_t* vbucket_base; float* vent_a;
     int64_t vmax_groups; int vel_attr_set;
+    int fold_est_mode;                 // >= 0: the scoring kernel's last CTA also writes the single-rank estimate (dpe_epoch_*)
+    int carr_direct;                   // debug switch: evaluate the carrier spectrum directly (k_carr_partial_direct)
     int32_t Wd, NBd, n_fft; int have_vgrid;
     // state
     int have_block, have_epoch, have_prepare, have_corr, have_scores;
@@ -139,6 +141,9 @@ struct dpe_ctx {
     int sort_pending;                  // a presort on another stream has not been waited for yet
     cudaEvent_t ev_epoch, ev_grid, ev_sort;   // epoch upload done / grid upload done / presort done
     cudaStream_t aux_stream;           // dpe_epoch_run's own presort stream (created on first use)
+    // the velocity manifold (lookup formulation) runs on its own stream beside the position scoring: dpe_score_pos records
+    // ev_fork before its first launch, dpe_score_vel enqueues on vel_stream behind it and joins the caller's stream again
+    cudaStream_t vel_stream; cudaEvent_t ev_fork, ev_vel; int fork_valid, vel_fork;
     int64_t launches;
     int lk_cand_forced;                // DPE_LK_CAND = 3 | 4 | 6: candidates per thread of k_score_lookup (0 = chosen per launch)
     int want_sums;                     // k_score_pairs accumulates sum s*x (0 only inside an arg-max dpe_epoch_submit)
@@ -222,7 +227,6 @@ struct DevGuard {
 int launch_brute_planes(dpe_ctx* c, cudaStream_t s);
 int launch_brute_sort(dpe_ctx* c, int sat_mode, cudaStream_t s);
 int launch_score_vel(dpe_ctx* c, cudaStream_t s);
-int launch_dc_sum(dpe_ctx* c, cudaStream_t s);
 size_t brute_smem_bytes(int H);
 int launch_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, cudaStream_t s);
 int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStream_t s);

@@ -82,20 +82,20 @@ __global__ void __launch_bounds__(256) k_gen_time(double fs, int S, double* __re
 //   3. the CTA that takes the last ticket of its channel adds the chunk partials in chunk order (FP64,
 //      fixed order), decides flip / no-flip on lag 0 (BCS_ChooseCodeCorr, batchcorrscores.cu:499-543) and
 //      writes the window (BCS_cufftBatchShift, :554-584: cs[l] <-> shifted bin l - W + S/2).
-// xw / rs (and zw for the carrier branch) still go to HBM once: the brute-force planes and the velocity
-// manifold read them.
+// xw / rs (and the conjugate carrier cc for the carrier branch) still go to HBM once: the brute-force planes and the
+// velocity manifold read them.
 // ---------------------------------------------------------------------------
 __global__ void DPE_SIDE128
 k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const double* __restrict__ tidx,
             const EpochDev* __restrict__ ep, double fs, int S, int W, int NL, int NLp, int nchunk,
             float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
-            int32_t* __restrict__ idx_next, const long long* __restrict__ dc, float2* __restrict__ zw,
+            int32_t* __restrict__ idx_next, long long* __restrict__ dc_part, float2* __restrict__ cc,
             double2* __restrict__ cpart, double2* __restrict__ cs, int32_t* __restrict__ no_flip,
             unsigned int* __restrict__ chan_ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_edge;
     __shared__ bool s_last;
-    __shared__ int s_keep;
+    __shared__ int s_dc[4][2];
     const int c = blockIdx.y;
     const EpochDev& e = *ep;
     if (c >= e.C) return;
@@ -117,9 +117,10 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     __syncthreads();
 
     const double fc = e.fc[c], rc = e.rc_start[c], fi = e.fi[c], ri = e.ri_start[c];
-    // DC mean for the carrier branch: sum / (float)S (ComplexDivide, batchcorrscores.cu:1065,1210-1216)
-    const double inv = 1.0 / (double)(float)S;
-    const float mr = dc ? (float)((double)dc[0] * inv) : 0.f, mi = dc ? (float)((double)dc[1] * inv) : 0.f;
+    // carrier branch (velocity manifold): the CTAs of channel 0 also sum the raw samples of their chunk -- the DC sum of
+    // the block (thrust::reduce, batchcorrscores.cu:1065) as exact integers, chunk by chunk -- and every channel keeps the
+    // conjugate carrier, so that (x - mean) conj(carrier) = xw - mean cc is formed where the mean is known (dpe_vel.cu)
+    int dc_i = 0, dc_q = 0;
     // batches of 4 samples per thread: the 8 global loads of a batch are in flight together (one sample at a time the
     // kernel sat in "long scoreboard": 3.3 stalled warps per issue at 16 % occupancy)
     for (int i0 = threadIdx.x; i0 < nx; i0 += 4 * blockDim.x) {
@@ -161,8 +162,8 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
                     rs[o] = rv;
                     if (chip_idx) chip_idx[o] = (int16_t)chip;
                     xw[o] = x;
-                    if (zw)   // (x - mean) * conj(carrier), BCS_SubtractDCOffset :470-485
-                        zw[o] = make_float2(fmaf(I - mr, cn, (Q - mi) * sn), fmaf(Q - mi, cn, -(I - mr) * sn));
+                    if (cc) cc[o] = make_float2(cn, -sn);
+                    dc_i += v.x; dc_q += v.y;
                 }
                 r_s[m + (m >> 3)] = r;
             }
@@ -173,6 +174,17 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     int edge = s_edge;
     if (!(edge > 0 && edge < S)) edge = S;           // no edge in block: everything is part A
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (dc_part && c == 0) {                          // <= 9 samples per thread: the sums fit an int with room to spare
+        dc_i = __reduce_add_sync(0xffffffffu, dc_i);
+        dc_q = __reduce_add_sync(0xffffffffu, dc_q);
+        if (lane == 0) { s_dc[warp][0] = dc_i; s_dc[warp][1] = dc_q; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long si = 0, sq = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { si += s_dc[w][0]; sq += s_dc[w][1]; }
+            dc_part[2 * chunk] = si; dc_part[2 * chunk + 1] = sq;
+        }
+    }
     const int n_lag_runs = NLp / kLagTile;
     for (int lr = warp; lr < n_lag_runs; lr += (int)(blockDim.x >> 5)) {
         float2 accA[kLagTile], accB[kLagTile];
@@ -243,28 +255,34 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     if (!s_last) return;
     __threadfence();
     const bool has_edge = (s_edge > 0) && (s_edge < S);
-    if (threadIdx.x == 0) {                           // lag 0 decides (:512)
+    // Sums over the chunks, part A and part B of every lag: one warp per lag, lanes stride the chunks, xor-tree in FP64 (a
+    // fixed order).  (The first version walked the 49 chunks serially per lag, twice -- once in thread 0 for the decision
+    // on lag 0, once per lag -- about 100 dependent L2 round trips at the end of a latency-bound kernel.)
+    double2* sumA = reinterpret_cast<double2*>(smem_raw);      // the shared tiles are dead by now: [NL] + [NL]
+    double2* sumB = sumA + NL;
+    for (int l = warp; l < NL; l += (int)(blockDim.x >> 5)) {
         double ax = 0, ay = 0, bx_ = 0, by = 0;
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + W;
-            const double2 a = __ldcg(p), b2 = __ldcg(p + NLp);
-            ax += a.x; ay += a.y; bx_ += b2.x; by += b2.y;
-        }
-        const int keep = !has_edge || (hypot(ax + bx_, ay + by) > hypot(ax - bx_, ay - by));
-        s_keep = keep;
-        no_flip[c] = keep;
-    }
-    __syncthreads();
-    const bool keep = s_keep != 0;
-    for (int l = threadIdx.x; l < NL; l += blockDim.x) {
-        double ax = 0, ay = 0, bx_ = 0, by = 0;
-        for (int ch = 0; ch < nchunk; ++ch) {         // chunk order: a fixed summation order
+        for (int ch = lane; ch < nchunk; ch += 32) {
             const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + l;
             const double2 a = __ldcg(p), b2 = __ldcg(p + NLp);
             ax += a.x; ay += a.y; bx_ += b2.x; by += b2.y;
         }
-        cs[(size_t)c * NL + l] = keep ? make_double2(ax + bx_, ay + by)     // no-flip = A + B
-                                      : make_double2(ax - bx_, ay - by);    // flipped = A - B (only chosen when an edge exists)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o);
+            bx_ += __shfl_xor_sync(0xffffffffu, bx_, o); by += __shfl_xor_sync(0xffffffffu, by, o);
+        }
+        if (lane == 0) { sumA[l] = make_double2(ax, ay); sumB[l] = make_double2(bx_, by); }
+    }
+    __syncthreads();
+    // lag 0 decides (:512); every thread evaluates the same expression on the same sums
+    const double2 a0 = sumA[W], b0 = sumB[W];
+    const bool keep = !has_edge || (hypot(a0.x + b0.x, a0.y + b0.y) > hypot(a0.x - b0.x, a0.y - b0.y));
+    if (threadIdx.x == 0) no_flip[c] = keep;
+    for (int l = threadIdx.x; l < NL; l += blockDim.x) {
+        const double2 a = sumA[l], b2 = sumB[l];
+        cs[(size_t)c * NL + l] = keep ? make_double2(a.x + b2.x, a.y + b2.y)     // no-flip = A + B
+                                      : make_double2(a.x - b2.x, a.y - b2.y);    // flipped = A - B (only chosen when an edge exists)
     }
 }
 
@@ -341,9 +359,8 @@ int launch_prepare(dpe_ctx* c, cudaStream_t s) {
                         (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float) + 1024;
     dim3 grid(c->nchunk, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
-    if (c->Gv > 0) { int rc = launch_dc_sum(c, s); if (rc) return rc; }
     k_prep_corr<<<grid, 128, smem, s>>>(c->iq, c->ca, c->tidx, c->ep, c->cfg.fs, S, c->W, c->NL, c->NLp, c->nchunk,
-                                        c->xw, c->rs, c->chip_idx, c->idx_next, c->Gv > 0 ? c->dc_sum : nullptr,
+                                        c->xw, c->rs, c->chip_idx, c->idx_next, c->Gv > 0 ? c->dc_part : nullptr,
                                         c->Gv > 0 ? c->bb : nullptr, c->cpart, c->cs, c->no_flip, c->chan_ticket);
     c->launches++;
     DPE_CUDA(cudaGetLastError());

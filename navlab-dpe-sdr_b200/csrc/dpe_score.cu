@@ -25,12 +25,15 @@ namespace dpe {
 // kLkCand candidates per thread: 3 (<= 64 registers, 8 CTAs per SM), 4 or 6 (<= 128 registers, 4 CTAs per SM).  The
 // launcher picks the one whose CTA count fills whole waves best: at the demo size (390 625 candidates) 4 per thread is
 // 763 CTAs on 592 slots -- 1.29 waves, the second one 29 % full -- while 6 per thread is 509 CTAs: one wave.
+// (Tried: 64-thread CTAs, 8 per SM, so that the 0.86 wave spreads 6-7 CTAs instead of 3-4 over every SM: 41.6 us against
+// 37.5 -- the finer spread does not pay for twice the prologues and block partials.)
 template <int SAT_MODE, int WITH_SUMS, int kLkCand>
 __global__ void __launch_bounds__(kReduceBlock, (kLkCand == 3) ? 8 : 4)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
                int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
-               unsigned int* __restrict__ ticket, double* __restrict__ partial, const SatGeo* __restrict__ geo_tab) {
+               unsigned int* __restrict__ ticket, double* __restrict__ partial, const SatGeo* __restrict__ geo_tab,
+               const FoldEst fold) {
     __shared__ EpochDev e;
     __shared__ ChanConst cc[DPE_MAX_CHAN];
     __shared__ SatGeo geo_mid[DPE_MAX_CHAN];
@@ -115,7 +118,7 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         if (score[k] > mx) { mx = score[k]; mi = (double)(j + grid_offset); }
     }
     block_reduce_store_vals<WITH_SUMS ? 5 : 1>(v, mx, mi, (double)oow, blk_partial);
-    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial);
+    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial, fold);
 }
 
 __global__ void __launch_bounds__(128) k_sat_geo(const EpochDev* __restrict__ ep, const double* __restrict__ sat, int T,
@@ -160,25 +163,7 @@ __global__ void __launch_bounds__(256) k_debug_bins(const double* __restrict__ g
 __global__ void k_finalize(const double* __restrict__ parts, int nranks, int est_mode,
                            double* __restrict__ zval, double* __restrict__ rval, double* __restrict__ res) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double sum[5] = {0, 0, 0, 0, 0}, oow = 0, mx = -1.0, mi = 9.0e18;
-    int best = -1;
-    for (int r = 0; r < nranks; ++r) {
-        const double* q = parts + (size_t)r * kPartialLen;
-        for (int k = 0; k < 5; ++k) sum[k] += q[k];
-        oow += q[7];
-        if (q[5] > mx || (q[5] == mx && q[6] < mi)) { mx = q[5]; mi = q[6]; best = r; }
-    }
-    double z[4] = {0, 0, 0, 0};
-    if (est_mode == DPE_EST_WEIGHTED) {                       // BCM_ReduceAndPosMeas :1497-1500
-        for (int k = 0; k < 4; ++k) z[k] = sum[k] / sum[4];
-    } else if (best >= 0) {                                   // BCM_MakePosMeas
-        for (int k = 0; k < 4; ++k) z[k] = parts[(size_t)best * kPartialLen + 8 + k];
-    }
-    for (int k = 0; k < 4; ++k) zval[k] = z[k];
-    for (int r = 0; r < 4; ++r)                               // RVal rows 0-3 <- identity (:2008-2014)
-        for (int k = 0; k < 8; ++k) rval[r * 8 + k] = (r == k) ? 1.0 : 0.0;
-    res[0] = z[0]; res[1] = z[1]; res[2] = z[2]; res[3] = z[3];
-    res[8] = mx; res[9] = sum[4]; res[10] = mi; res[11] = oow;
+    finalize_estimate(parts, nranks, est_mode, zval, rval, res);
 }
 
 // ---------------------------------------------------------------------------
@@ -206,6 +191,7 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     const int per = kReduceBlock * nc;
     const int nblk = (int)((c->G + per - 1) / per);
     prof_begin(c, DPE_STAGE_LOOKUP, s);
+    const FoldEst fold = {c->fold_est_mode, c->zval, c->rval, c->result};
     const SatGeo* tab = nullptr;
     if (sat_mode == DPE_SAT_PER_TIME) {
         int rc = launch_sat_geo(c, s);
@@ -214,7 +200,7 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     }
 #define DPE_LK(SM, WS, NC) k_score_lookup<SM, WS, NC><<<nblk, kReduceBlock, 0, s>>>(                                \
         c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,              \
-        c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab)
+        c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab, fold)
 #define DPE_LK_NC(SM, WS) do { if (nc == 3) DPE_LK(SM, WS, 3); else if (nc == 6) DPE_LK(SM, WS, 6); else DPE_LK(SM, WS, 4); } while (0)
     if (sat_mode == DPE_SAT_PER_TIME) { if (c->want_sums) DPE_LK_NC(DPE_SAT_PER_TIME, 1); else DPE_LK_NC(DPE_SAT_PER_TIME, 0); }
     else { if (c->want_sums) DPE_LK_NC(DPE_SAT_MIDDLE, 1); else DPE_LK_NC(DPE_SAT_MIDDLE, 0); }

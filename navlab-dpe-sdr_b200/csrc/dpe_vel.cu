@@ -9,28 +9,38 @@
 // Here: a velocity grid of +-V m/s only reaches Doppler bins within +-Wd of the prompt
 // (bin width fs / N_c = 4.77 Hz at 2.5 MHz), so those 2*Wd+2 bins of the zero-padded spectrum are
 // evaluated directly,  carr[m] = sum_n bb[n] exp(-j 2 pi n m / N_c),  with the twiddle angle
-// reduced exactly in integers (n*m mod N_c) before sincospif; FP32 inside a 1024-sample chunk,
-// FP64 across chunks.  The scoring kernel is the position one with a Doppler geometry.
+// reduced exactly in integers before sincospif; FP32 inside a 1024-sample chunk, FP64 across chunks.
+// Those bins are a narrow band (+-310 Hz of 2.5 MHz): inside a block of 32 samples the twiddle turns by at most
+// 0.012 rad, so a block enters every bin through its four complex MOMENTS  M_k = sum_b t^k bb[n0 + b]
+// (k_carr_partial; Taylor remainder < 1e-9, below the FP32 rounding of the sums) -- 22 FP32 operations per
+// (block, bin) instead of 256.  Windows too wide for that bound take the direct kernel (k_carr_partial_direct).
+// The scoring kernel is the position one with a Doppler geometry.
 #include "dpe_geom.cuh"
 
 namespace dpe {
 
-// integer sum of the block (exact; the reference reduces doubles with thrust, :1065)
-__global__ void DPE_SIDE256 k_dc_sum(const int16_t* __restrict__ iq, int S, long long* __restrict__ out) {
+// DC mean of the block, sum / (float)S (ComplexDivide, batchcorrscores.cu:1065,1210-1216), from the per-chunk integer sums
+// k_prep_corr left behind; every warp evaluates it for itself (lanes stride the chunks, xor-tree: no barrier needed).
+__device__ __forceinline__ float2 dc_mean(const long long* __restrict__ dc_part, int nchunk, int S) {
     long long si = 0, sq = 0;
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < S; n += gridDim.x * blockDim.x) {
-        const short2 v = reinterpret_cast<const short2*>(iq)[n];
-        si += v.x; sq += v.y;
-    }
+    for (int ch = threadIdx.x & 31; ch < nchunk; ch += 32) { si += dc_part[2 * ch]; sq += dc_part[2 * ch + 1]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         si += __shfl_xor_sync(0xffffffffu, si, o);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)si);
-        atomicAdd(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)sq);
-    }
+    const double inv = 1.0 / (double)(float)S;
+    return make_float2((float)((double)si * inv), (float)((double)sq * inv));
+}
+
+// bb[n] = (x[n] - mean) conj(carrier[n]) * chosen replica[n] = (xw[n] - mean cc[n]) r[n]
+// (BCS_SubtractDCOffset :470-485, BCS_ChoosyBatchMultiplyAndPad :422-452)
+__device__ __forceinline__ float2 baseband(const float2* __restrict__ xw, const float2* __restrict__ cc,
+                                           const int8_t* __restrict__ rs, size_t o, float2 mean, bool negate) {
+    const float2 x = xw[o], k = cc[o];
+    float r = (float)rs[o];
+    if (negate) r = -r;
+    return make_float2((x.x - (mean.x * k.x - mean.y * k.y)) * r, (x.y - (mean.x * k.y + mean.y * k.x)) * r);
 }
 
 // One CTA per (1024-sample chunk, channel); warp w owns bins w, w+8, ...; lanes stride the samples.
@@ -40,25 +50,20 @@ __global__ void DPE_SIDE256 k_dc_sum(const int16_t* __restrict__ iq, int S, long
 // (integer n*m mod N_c -> sincospif) every 8th step and advanced by the exact 32-sample rotation in
 // between (7 complex multiplies: < 5e-7 relative drift).
 __global__ void DPE_SIDE256
-k_carr_partial(const float2* __restrict__ zw, const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
-               const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
-               int n_fft, int nchunk, double2* __restrict__ vpart) {
+k_carr_partial_direct(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part,
+                      const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
+                      const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
+                      int n_fft, int nchunk, double2* __restrict__ vpart) {
     __shared__ float2 xs[kCorrChunk];
     const int c = blockIdx.y;
     if (c >= ep->C) return;
     const int chunk = blockIdx.x, n0 = chunk * kCorrChunk;
     const bool flip = !no_flip[c];
     const int edge = idx_next[c];
+    const float2 mean = dc_mean(dc_part, nchunk, S);
     for (int i = threadIdx.x; i < kCorrChunk; i += blockDim.x) {
         const int n = n0 + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (n < S) {
-            v = zw[(size_t)c * S + n];
-            float r = (float)rs[(size_t)c * S + n];
-            if (flip && n >= edge) r = -r;
-            v.x *= r; v.y *= r;
-        }
-        xs[i] = v;
+        xs[i] = (n < S) ? baseband(xw, cc, rs, (size_t)c * S + n, mean, flip && n >= edge) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,6 +93,80 @@ k_carr_partial(const float2* __restrict__ zw, const int8_t* __restrict__ rs, con
             ai += __shfl_xor_sync(0xffffffffu, ai, o);
         }
         if (lane == 0) vpart[((size_t)c * nchunk + chunk) * NBd + l] = make_double2((double)ar, (double)ai);
+    }
+}
+
+// The same partial spectrum through block moments.  One CTA per (1024-sample chunk, channel):
+//   1. warp w takes blocks 4w .. 4w+3 of 32 samples: lane b holds sample b, t = (b - 15.5) / 16, the four complex
+//      moments sum_b t^k bb are butterfly-summed and kept in shared memory;
+//   2. one item = (quarter of 8 blocks, bin m): with phi = 32 pi m / N_c
+//          sum_b bb[b] exp(-j 2 pi (n0 + b) m / N_c) = exp(-j 2 pi nc m / N_c) (M0 - j phi M1 - phi^2/2 M2 + j phi^3/6 M3) + O(phi^4/24)
+//      (nc = n0 + 15.5 the block centre; its phase is reduced exactly in integers, (2 nc) m mod 2 N_c, for the first
+//      block of the quarter and advanced by the exact 32-sample rotation for the other seven);
+//   3. the four quarters are added in FP64.
+// The launcher only takes this kernel when (2 pi (Wd + 1) 15.5 / N_c)^4 / 24 < 2e-8 and 2 N_c <= 2^24.
+__global__ void DPE_SIDE256
+k_carr_partial(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part,
+               const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
+               const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
+               int n_fft, int nchunk, double2* __restrict__ vpart) {
+    extern __shared__ float2 qpart[];                           // [4][NBd] quarter partials
+    __shared__ float2 mom[kCorrChunk / 32][4];
+    const int c = blockIdx.y;
+    if (c >= ep->C) return;
+    const int chunk = blockIdx.x, n0 = chunk * kCorrChunk;
+    const bool flip = !no_flip[c];
+    const int edge = idx_next[c];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float t = ((float)lane - 15.5f) * 0.0625f;
+    const float2 mean = dc_mean(dc_part, nchunk, S);
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+        const int blk = 4 * warp + bi;
+        const int n = n0 + 32 * blk + lane;
+        const float2 v = (n < S) ? baseband(xw, cc, rs, (size_t)c * S + n, mean, flip && n >= edge) : make_float2(0.f, 0.f);
+        float m[8] = {v.x, v.y, t * v.x, t * v.y, 0.f, 0.f, 0.f, 0.f};
+        m[4] = t * m[2]; m[5] = t * m[3]; m[6] = t * m[4]; m[7] = t * m[5];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] += __shfl_xor_sync(0xffffffffu, m[k], o);
+        if (lane < 4) mom[blk][lane] = make_float2(lane == 0 ? m[0] : lane == 1 ? m[2] : lane == 2 ? m[4] : m[6],
+                                                   lane == 0 ? m[1] : lane == 1 ? m[3] : lane == 2 ? m[5] : m[7]);
+    }
+    __syncthreads();
+    const unsigned mask2 = 2u * (unsigned)n_fft - 1u;             // n_fft is a power of two
+    const float inv_n = 1.0f / (float)n_fft;
+    for (int item = threadIdx.x; item < 4 * NBd; item += blockDim.x) {
+        const int q = item / NBd, l = item - q * NBd;
+        const int m = l - Wd;                                   // bin relative to 0 Hz
+        const float phi = (float)m * (32.0f * 3.14159265358979f * inv_n);
+        const float a2 = 0.5f * phi * phi, a3 = phi * phi * (1.0f / 6.0f);
+        float stp_s, stp_c, sn, cs;                             // 32-sample rotation; phase of the first block centre
+        sincospif((float)((64u * (unsigned)m) & mask2) * inv_n, &stp_s, &stp_c);
+        const unsigned twice_nc = 2u * (unsigned)(n0 + 256 * q) + 31u;
+        sincospif((float)((twice_nc * (unsigned)m) & mask2) * inv_n, &sn, &cs);
+        float ar = 0.f, ai = 0.f;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const float2* M = mom[8 * q + b];
+            const float2 M0 = M[0], M1 = M[1], M2 = M[2], M3 = M[3];
+            const float Ar = fmaf(-a2, M2.x, M0.x), Ai = fmaf(-a2, M2.y, M0.y);
+            const float Br = fmaf(-a3, M3.x, M1.x), Bi = fmaf(-a3, M3.y, M1.y);
+            const float Pr = fmaf(phi, Bi, Ar), Pi = fmaf(-phi, Br, Ai);          // A - j phi B
+            ar = fmaf(Pr, cs, fmaf(Pi, sn, ar));                                   // P * (cs - j sn)
+            ai = fmaf(Pi, cs, fmaf(-Pr, sn, ai));
+            const float c2 = cs * stp_c - sn * stp_s, s2 = sn * stp_c + cs * stp_s;
+            cs = c2; sn = s2;
+        }
+        qpart[item] = make_float2(ar, ai);
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < NBd; l += blockDim.x) {
+        double re = 0, im = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { re += (double)qpart[q * NBd + l].x; im += (double)qpart[q * NBd + l].y; }
+        vpart[((size_t)c * nchunk + chunk) * NBd + l] = make_double2(re, im);
     }
 }
 
@@ -132,78 +211,115 @@ __device__ __forceinline__ void finish_velocity(const double* __restrict__ blk_p
     }
 }
 
-// unit line of sight to the grid CENTRE + satellite velocity / clock drift of every channel (batchcorrmanifold.cu:1917-1921)
-__device__ __forceinline__ void vel_los(const EpochDev& e, const double* __restrict__ sat, int T, double (*los_s)[8]) {
+// Per-channel terms of the Doppler geometry that do not depend on the candidate: unit line of sight to the grid CENTRE
+// (batchcorrmanifold.cu:1917-1921: one per channel, not per candidate), satellite velocity / clock drift, the carrier
+// frequency of the channel, the row offset N_c * c the reference adds before the floor and the first bin of the window.
+struct VelChan { double ux, uy, uz, svx, svy, svz, drift, inv_sign, fi, off, lbase; };
+
+__device__ __forceinline__ void vel_chan_consts(const EpochDev& e, const double* __restrict__ sat, int T, int n_fft, int Wd,
+                                                VelChan* __restrict__ vc) {
     if (threadIdx.x < e.C) {
         const int c = threadIdx.x;
         const double* s = sat + ((size_t)c * T + T / 2) * 8;
         double los[3] = {s[0] - e.center[0], s[1] - e.center[1], s[2] - e.center[2]};
         const double range = norm(3, los);
-        los_s[c][0] = los[0] / range; los_s[c][1] = los[1] / range; los_s[c][2] = los[2] / range;
-        los_s[c][3] = s[4]; los_s[c][4] = s[5]; los_s[c][5] = s[6]; los_s[c][6] = s[7];
+        VelChan u;
+        u.ux = los[0] / range; u.uy = los[1] / range; u.uz = los[2] / range;
+        u.svx = s[4]; u.svy = s[5]; u.svz = s[6]; u.drift = s[7];
+        u.inv_sign = 1.0 / e.doppler_sign;
+        u.fi = e.fi[c];
+        u.off = (double)((int64_t)n_fft * c);
+        u.lbase = u.off + (double)(n_fft / 2 - Wd);
+        vc[c] = u;
     }
 }
 
 // Doppler bin of one (velocity candidate, channel) pair (batchcorrmanifold.cu:1932-1950): window entry l (bin l - Wd
-// relative to 0 Hz), lerp weight of entry l + 1; false when the pair falls outside the window / the spectrum
+// relative to 0 Hz), lerp weights of entries l + 1 and l; false when the pair falls outside the window / the spectrum.
+// The reference divides by c and by the Doppler sign (+-1); the products below differ from that by an ulp of a frequency
+// of ~1e3 Hz -- 1e-13 of a bin, and the lerp is continuous across a bin boundary.  All integers here are below 2^53, so
+// the window entry is formed in FP64 (exact) and converted once.
 struct VelCand { double ex, ey, ez, pt; };
-__device__ __forceinline__ bool vel_bin(const EpochDev& e, const double* __restrict__ u, const VelCand& v, int c, double fs,
-                                        int n_fft, int Wd, int NBd, int64_t* l_out, double* wg, double* wf) {
-    const double rate = (u[0] * (v.ex - u[3])) + (u[1] * (v.ey - u[4])) + (u[2] * (v.ez - u[5]));
-    const double bc_fi = K_F_L1 * ((rate - v.pt) / K_C + u[6]) / e.doppler_sign;
-    const double fi0 = bc_fi - e.fi[c];
-    const double idx_base = (n_fft / fs) * fi0 + n_fft / 2.0;
-    const bool valid = (idx_base < n_fft) && (idx_base > 0);
-    const double idxo = idx_base + (double)((int64_t)n_fft * c);
+__device__ __forceinline__ bool vel_bin(const VelChan& u, const VelCand& v, double scale, double half, double nf, int NBd,
+                                        int* l_out, double* wg, double* wf) {
+    const double rate = fma(u.ux, v.ex - u.svx, fma(u.uy, v.ey - u.svy, u.uz * (v.ez - u.svz)));
+    const double bc_fi = K_F_L1 * fma(rate - v.pt, 1.0 / K_C, u.drift) * u.inv_sign;
+    const double idx_base = fma(scale, bc_fi - u.fi, half);
+    const bool valid = (idx_base < nf) && (idx_base > 0.0);
+    const double idxo = idx_base + u.off;
     const double f = floor(idxo), gg = floor(idxo + 1.0);
-    const int64_t l = (int64_t)f - (int64_t)n_fft * c - n_fft / 2 + Wd;
-    *l_out = l;
+    const double lrel = f - u.lbase;
+    const bool ok = valid && lrel >= 0.0 && lrel <= (double)(NBd - 2);
+    *l_out = ok ? (int)lrel : 0;
     *wg = idxo - f;
     *wf = gg - idxo;
-    return valid && l >= 0 && l + 1 < NBd;
+    return ok;
 }
 
-// BCM_VelMeasML with the arg-max fused (batchcorrmanifold.cu:1896-1962); partial layout as the
-// position kernels' (sum s*v, sum s, max, argmax, out-of-window).
-__global__ void __launch_bounds__(kReduceBlock, 6)
+__device__ __forceinline__ VelCand vel_cand(const EpochDev& e, const double* __restrict__ g4) {
+    const double2 a = *reinterpret_cast<const double2*>(g4);
+    const double2 b = *reinterpret_cast<const double2*>(g4 + 2);
+    const double vx = e.R[0] * a.x + e.R[1] * a.y + e.R[2] * b.x + e.center[4];
+    const double vy = e.R[3] * a.x + e.R[4] * a.y + e.R[5] * b.x + e.center[5];
+    const double vz = e.R[6] * a.x + e.R[7] * a.y + e.R[8] * b.x + e.center[6];
+    return VelCand{vx - K_OEDOT * e.center[1], vy + K_OEDOT * e.center[0], vz, b.y + e.center[7]};
+}
+
+// BCM_VelMeasML with the arg-max fused (batchcorrmanifold.cu:1896-1962); partial layout as the position kernels'
+// (sum of scores, max, argmax, out-of-window).  kVelCand candidates per thread (j = base + tid + 128 k), branch-free over
+// them so that their FP64 chains interleave -- one candidate per thread left the kernel at 45 us for 25^4 candidates,
+// latency bound, with the per-CTA prologue (EpochDev copy, lines of sight) paid once per 128 candidates.
+constexpr int kVelCand = 6;
+__global__ void __launch_bounds__(kReduceBlock, 4)
 k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
             double* __restrict__ vscores, double* __restrict__ blk_partial, unsigned int* __restrict__ ticket,
             const double* __restrict__ vgrid_all, double* __restrict__ zval, double* __restrict__ rval,
             double* __restrict__ res) {
     __shared__ EpochDev e;
-    __shared__ double los_s[DPE_MAX_CHAN][8];
+    __shared__ VelChan vch[DPE_MAX_CHAN];
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
     __syncthreads();
-    // the line of sight goes to the grid CENTRE (batchcorrmanifold.cu:1917-1921): one per channel, not per candidate
-    vel_los(e, sat, T, los_s);
+    vel_chan_consts(e, sat, T, n_fft, Wd, vch);
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = j < Gv;
-    double score = 0.0;
-    int oow = 0;
-    Cand v = {0, 0, 0, 0};
-    if (active) {
-        const double* g = vgrid + 4 * j;
-        v.px = e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4];
-        v.py = e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5];
-        v.pz = e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6];
-        v.pt = g[3] + e.center[7];
-        const VelCand vc = {v.px - K_OEDOT * e.center[1], v.py + K_OEDOT * e.center[0], v.pz, v.pt};
-        for (int c = 0; c < e.C; ++c) {
-            int64_t l;
-            double wg, wf;
-            if (vel_bin(e, los_s[c], vc, c, fs, n_fft, Wd, NBd, &l, &wg, &wf)) {
-                const double2 lo = carr[(size_t)c * NBd + l], hi = carr[(size_t)c * NBd + l + 1];
-                score += mag_pow(hi.x * wg + lo.x * wf, hi.y * wg + lo.y * wf, lpower);
-            } else {
-                ++oow;
-            }
-        }
-        vscores[j] = score;
+    const int64_t base = (int64_t)blockIdx.x * (kReduceBlock * kVelCand) + threadIdx.x;
+    VelCand vc[kVelCand];
+    double score[kVelCand];
+    bool act[kVelCand];
+#pragma unroll
+    for (int k = 0; k < kVelCand; ++k) {
+        const int64_t j = base + (int64_t)k * kReduceBlock;
+        act[k] = j < Gv;
+        score[k] = 0.0;
+        vc[k] = act[k] ? vel_cand(e, vgrid + 4 * j) : VelCand{0, 0, 0, 0};
     }
-    block_reduce_store(score, j, v, active, oow, blk_partial);
+    const double scale = n_fft / fs, half = n_fft / 2.0, nf = (double)n_fft;
+    int oow = 0;
+    for (int c = 0; c < e.C; ++c) {
+        const VelChan u = vch[c];
+        const double2* __restrict__ cc = carr + (size_t)c * NBd;
+#pragma unroll
+        for (int k = 0; k < kVelCand; ++k) {
+            int l;
+            double wg, wf;
+            const bool ok = vel_bin(u, vc[k], scale, half, nf, NBd, &l, &wg, &wf);
+            const double2 lo = cc[l], hi = cc[l + 1];                 // l = 0 when not ok: the loads are unconditional
+            const double m = mag_pow(hi.x * wg + lo.x * wf, hi.y * wg + lo.y * wf, lpower);
+            score[k] += (ok && act[k]) ? m : 0.0;
+            oow += (act[k] && !ok) ? 1 : 0;
+        }
+    }
+    double v[5] = {0, 0, 0, 0, 0}, mx = -1.0, mi = 9.0e18;
+#pragma unroll
+    for (int k = 0; k < kVelCand; ++k) {
+        if (!act[k]) continue;
+        const int64_t j = base + (int64_t)k * kReduceBlock;
+        vscores[j] = score[k];
+        v[4] += score[k];
+        if (score[k] > mx) { mx = score[k]; mi = (double)j; }    // increasing index order: the lowest index wins ties
+    }
+    block_reduce_store_vals<1>(v, mx, mi, (double)oow, blk_partial);
     // last CTA: arg-max over all candidates + BCM_MakeVelMeas (zVal[4:8], RVal rows 4-7, batchcorrmanifold.cu:2030-2068)
     if (take_last_ticket(ticket)) finish_velocity(blk_partial, gridDim.x, e, vgrid_all, zval, rval, res);
 }
@@ -227,21 +343,17 @@ constexpr int kVelTile = 1024;
 constexpr size_t kVelSmem = 2 * 2 * kVelTile * sizeof(float4);   // 64 KB: two buffers of (A, B)
 
 __global__ void DPE_SIDE256
-k_vel_plane(const float2* __restrict__ zw, const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
+k_vel_plane(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part, int nchunk,
+            const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
             const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int64_t S_pad,
             float2* __restrict__ vbb) {
     const int c = blockIdx.y;
     if (c >= ep->C) return;
+    const float2 mean = dc_mean(dc_part, nchunk, S);            // before any thread leaves: the shuffles need whole warps
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= S_pad) return;
-    float2 v = make_float2(0.f, 0.f);
-    if (n < S) {
-        v = zw[(size_t)c * S + n];
-        float r = (float)rs[(size_t)c * S + n];
-        if (!no_flip[c] && n >= idx_next[c]) r = -r;
-        v.x *= r; v.y *= r;
-    }
-    vbb[(size_t)c * S_pad + n] = v;
+    vbb[(size_t)c * S_pad + n] = (n < S) ? baseband(xw, cc, rs, (size_t)c * S + n, mean, !no_flip[c] && n >= idx_next[c])
+                                         : make_float2(0.f, 0.f);
 }
 
 __global__ void DPE_SIDE128
@@ -250,28 +362,25 @@ k_vel_pair_bins(const double* __restrict__ vgrid, const EpochDev* __restrict__ e
                 float* __restrict__ pair_a, float2* __restrict__ pair_v, int32_t* __restrict__ blk_hist) {
     extern __shared__ int32_t hs[];
     __shared__ EpochDev e;
-    __shared__ double los_s[DPE_MAX_CHAN][8];
+    __shared__ VelChan vch[DPE_MAX_CHAN];
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
     __syncthreads();
     const int NB = 2 * Wd + 1, nbuck = e.C * NB;
     for (int i = threadIdx.x; i < nbuck; i += blockDim.x) hs[i] = 0;
-    vel_los(e, sat, T, los_s);
+    vel_chan_consts(e, sat, T, n_fft, Wd, vch);
     __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < Gv) {
-        const double* g = vgrid + 4 * j;
-        const double vx = e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4];
-        const double vy = e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5];
-        const double vz = e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6];
-        const VelCand vc = {vx - K_OEDOT * e.center[1], vy + K_OEDOT * e.center[0], vz, g[3] + e.center[7]};
+        const VelCand vc = vel_cand(e, vgrid + 4 * j);
+        const double scale = n_fft / fs, half = n_fft / 2.0, nf = (double)n_fft;
         for (int c = 0; c < e.C; ++c) {
-            int64_t l;
+            int l;
             double wg, wf;
-            const bool ok = vel_bin(e, los_s[c], vc, c, fs, n_fft, Wd, NBd, &l, &wg, &wf);
+            const bool ok = vel_bin(vch[c], vc, scale, half, nf, NBd, &l, &wg, &wf);
             pair_k[(size_t)c * Gv + j] = ok ? (int16_t)l : (int16_t)-1;
             pair_a[(size_t)c * Gv + j] = (float)wg;
-            if (ok) atomicAdd(&hs[c * NB + (int)l], 1);
+            if (ok) atomicAdd(&hs[c * NB + l], 1);
             else pair_v[(size_t)c * Gv + j] = make_float2(__int_as_float(0x7fc00000), 0.f);   // NaN: "not scored"
         }
     }
@@ -418,7 +527,8 @@ int launch_score_vel_brute(dpe_ctx* c, cudaStream_t s) {
     const int NB = 2 * c->Wd + 1, nbuck = C * NB;
     prof_begin(c, DPE_STAGE_VELOCITY, s);
     dim3 gp((unsigned)((c->vS_pad + 255) / 256), C);
-    k_vel_plane<<<gp, 256, 0, s>>>(c->bb, c->rs, c->idx_next, c->no_flip, c->ep, S, c->vS_pad, c->vbb);
+    k_vel_plane<<<gp, 256, 0, s>>>(c->xw, c->bb, c->dc_part, c->nchunk, c->rs, c->idx_next, c->no_flip, c->ep, S, c->vS_pad,
+                                   c->vbb);
     c->launches++;
     const int nblk = (int)((c->Gv + kSortBlock - 1) / kSortBlock);
     k_vel_pair_bins<<<nblk, kSortBlock, sizeof(int32_t) * nbuck, s>>>(c->vgrid, c->ep, c->sat, c->cfg.fs, c->n_fft, c->Wd,
@@ -437,19 +547,9 @@ int launch_score_vel_brute(dpe_ctx* c, cudaStream_t s) {
     DPE_CUDA(cudaGetLastError());
     const int nb2 = (int)((c->Gv + kReduceBlock - 1) / kReduceBlock);
     k_score_vpairs<<<nb2, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->vpair_v, c->cfg.lpower, c->Gv, c->vscores,
-                                                c->vblk_partial, c->ticket, c->zval, c->rval, c->result);
+                                                c->vblk_partial, c->ticket + 3, c->zval, c->rval, c->result);
     c->launches++;
     prof_end(c, s);
-    DPE_CUDA(cudaGetLastError());
-    return DPE_OK;
-}
-
-// DC sum of the block; runs before k_prepare when a velocity grid exists (k_prepare then also
-// emits zw = (x - mean) * conj(carrier))
-int launch_dc_sum(dpe_ctx* c, cudaStream_t s) {
-    DPE_CUDA(cudaMemsetAsync(c->dc_sum, 0, 2 * sizeof(long long), s));
-    k_dc_sum<<<32, 256, 0, s>>>(c->iq, (int)c->S, c->dc_sum);
-    c->launches++;
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;
 }
@@ -458,13 +558,20 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S, C = c->epoch_C;
     prof_begin(c, DPE_STAGE_VELOCITY, s);
     dim3 g2(c->nchunk, C);
-    k_carr_partial<<<g2, 256, 0, s>>>(c->bb, c->rs, c->idx_next, c->no_flip, c->ep, S, c->Wd, c->NBd, c->n_fft,
-                                      c->nchunk, c->vpart);
+    // block moments when the Doppler window is narrow enough for the 4-term Taylor bound (and the doubled phase stays
+    // exact in a float), the direct evaluation otherwise
+    const double x = 2.0 * 3.141592653589793 * (c->Wd + 1) * 15.5 / (double)c->n_fft;
+    if (x * x * x * x / 24.0 < 2.0e-8 && c->n_fft <= (1 << 23) && !c->carr_direct)
+        k_carr_partial<<<g2, 256, sizeof(float2) * 4 * c->NBd, s>>>(c->xw, c->bb, c->dc_part, c->rs, c->idx_next, c->no_flip,
+                                                                   c->ep, S, c->Wd, c->NBd, c->n_fft, c->nchunk, c->vpart);
+    else
+        k_carr_partial_direct<<<g2, 256, 0, s>>>(c->xw, c->bb, c->dc_part, c->rs, c->idx_next, c->no_flip, c->ep, S, c->Wd,
+                                                 c->NBd, c->n_fft, c->nchunk, c->vpart);
     dim3 g3(C, (c->NBd + 7) / 8);
     k_carr_finalize<<<g3, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->nchunk, c->carr);
-    const int nblk = (int)((c->Gv + kReduceBlock - 1) / kReduceBlock);
+    const int nblk = (int)((c->Gv + kReduceBlock * kVelCand - 1) / (kReduceBlock * kVelCand));
     k_score_vel<<<nblk, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd,
-                                              c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial, c->ticket,
+                                              c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial, c->ticket + 3,
                                               c->vgrid, c->zval, c->rval, c->result);
     c->launches += 3;
     prof_end(c, s);
@@ -473,8 +580,8 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
 }
 
 int kernel_attr_vel(const char* name, cudaFuncAttributes* a) {
-    DPE_KATTR("k_dc_sum", k_dc_sum);
     DPE_KATTR("k_carr_partial", k_carr_partial);
+    DPE_KATTR("k_carr_partial_direct", k_carr_partial_direct);
     DPE_KATTR("k_carr_finalize", k_carr_finalize);
     DPE_KATTR("k_score_vel", k_score_vel);
     DPE_KATTR("k_brute_vel", k_brute_vel);
