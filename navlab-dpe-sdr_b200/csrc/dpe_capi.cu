@@ -150,6 +150,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     c->NLp = ((c->NL + kLagTile - 1) / kLagTile) * kLagTile;
     c->H = ((c->W + 8 + 31) / 32) * 32;
     c->nchunk = (int)((c->S + kCorrChunk - 1) / kCorrChunk);
+    c->vnchunk = (int)((c->S + kCarrChunk - 1) / kCarrChunk);
     c->maxC = cfg->max_chan;
     c->T = cfg->time_dim > 0 ? cfg->time_dim : 1;
     c->nranks = 1;
@@ -215,7 +216,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->carr, C * c->NBd);
         DPE_ALLOC(c->dc_part, 2 * c->nchunk);
         DPE_ALLOC(c->bb, C * S);
-        DPE_ALLOC(c->vpart, C * c->nchunk * c->NBd);
+        DPE_ALLOC(c->vpart, C * c->vnchunk * c->NBd);
         DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
         if (cfg->flags & DPE_FLAG_BRUTE_VEL) {
             const size_t NBv = 2 * c->Wd + 1, Gv = (size_t)cfg->Gv;

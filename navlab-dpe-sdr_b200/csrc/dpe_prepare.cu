@@ -121,14 +121,16 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     // the block (thrust::reduce, batchcorrscores.cu:1065) as exact integers, chunk by chunk -- and every channel keeps the
     // conjugate carrier, so that (x - mean) conj(carrier) = xw - mean cc is formed where the mean is known (dpe_vel.cu)
     int dc_i = 0, dc_q = 0;
-    // batches of 4 samples per thread: the 8 global loads of a batch are in flight together (one sample at a time the
-    // kernel sat in "long scoreboard": 3.3 stalled warps per issue at 16 % occupancy)
-    for (int i0 = threadIdx.x; i0 < nx; i0 += 4 * blockDim.x) {
-        double tq[4];
-        short2 vq[4];
-        int nq[4];
+    // batches of kPrepBatch samples per thread: the global loads of a batch are in flight together (one sample at a time
+    // the kernel sat in "long scoreboard": 3.3 stalled warps per issue at 16 % occupancy); 2 x 5 x 128 covers the 1024
+    // samples of the chunk and the halo of the usual lag windows in two rounds of loads
+    constexpr int kPrepBatch = 5;
+    for (int i0 = threadIdx.x; i0 < nx; i0 += kPrepBatch * blockDim.x) {
+        double tq[kPrepBatch];
+        short2 vq[kPrepBatch];
+        int nq[kPrepBatch];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kPrepBatch; ++q) {
             const int i = i0 + q * blockDim.x;
             int n = n0 - W + i;
             n %= S; if (n < 0) n += S;
@@ -137,7 +139,7 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
             vq[q] = (i < nx) ? __ldg(reinterpret_cast<const short2*>(iq) + n) : make_short2(0, 0);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kPrepBatch; ++q) {
             const int i = i0 + q * blockDim.x;
             if (i >= nx) break;
             const int n = nq[q];

@@ -53,15 +53,15 @@ __global__ void DPE_SIDE256
 k_carr_partial_direct(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part,
                       const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
                       const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
-                      int n_fft, int nchunk, double2* __restrict__ vpart) {
-    __shared__ float2 xs[kCorrChunk];
+                      int n_fft, int nchunk, int n_dc, double2* __restrict__ vpart) {
+    __shared__ float2 xs[kCarrChunk];
     const int c = blockIdx.y;
     if (c >= ep->C) return;
-    const int chunk = blockIdx.x, n0 = chunk * kCorrChunk;
+    const int chunk = blockIdx.x, n0 = chunk * kCarrChunk;
     const bool flip = !no_flip[c];
     const int edge = idx_next[c];
-    const float2 mean = dc_mean(dc_part, nchunk, S);
-    for (int i = threadIdx.x; i < kCorrChunk; i += blockDim.x) {
+    const float2 mean = dc_mean(dc_part, n_dc, S);
+    for (int i = threadIdx.x; i < kCarrChunk; i += blockDim.x) {
         const int n = n0 + i;
         xs[i] = (n < S) ? baseband(xw, cc, rs, (size_t)c * S + n, mean, flip && n >= edge) : make_float2(0.f, 0.f);
     }
@@ -75,7 +75,7 @@ k_carr_partial_direct(const float2* __restrict__ xw, const float2* __restrict__ 
         sincospif((float)((32u * (unsigned)m) & mask) * scale, &stp_s, &stp_c);
         float ar = 0.f, ai = 0.f;
 #pragma unroll 1
-        for (int i0 = lane; i0 < kCorrChunk; i0 += 32 * 8) {
+        for (int i0 = lane; i0 < kCarrChunk; i0 += 32 * 8) {
             float sn, cs;
             sincospif((float)(((unsigned)(n0 + i0) * (unsigned)m) & mask) * scale, &sn, &cs);   // exact re-sync
 #pragma unroll
@@ -109,17 +109,17 @@ __global__ void DPE_SIDE256
 k_carr_partial(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part,
                const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
                const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
-               int n_fft, int nchunk, double2* __restrict__ vpart) {
+               int n_fft, int nchunk, int n_dc, double2* __restrict__ vpart) {
     extern __shared__ float2 qpart[];                           // [4][NBd] quarter partials
-    __shared__ float2 mom[kCorrChunk / 32][4];
+    __shared__ float2 mom[kCarrChunk / 32][4];
     const int c = blockIdx.y;
     if (c >= ep->C) return;
-    const int chunk = blockIdx.x, n0 = chunk * kCorrChunk;
+    const int chunk = blockIdx.x, n0 = chunk * kCarrChunk;
     const bool flip = !no_flip[c];
     const int edge = idx_next[c];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float t = ((float)lane - 15.5f) * 0.0625f;
-    const float2 mean = dc_mean(dc_part, nchunk, S);
+    const float2 mean = dc_mean(dc_part, n_dc, S);
 #pragma unroll
     for (int bi = 0; bi < 4; ++bi) {
         const int blk = 4 * warp + bi;
@@ -557,18 +557,18 @@ int launch_score_vel_brute(dpe_ctx* c, cudaStream_t s) {
 int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S, C = c->epoch_C;
     prof_begin(c, DPE_STAGE_VELOCITY, s);
-    dim3 g2(c->nchunk, C);
+    dim3 g2(c->vnchunk, C);
     // block moments when the Doppler window is narrow enough for the 4-term Taylor bound (and the doubled phase stays
     // exact in a float), the direct evaluation otherwise
     const double x = 2.0 * 3.141592653589793 * (c->Wd + 1) * 15.5 / (double)c->n_fft;
     if (x * x * x * x / 24.0 < 2.0e-8 && c->n_fft <= (1 << 23) && !c->carr_direct)
         k_carr_partial<<<g2, 256, sizeof(float2) * 4 * c->NBd, s>>>(c->xw, c->bb, c->dc_part, c->rs, c->idx_next, c->no_flip,
-                                                                   c->ep, S, c->Wd, c->NBd, c->n_fft, c->nchunk, c->vpart);
+                                                                   c->ep, S, c->Wd, c->NBd, c->n_fft, c->vnchunk, c->nchunk, c->vpart);
     else
         k_carr_partial_direct<<<g2, 256, 0, s>>>(c->xw, c->bb, c->dc_part, c->rs, c->idx_next, c->no_flip, c->ep, S, c->Wd,
-                                                 c->NBd, c->n_fft, c->nchunk, c->vpart);
+                                                 c->NBd, c->n_fft, c->vnchunk, c->nchunk, c->vpart);
     dim3 g3(C, (c->NBd + 7) / 8);
-    k_carr_finalize<<<g3, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->nchunk, c->carr);
+    k_carr_finalize<<<g3, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->vnchunk, c->carr);
     const int nblk = (int)((c->Gv + kReduceBlock * kVelCand - 1) / (kReduceBlock * kVelCand));
     k_score_vel<<<nblk, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd,
                                               c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial, c->ticket + 3,
