@@ -425,7 +425,7 @@ k_brute(const float* __restrict__ bx, const float* __restrict__ brd,
 // the lag window carries NaN in pair_v (k_pair_bins).  WITH_SUMS = 0 (arg-max estimate): the candidate
 // states are not needed per candidate -- 8 B x C + 8 B per candidate instead of 10 B x C + 40 B.
 template <int WITH_SUMS>
-__global__ void __launch_bounds__(kReduceBlock, 6)
+__global__ void __launch_bounds__(kReduceBlock, 8)      // 64 registers: a streaming kernel, occupancy is what hides its loads
 k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
               const float2* __restrict__ pair_v, int lpower,
               int64_t G, int64_t grid_offset, double* __restrict__ scores, double* __restrict__ blk_partial,
@@ -438,11 +438,18 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     Cand p = {0, 0, 0, 0};
     if (active) {
         if (WITH_SUMS) p = cand_ecef(e, grid + 4 * j);
-#pragma unroll 4
-        for (int c = 0; c < e.C; ++c) {
-            const float2 v = __ldcs(&pair_v[(size_t)c * G + j]);   // streamed once
-            if (v.x == v.x) score += mag_pow((double)v.x, (double)v.y, lpower);
-            else ++oow;
+        // batches of 4 channels: the four streamed loads are in flight together, the sums stay in channel order
+        for (int c0 = 0; c0 < e.C; c0 += 4) {
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                v[q] = (c0 + q < e.C) ? __ldcs(&pair_v[(size_t)(c0 + q) * G + j]) : make_float2(0.f, 0.f);   // streamed once
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c0 + q >= e.C) break;
+                if (v[q].x == v[q].x) score += mag_pow((double)v[q].x, (double)v[q].y, lpower);
+                else ++oow;
+            }
         }
         __stcs(&scores[j], score);
     }

@@ -263,7 +263,8 @@ __device__ __forceinline__ void reduce_all_partials(const double* __restrict__ b
 // Estimate from per-rank partials (rank order = ascending grid offset, so "first maximum" = lowest global index, like
 // thrust::max_element / np.argmax).  partial[0..7] as block partials, [8..11] = ECEF / clock of the rank's arg-max
 // candidate.  result layout mirrors dpe_result (doubles; indices exact below 2^53).  One thread.
-__device__ __forceinline__ void finalize_estimate(const double* __restrict__ parts, int nranks, int est_mode,
+// (not inlined: it runs once per launch, in one thread of the last CTA -- inlined it cost k_score_pairs 14 registers and two of its eight CTAs per SM)
+static __device__ __noinline__ void finalize_estimate(const double* __restrict__ parts, int nranks, int est_mode,
                                                   double* __restrict__ zval, double* __restrict__ rval,
                                                   double* __restrict__ res) {
     double sum[5] = {0, 0, 0, 0, 0}, oow = 0, mx = -1.0, mi = 9.0e18;

@@ -504,10 +504,17 @@ k_score_vpairs(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep
     double score = 0.0;
     int oow = 0;
     if (active) {
-        for (int c = 0; c < e.C; ++c) {
-            const float2 v = __ldcs(&pair_v[(size_t)c * Gv + j]);
-            if (v.x == v.x) score += mag_pow((double)v.x, (double)v.y, lpower);
-            else ++oow;
+        for (int c0 = 0; c0 < e.C; c0 += 4) {
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                v[q] = (c0 + q < e.C) ? __ldcs(&pair_v[(size_t)(c0 + q) * Gv + j]) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c0 + q >= e.C) break;
+                if (v[q].x == v[q].x) score += mag_pow((double)v[q].x, (double)v[q].y, lpower);
+                else ++oow;
+            }
         }
         vscores[j] = score;
     }
