@@ -261,6 +261,11 @@ int dpe_brute_presort(dpe_ctx* ctx, int sat_mode, void* stream);
  * ascending grid_offset).  Replaces thrust::max_element + BCM_MakePosMeas or
  * BCM_ReduceAndPosMeas (batchcorrmanifold.cu:2589-2596, 1365-1510).             */
 int dpe_estimate(dpe_ctx* ctx, int est_mode, const double* gathered, int nranks, void* stream);
+/* dpe_fold_estimate: a single-GPU stage-by-stage caller (one context = the whole grid) lets dpe_score_pos write the
+ * estimate itself, in the tail of the scoring kernel -- what dpe_epoch_run does; the following
+ * dpe_estimate(ctx, est_mode, NULL, ...) with the same mode then has nothing left to launch.  est_mode = -1 turns
+ * it off again (sharded grids: the partials must be gathered first).                                            */
+int dpe_fold_estimate(dpe_ctx* ctx, int est_mode);
 
 /* Velocity-drift manifold: DC-removed carrier branch on
  * carrier bins -Wd..Wd+1 (direct DFT of the zero-padded spectrum's bins) +

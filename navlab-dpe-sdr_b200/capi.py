@@ -43,7 +43,7 @@ EXPORTS = (
     "dpe_microbench_hbm", "dpe_epoch_submit", "dpe_epoch_collect", "dpe_epoch_pending", "dpe_epoch_run_dist",
     "dpe_comm_get_unique_id", "dpe_comm_init", "dpe_comm_destroy", "dpe_comm_info", "dpe_ctx_stream",
     "dpe_kernel_attr", "dpe_epoch_set_device", "dpe_stream_create_on", "dpe_device_alloc",
-    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute")
+    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute", "dpe_fold_estimate")
 
 
 class DpeCfg(C.Structure):
@@ -104,6 +104,7 @@ def load_library(path: str | None = None):
     lib.dpe_score_pos.argtypes = [vp, i32, i32, vp]
     lib.dpe_brute_presort.argtypes = [vp, i32, vp]
     lib.dpe_estimate.argtypes = [vp, i32, vp, i32, vp]
+    lib.dpe_fold_estimate.argtypes = [vp, i32]
     lib.dpe_score_vel.argtypes = [vp, vp]
     lib.dpe_score_vel_brute.argtypes = [vp, vp]
     lib.dpe_result_fetch.argtypes = [vp, C.POINTER(DpeResult), vp]
@@ -215,6 +216,9 @@ class Context:
         g = np.ascontiguousarray(vgrid, dtype=np.float64)
         self._vgrid = g
         _check(self.lib, self.lib.dpe_vel_grid_set(self.h, _ptr(g), g.shape[0], C.c_void_p(stream)))
+
+    def fold_estimate(self, est_mode):
+        _check(self.lib, self.lib.dpe_fold_estimate(self.h, est_mode))
 
     def score_vel(self, stream=0):
         _check(self.lib, self.lib.dpe_score_vel(self.h, C.c_void_p(stream)))

@@ -156,6 +156,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     c->nranks = 1;
     c->want_sums = 1;
     c->fold_est_mode = -1;
+    c->stage_fold_est = -1;
     const size_t C = c->maxC, S = c->S, G = c->G;
 
     // epoch packet {iq | EpochDev | sat}: device copy + page-locked staging copy
@@ -538,6 +539,9 @@ int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
         DPE_CUDA(cudaEventRecord(c->ev_fork, (cudaStream_t)stream));
         c->fork_valid = 1;
     }
+    const bool fold_here = c->fold_est_mode < 0 && c->stage_fold_est >= 0;     // stage-by-stage caller asked for it (dpe_fold_estimate)
+    if (fold_here) c->fold_est_mode = c->stage_fold_est;
+    c->folded_est = c->fold_est_mode >= 0 ? c->fold_est_mode + 1 : 0;
     if (score_mode == DPE_SCORE_LOOKUP) {
         rc = launch_score_lookup(c, sat_mode, (cudaStream_t)stream);
     } else if (score_mode == DPE_SCORE_BRUTE) {
@@ -548,9 +552,10 @@ int dpe_score_pos(dpe_ctx* c, int score_mode, int sat_mode, void* stream) {
         rc = launch_score_brute(c, sat_mode, (cudaStream_t)stream);
     } else {
         set_error("bad score_mode %d", score_mode);
-        return DPE_EINVAL;
+        rc = DPE_EINVAL;
     }
-    if (rc) return rc;
+    if (fold_here) c->fold_est_mode = -1;
+    if (rc) { c->folded_est = 0; return rc; }
     c->have_scores = 1;
     return DPE_OK;
 }
@@ -582,7 +587,16 @@ int dpe_estimate(dpe_ctx* c, int est_mode, const double* gathered, int nranks, v
     DPE_REQUIRE(c->have_scores, DPE_ESTATE, "estimate before score_pos");
     DPE_REQUIRE(est_mode == DPE_EST_ARGMAX || est_mode == DPE_EST_WEIGHTED, DPE_EINVAL, "bad est_mode");
     DPE_REQUIRE(!gathered || nranks >= 1, DPE_EINVAL, "nranks must be >= 1");
+    if (!gathered && c->folded_est == est_mode + 1) return DPE_OK;     // dpe_score_pos already wrote this estimate (dpe_fold_estimate)
     return launch_estimate(c, est_mode, gathered, nranks, (cudaStream_t)stream);
+}
+
+int dpe_fold_estimate(dpe_ctx* c, int est_mode) {
+    DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(est_mode == -1 || est_mode == DPE_EST_ARGMAX || est_mode == DPE_EST_WEIGHTED, DPE_EINVAL, "bad est_mode");
+    c->stage_fold_est = est_mode;
+    c->folded_est = 0;
+    return DPE_OK;
 }
 
 int dpe_score_vel(dpe_ctx* c, void* stream) {
@@ -720,7 +734,10 @@ static int compute_epoch(dpe_ctx* c, int score_mode, int est_mode, int with_vel,
     if ((rc = dpe_correlogram(c, s))) return rc;
     c->want_sums = (est_mode == DPE_EST_WEIGHTED);     // an arg-max epoch needs no per-candidate sum s*x
     c->fold_est_mode = c->comm ? -1 : est_mode;        // one GPU: the estimate is the tail of the scoring kernel
+    const int stage_fold = c->stage_fold_est;
+    c->stage_fold_est = -1;                            // (a sharded epoch never folds, whatever dpe_fold_estimate set)
     rc = dpe_score_pos(c, score_mode, sat_mode, s);
+    c->stage_fold_est = stage_fold;
     c->want_sums = 1;
     c->fold_est_mode = -1;
     if (rc) return rc;

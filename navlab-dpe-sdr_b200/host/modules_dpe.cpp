@@ -339,6 +339,7 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
         }
         std::clog << "[" << ModuleName << "] grid sharded over " << numGPUs << " GPUs, " << per << " candidates each" << std::endl;
     }
+    DPE_CALL(dpe_fold_estimate(sh->ctx, numGPUs > 1 ? -1 : sh->est_mode));   // one GPU: the estimate is the scoring kernel's tail
     DPE_CALL(dpe_grid_set(sh->ctx, grid.data(), cfg.G, stream));
     if (cfg.Gv > 0) DPE_CALL(dpe_vel_grid_set(sh->ctx, vgrid.data(), cfg.Gv, stream));
     haveVel = cfg.Gv > 0;

@@ -179,6 +179,37 @@ def test_weighted_estimate_matches_oracle(capi):
     assert abs(res.sum_score - ref["sum_score"]) / ref["sum_score"] < 1e-7
 
 
+@pytest.mark.parametrize("est,sat,score", [("EST_ARGMAX", "SAT_MIDDLE", "SCORE_LOOKUP"), ("EST_WEIGHTED", "SAT_PER_TIME", "SCORE_LOOKUP"),
+                                           ("EST_ARGMAX", "SAT_MIDDLE", "SCORE_BRUTE")])
+def test_fold_estimate_in_the_stage_api(capi, est, sat, score):
+    """dpe_fold_estimate: the scoring kernel's last CTA writes the single-GPU estimate itself; the result block equals
+    the one of the separate k_finalize launch bit for bit, dpe_estimate then launches nothing, and a different mode asked
+    of dpe_estimate afterwards still gets its own launch."""
+    est, sat, score = getattr(capi, est), getattr(capi, sat), getattr(capi, score)
+    sc, iq, grid, ep = H.epoch_case(n=9, center_offset=(3.0, 1.0, -2.0, 4.0))
+    out = []
+    for fold in (False, True):
+        ctx = _run_prepare(capi, iq, grid, ep, flags=capi.FLAG_BRUTE_TILES)
+        if fold:
+            ctx.fold_estimate(est)
+        ctx.score_pos(score, sat)
+        n0 = ctx.launch_count()
+        ctx.estimate(est)
+        out.append((ctx.result_fetch(), ctx.launch_count() - n0, ctx.copy_out(capi.PTR_ZVAL, np.float64, 4),
+                    ctx.copy_out(capi.PTR_RVAL, np.float64, 64)))
+        if fold:
+            other = capi.EST_ARGMAX if est == capi.EST_WEIGHTED else capi.EST_WEIGHTED
+            ctx.estimate(other)
+            assert ctx.launch_count() - n0 == 1
+            ctx.fold_estimate(-1)
+        ctx.close()
+    (r0, l0, z0, rv0), (r1, l1, z1, rv1) = out
+    assert (l0, l1) == (1, 0)
+    assert list(r0.z) == list(r1.z) and r0.argmax == r1.argmax and r0.max_score == r1.max_score
+    assert r0.sum_score == r1.sum_score and r0.out_of_window == r1.out_of_window
+    assert np.array_equal(z0, z1) and np.array_equal(rv0, rv1)
+
+
 @pytest.mark.parametrize("fs,prns,n", [(2.5e6, synth.PRNS_8, 9), (2.5e6, synth.PRNS_12, 7),
                                         (10.0e6, synth.PRNS_12, 7)])
 def test_brute_force_scores_match_oracle(capi, fs, prns, n):
