@@ -169,6 +169,42 @@ def test_minimum_sizes_one_candidate_one_channel(capi):
     ctx.close()
 
 
+def test_maximum_channel_count_37(capi):
+    """DPE_MAX_CHAN = CONST_PRN_MAX = 37 channels (the 12 satellites of the ephemeris set repeated: the channel arrays,
+    the per-channel shared tables and the (PRN, lag) / (PRN, Doppler bin) bucket lists at their maximum): lookup, brute
+    force and both velocity formulations against the oracle."""
+    prns = (synth.PRNS_12 * 4)[:37]
+    sc = H.scenario(2.5e6, prns)
+    grid, tg = synth.uniform_grid(5, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(5, (0.5, 0.5, 0.5, 0.25))
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[:4] += (3.0, -2.0, 1.0, 4.0)
+    center[4:] += (0.6, -0.4, 0.2, 0.1)
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    C = len(prns)
+    assert C == 37 == sc.C
+    bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"], want_carrier=True)
+    ref = H.oracle_pos(bcs, grid, ep)
+    vref = orc.vel_meas_ml(bcs["carr_scores"], vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"], ep["time_dim"],
+                           ep["fi"], ep["doppler_sign"], ep["fs"], bcs["n_fft"])
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=C, G=grid.shape[0], time_dim=len(tg), lag_halfwidth=16,
+                       Gv=vgrid.shape[0], dopp_halfwidth=32, flags=capi.FLAG_BRUTE_TILES | capi.FLAG_BRUTE_VEL)
+    ctx.grid_set(grid)
+    ctx.vel_grid_set(vgrid)
+    for mode in (capi.SCORE_LOOKUP, capi.SCORE_BRUTE):
+        for vel in (1, 2):
+            r = ctx.epoch_run(iq, ep, score_mode=mode, with_vel=vel)
+            s = ctx.copy_out(capi.PTR_POS_SCORES, np.float64, grid.shape[0])
+            vs = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+            assert r.argmax == ref["argmax"] and r.out_of_window == 0
+            assert np.max(np.abs(s - ref["scores"]) / ref["scores"]) < RTOL
+            assert r.vel_argmax == vref["argmax"] and r.vel_out_of_window == 0
+            assert np.max(np.abs(vs - vref["scores"]) / vref["scores"]) < RTOL
+    ctx.close()
+
+
 def test_ten_megahertz_block_length_beyond_16_bits(capi):
     """S = 200000 overflows the reference's unsigned short block length (sampleblock.h:81)."""
     sc, iq, grid, ep = H.epoch_case(fs=10.0e6, prns=synth.PRNS_12, n=5, spacing=(2.0, 2.0, 2.0, 2.0))
