@@ -65,7 +65,7 @@ k_pair_bins(const double* __restrict__ grid, const EpochDev* __restrict__ ep, co
         for (int c = 0; c < e.C; ++c) {
             const SatGeo& sg = (SAT_MODE == DPE_SAT_PER_TIME) ? geo_tab[(size_t)c * T + it] : geo_mid[c];
             const double idx = code_index_fast(e, cc[c], sg, p, rel, sat + ((size_t)c * T + it) * 8, c, (double)S);
-            const Bin b = make_bin(idx, c, S, W);
+            const BinFast b = make_bin_fast(idx, c, S, W);
             pair_k[(size_t)c * G + j] = b.ok ? (int16_t)b.l : (int16_t)-1;
             pair_a[(size_t)c * G + j] = (float)b.wg;
             if (b.ok) atomicAdd(&hs[c * NB + b.l], 1);

@@ -115,6 +115,25 @@ __device__ __forceinline__ double code_index_fast(const EpochDev& e, const ChanC
 
 struct Bin { int64_t f; double wf, wg; int l; bool ok; };   // v = cs[l+1]*wg + cs[l]*wf
 
+// The same bin for the scoring kernels: the row offset S * c and the first bin of the window are formed once per launch
+// (all integers here are below 2^53, so the FP64 differences are exact and the window entry needs ONE conversion --
+// make_bin's int64 chain was 8 of the ~100 instructions per pair).  Identical l / wg / wf / ok by construction;
+// k_debug_bins keeps make_bin, and test_code_phase_bins_bit_exact compares the scores' bins with it.
+struct BinFast { double wf, wg; int l; bool ok; };
+__device__ __forceinline__ BinFast make_bin_fast(double idx_base, int c, int S, int W) {
+    const double off = (double)((int64_t)S * c);                 // loop-invariant per channel: hoisted
+    const double lbase = off + (double)(S / 2 - W);
+    BinFast b;
+    const bool valid = (idx_base < (double)S) && (idx_base > 0.0);
+    const double idxo = idx_base + off;
+    const double f = floor(idxo), g = floor(idxo + 1.0);
+    b.wg = idxo - f;
+    b.wf = g - idxo;
+    b.l = (int)(f - lbase);                                      // saturating; NaN -> 0 with valid = false
+    b.ok = valid && b.l >= 0 && b.l <= 2 * W;
+    return b;
+}
+
 // batchcorrmanifold.cu:1795-1812 (row offset S*chan added before the floor, as there)
 __device__ __forceinline__ Bin make_bin(double idx_base, int c, int S, int W) {
     Bin b;
@@ -131,21 +150,33 @@ __device__ __forceinline__ Bin make_bin(double idx_base, int c, int S, int W) {
 }
 
 // sqrt(s) from the FP32 reciprocal square root (MUFU.RSQ) and ONE FP64 Newton step: the seed is good to 1.2e-7, the
-// step squares that -- 2e-14 relative, against 1.1e-16 for the IEEE sqrt (7 more FP64 instructions and a branch per
-// pair on a part whose FP64 pipe is what bounds the scoring kernels).  Outside the FP32 range: the IEEE sqrt.
+// step squares that -- 2e-14 relative, against 1.1e-16 for the IEEE sqrt (7 more FP64 instructions and a conditional
+// call per pair on a part whose FP64 pipe is what bounds the scoring kernels).  Branch-free, so that the chains of a
+// thread's candidates interleave: s = 0 gives 0; below 1e-30 (a squared correlation of int16 samples is either 0 or
+// far above) the clamped seed only bounds the result by 1e-15; above 1e37 is out of reach (|corr| < 1e11).
 __device__ __forceinline__ double sqrt_newton(double s) {
-    const float sf = (float)s;
-    if (__builtin_expect(!(sf > 1.0e-30f && sf < 1.0e37f), 0)) return sqrt(s);
-    const double y = (double)rsqrtf(sf);
+    const double y = (double)rsqrtf(fmaxf((float)s, 1.0e-30f));
     const double m = s * y;
     return fma(0.5 * y, fma(-m, m, s), m);
 }
+
+// LP1 = true: the exponent is known to be 1 (the reference's default LPower): no test, no pow() call in the instruction
+// stream -- the kernels that score several candidates per thread are instantiated for it, so that nothing but
+// straight-line code separates the chains of the candidates
+template <bool LP1>
+__device__ __forceinline__ double mag_pow_t(double re, double im, int L);
 
 __device__ __forceinline__ double mag_pow(double re, double im, int L) {
     const double m = sqrt_newton(re * re + im * im);
     if (L == 1) return m;
     if (L == 2) return m * m;
     return pow(m, (double)L);
+}
+
+template <bool LP1>
+__device__ __forceinline__ double mag_pow_t(double re, double im, int L) {
+    if (LP1) return sqrt_newton(re * re + im * im);
+    return mag_pow(re, im, L);
 }
 
 // Block-level reduction of (score-weighted sums, sum, max/argmax, out-of-window)

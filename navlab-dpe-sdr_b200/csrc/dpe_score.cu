@@ -27,7 +27,7 @@ namespace dpe {
 // 763 CTAs on 592 slots -- 1.29 waves, the second one 29 % full -- while 6 per thread is 509 CTAs: one wave.
 // (Tried: 64-thread CTAs, 8 per SM, so that the 0.86 wave spreads 6-7 CTAs instead of 3-4 over every SM: 41.6 us against
 // 37.5 -- the finer spread does not pay for twice the prologues and block partials.)
-template <int SAT_MODE, int WITH_SUMS, int kLkCand>
+template <int SAT_MODE, int WITH_SUMS, int kLkCand, bool LP1>
 __global__ void __launch_bounds__(kReduceBlock, (kLkCand == 3) ? 8 : 4)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
                const double2* __restrict__ cs, double fs, int S, int W, int NL, int T, int lpower,
@@ -90,12 +90,12 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         }
 #pragma unroll
         for (int k = 0; k < kLkCand; ++k) {
-            const Bin b = make_bin(idx[k], c, S, W);
+            const BinFast b = make_bin_fast(idx[k], c, S, W);
             const int l = min(max(b.l, 0), NL - 2);              // clamped: the loads are unconditional
             const double2 lo = csc[l], hi = csc[l + 1];
             const double re = hi.x * b.wg + lo.x * b.wf;         // :1808-1812
             const double im = hi.y * b.wg + lo.y * b.wf;
-            const double m = mag_pow(re, im, lpower);            // :1816
+            const double m = mag_pow_t<LP1>(re, im, lpower);     // :1816
             const bool use = b.ok && act[k];
             score[k] += use ? m : 0.0;
             oow += (act[k] && !b.ok) ? 1 : 0;
@@ -174,6 +174,15 @@ int launch_sat_geo(dpe_ctx* c, cudaStream_t s) {
     return DPE_OK;
 }
 
+template <int SAT_MODE, int WITH_SUMS, int NC>
+static void launch_lk(dpe_ctx* c, int nblk, const SatGeo* tab, const FoldEst& fold, cudaStream_t s) {
+#define DPE_LK_ARGS c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G, \
+                    c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab, fold
+    if (c->cfg.lpower == 1) k_score_lookup<SAT_MODE, WITH_SUMS, NC, true><<<nblk, kReduceBlock, 0, s>>>(DPE_LK_ARGS);
+    else k_score_lookup<SAT_MODE, WITH_SUMS, NC, false><<<nblk, kReduceBlock, 0, s>>>(DPE_LK_ARGS);
+#undef DPE_LK_ARGS
+}
+
 int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
     // candidates per thread: the choice that wastes the least of its last wave (ties: more per thread)
     static const int kNc[3] = {3, 4, 6}, kOcc[3] = {8, 4, 4};
@@ -198,14 +207,11 @@ int launch_score_lookup(dpe_ctx* c, int sat_mode, cudaStream_t s) {
         if (rc) return rc;
         tab = reinterpret_cast<const SatGeo*>(c->sat_geo);
     }
-#define DPE_LK(SM, WS, NC) k_score_lookup<SM, WS, NC><<<nblk, kReduceBlock, 0, s>>>(                                \
-        c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G,              \
-        c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab, fold)
-#define DPE_LK_NC(SM, WS) do { if (nc == 3) DPE_LK(SM, WS, 3); else if (nc == 6) DPE_LK(SM, WS, 6); else DPE_LK(SM, WS, 4); } while (0)
+#define DPE_LK_NC(SM, WS) do { if (nc == 3) launch_lk<SM, WS, 3>(c, nblk, tab, fold, s); else if (nc == 6) launch_lk<SM, WS, 6>(c, nblk, tab, fold, s); \
+                               else launch_lk<SM, WS, 4>(c, nblk, tab, fold, s); } while (0)
     if (sat_mode == DPE_SAT_PER_TIME) { if (c->want_sums) DPE_LK_NC(DPE_SAT_PER_TIME, 1); else DPE_LK_NC(DPE_SAT_PER_TIME, 0); }
     else { if (c->want_sums) DPE_LK_NC(DPE_SAT_MIDDLE, 1); else DPE_LK_NC(DPE_SAT_MIDDLE, 0); }
 #undef DPE_LK_NC
-#undef DPE_LK
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     c->n_blk_partial = nblk;
@@ -240,9 +246,9 @@ int launch_debug_bins(dpe_ctx* c, int64_t i0, int64_t n, int sat_mode, cudaStrea
 }
 
 int kernel_attr_score(const char* name, cudaFuncAttributes* a) {
-    DPE_KATTR("k_score_lookup", (k_score_lookup<DPE_SAT_MIDDLE, 0, 4>));
-    DPE_KATTR("k_score_lookup_3", (k_score_lookup<DPE_SAT_MIDDLE, 0, 3>));
-    DPE_KATTR("k_score_lookup_6", (k_score_lookup<DPE_SAT_MIDDLE, 0, 6>));
+    DPE_KATTR("k_score_lookup", (k_score_lookup<DPE_SAT_MIDDLE, 0, 4, true>));
+    DPE_KATTR("k_score_lookup_3", (k_score_lookup<DPE_SAT_MIDDLE, 0, 3, true>));
+    DPE_KATTR("k_score_lookup_6", (k_score_lookup<DPE_SAT_MIDDLE, 0, 6, true>));
     DPE_KATTR("k_finalize", k_finalize);
     return 0;
 }

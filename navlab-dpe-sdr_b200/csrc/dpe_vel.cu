@@ -270,6 +270,7 @@ __device__ __forceinline__ VelCand vel_cand(const EpochDev& e, const double* __r
 // them so that their FP64 chains interleave -- one candidate per thread left the kernel at 45 us for 25^4 candidates,
 // latency bound, with the per-CTA prologue (EpochDev copy, lines of sight) paid once per 128 candidates.
 constexpr int kVelCand = 6;
+template <bool LP1>
 __global__ void __launch_bounds__(kReduceBlock, 4)
 k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
@@ -305,7 +306,7 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
             double wg, wf;
             const bool ok = vel_bin(u, vc[k], scale, half, nf, NBd, &l, &wg, &wf);
             const double2 lo = cc[l], hi = cc[l + 1];                 // l = 0 when not ok: the loads are unconditional
-            const double m = mag_pow(hi.x * wg + lo.x * wf, hi.y * wg + lo.y * wf, lpower);
+            const double m = mag_pow_t<LP1>(hi.x * wg + lo.x * wf, hi.y * wg + lo.y * wf, lpower);
             score[k] += (ok && act[k]) ? m : 0.0;
             oow += (act[k] && !ok) ? 1 : 0;
         }
@@ -577,9 +578,11 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     dim3 g3(C, (c->NBd + 7) / 8);
     k_carr_finalize<<<g3, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->vnchunk, c->carr);
     const int nblk = (int)((c->Gv + kReduceBlock * kVelCand - 1) / (kReduceBlock * kVelCand));
-    k_score_vel<<<nblk, kReduceBlock, 0, s>>>(c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd,
-                                              c->T, c->cfg.lpower, c->Gv, c->vscores, c->vblk_partial, c->ticket + 3,
-                                              c->vgrid, c->zval, c->rval, c->result);
+#define DPE_VEL_ARGS c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd, c->T, c->cfg.lpower, c->Gv, c->vscores, \
+                     c->vblk_partial, c->ticket + 3, c->vgrid, c->zval, c->rval, c->result
+    if (c->cfg.lpower == 1) k_score_vel<true><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+    else k_score_vel<false><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+#undef DPE_VEL_ARGS
     c->launches += 3;
     prof_end(c, s);
     DPE_CUDA(cudaGetLastError());
@@ -590,7 +593,7 @@ int kernel_attr_vel(const char* name, cudaFuncAttributes* a) {
     DPE_KATTR("k_carr_partial", k_carr_partial);
     DPE_KATTR("k_carr_partial_direct", k_carr_partial_direct);
     DPE_KATTR("k_carr_finalize", k_carr_finalize);
-    DPE_KATTR("k_score_vel", k_score_vel);
+    DPE_KATTR("k_score_vel", k_score_vel<true>);
     DPE_KATTR("k_brute_vel", k_brute_vel);
     DPE_KATTR("k_vel_pair_bins", k_vel_pair_bins);
     DPE_KATTR("k_vel_plane", k_vel_plane);
