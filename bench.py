@@ -494,6 +494,18 @@ def run_ours(args):
     except Exception:
         pass
     fp32_peak = capi.microbench_fp32(rig.local, True)              # FFMA2 stream, measured in this run
+    if main.get("other_path") and main["other_path"]["path"] == "lookup":
+        # the lookup formulation is bound by the FP64 pipe's latency, not by HBM: report it against the DFMA rate measured here
+        o = main["other_path"]
+        fp64_peak = capi.microbench_fp64(rig.local)
+        slots = 37.0 * (config_for(args)["candidates"] // rig.world) * config_for(args)["prns"]   # FP64-pipe instructions of k_score_lookup's loop, per pair (SASS)
+        k_ms = (main.get("lookup_kernel_ms") or o["ms_per_step"])
+        o["fp64_pipe"] = dict(peak_tflops=fp64_peak, fp64_instructions_per_pair=37,
+                              achieved_tflops_equiv=2.0 * slots / (o["ms_per_step"] * 1e-3) / 1e12,
+                              frac_of_epoch=2.0 * slots / (o["ms_per_step"] * 1e-3) / 1e12 / fp64_peak,
+                              note="k_score_lookup executes 37 FP64-pipe instructions per (candidate, PRN) pair (static SASS count of its "
+                                   "loop); counted as FMA slots (2 FLOP) over the pipelined epoch time against the DFMA stream measured "
+                                   "in this run -- the kernel is latency bound (ncu: FP64 pipe 28 % active while it runs)")
     cfg = config_for(args)
     S = cfg["S"]
     roofline = roofline_of(main, S, main["clocks"], peaks, fp32_peak)

@@ -393,6 +393,7 @@ int64_t dpe_brute_pairs(dpe_ctx* ctx);
  * fp32: dependent-free FFMA2 streams on every SM; returns achieved TFLOP/s.
  * hbm : device copy of `bytes`; returns GB/s (read+write).                       */
 int dpe_microbench_fp32(int device, int use_ffma2, double* tflops);
+int dpe_microbench_fp64(int device, double* tflops);      /* DFMA stream: the pipe that bounds the lookup-path scoring kernels */
 int dpe_microbench_hbm(int device, size_t bytes, double* gbs);
 
 #ifdef __cplusplus

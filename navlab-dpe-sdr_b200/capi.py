@@ -43,7 +43,7 @@ EXPORTS = (
     "dpe_microbench_hbm", "dpe_epoch_submit", "dpe_epoch_collect", "dpe_epoch_pending", "dpe_epoch_run_dist",
     "dpe_comm_get_unique_id", "dpe_comm_init", "dpe_comm_destroy", "dpe_comm_info", "dpe_ctx_stream",
     "dpe_kernel_attr", "dpe_epoch_set_device", "dpe_stream_create_on", "dpe_device_alloc",
-    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute", "dpe_fold_estimate")
+    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute", "dpe_fold_estimate", "dpe_microbench_fp64")
 
 
 class DpeCfg(C.Structure):
@@ -133,6 +133,7 @@ def load_library(path: str | None = None):
     lib.dpe_kernel_attr.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dpe_microbench_fp32.argtypes = [i32, i32, C.POINTER(C.c_double)]
     lib.dpe_microbench_hbm.argtypes = [i32, C.c_size_t, C.POINTER(C.c_double)]
+    lib.dpe_microbench_fp64.argtypes = [i32, C.POINTER(C.c_double)]
     if path is None:
         _lib = lib
     return lib
@@ -390,6 +391,13 @@ def microbench_fp32(device=0, use_ffma2=True) -> float:
     lib = load_library()
     v = C.c_double()
     _check(lib, lib.dpe_microbench_fp32(device, 1 if use_ffma2 else 0, C.byref(v)))
+    return v.value
+
+
+def microbench_fp64(device=0) -> float:
+    lib = load_library()
+    v = C.c_double()
+    _check(lib, lib.dpe_microbench_fp64(device, C.byref(v)))
     return v.value
 
 

@@ -41,6 +41,24 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a
     if (s == 12345.678f) out[0] = s;   // keep the chains alive
 }
 
+// FP64 pipe: 16 independent DFMA chains per thread (the lookup-path scoring kernels are bound by this pipe)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 12345.678) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) k_copy(const float4* __restrict__ a, float4* __restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -72,6 +90,34 @@ extern "C" int dpe_microbench_fp32(int device, int use_ffma2, double* tflops) {
         float ms;
         DPE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         const double flops = (double)blocks * 256 * iters * 4 * 16 * 2 * 2;   // 2 lanes x (mul+add)
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return DPE_OK;
+}
+
+extern "C" int dpe_microbench_fp64(int device, double* tflops) {
+    if (!tflops) { set_error("null argument"); return DPE_EINVAL; }
+    DPE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DPE_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* out;
+    DPE_CUDA(cudaMalloc(&out, 64));
+    const int iters = 512, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    DPE_CUDA(cudaEventCreate(&e0));
+    DPE_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        DPE_CUDA(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, 256>>>(out, iters, 0.999, 1e-3);
+        DPE_CUDA(cudaEventRecord(e1));
+        DPE_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        DPE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)blocks * 256 * iters * 4 * 16 * 2;
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
