@@ -499,7 +499,6 @@ def run_ours(args):
         o = main["other_path"]
         fp64_peak = capi.microbench_fp64(rig.local)
         slots = 37.0 * (config_for(args)["candidates"] // rig.world) * config_for(args)["prns"]   # FP64-pipe instructions of k_score_lookup's loop, per pair (SASS)
-        k_ms = (main.get("lookup_kernel_ms") or o["ms_per_step"])
         o["fp64_pipe"] = dict(peak_tflops=fp64_peak, fp64_instructions_per_pair=37,
                               achieved_tflops_equiv=2.0 * slots / (o["ms_per_step"] * 1e-3) / 1e12,
                               frac_of_epoch=2.0 * slots / (o["ms_per_step"] * 1e-3) / 1e12 / fp64_peak,
