@@ -433,6 +433,39 @@ def side_kernel_report(capi):
     return rep
 
 
+def ncu_traffic(workload, timeout_s=150):
+    """DRAM bytes of ONE k_brute launch, measured now: a child process (scripts/brute_probe.py on the same workload) under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`, outside every timed region.  None when ncu is not
+    available or refuses (no permission for the counters): the caller then falls back to the committed capture."""
+    import shutil
+    import subprocess
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "-k", "k_brute", "-s", "1", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "scripts", "brute_probe.py"), workload]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout_s, cwd=ROOT)
+    except Exception:
+        return None
+    rd = wr = None
+    for line in r.stdout.splitlines():
+        if "dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line:
+            try:
+                val = float(line.rstrip().rstrip('"').split('"')[-1].replace(",", ""))
+            except ValueError:
+                continue
+            if "dram__bytes_read.sum" in line:
+                rd = val
+            else:
+                wr = val
+    if rd is None or wr is None:
+        return None
+    return dict(dram_read=rd, dram_write=wr, dram_bytes_per_launch=rd + wr,
+                source="ncu child process of this bench run (scripts/brute_probe.py %s, second k_brute launch): "
+                       "dram__bytes_read.sum + dram__bytes_write.sum" % workload)
+
+
 def roofline_of(m, S, clocks, peaks, fp32_peak):
     if "k_brute" in m:
         kb = m["k_brute"]
@@ -508,6 +541,11 @@ def run_ours(args):
     cfg = config_for(args)
     S = cfg["S"]
     roofline = roofline_of(main, S, main["clocks"], peaks, fp32_peak)
+    if rig.world == 1 and args.path == "brute" and args.ncu_traffic:
+        tr = ncu_traffic(args.workload)                            # measured in this run, outside the timed regions
+        if tr:
+            roofline["traffic"], roofline["traffic_note"] = tr["dram_bytes_per_launch"], tr["source"]
+            roofline["traffic_read_write"] = [tr["dram_read"], tr["dram_write"]]
     if rig.world == 1 and args.workload == "demo" and args.vel_brute:
         try:
             vel_brute = velocity_brute_leg(rig, args, fp32_peak)
@@ -745,6 +783,8 @@ def main():
     ap.add_argument("--both", action="store_true", default=True, help="also time the other scoring path")
     ap.add_argument("--no-both", dest="both", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ncu-traffic", dest="ncu_traffic", action="store_false", default=True,
+                    help="do not measure roofline.traffic with an ncu child process (1 GPU); use the committed capture")
     ap.add_argument("--no-vel-brute", dest="vel_brute", action="store_false", default=True,
                     help="skip the brute-force velocity manifold leg (1 GPU, demo)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

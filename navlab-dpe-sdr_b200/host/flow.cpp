@@ -1,5 +1,7 @@
 #include "flow.h"
 #include <chrono>
+#include <vector>
+#include <cstdlib>
 #include <iostream>
 #include "../../include/dpe_b200.h"
 
@@ -109,10 +111,18 @@ void Flow::FlowThread(long maxEpochs) {
     double total_us = 0;
     stats = FlowStats();
     stats.min_us = 1e300;
+    // DPE_FLOW_PROFILE=1: host time spent inside each module's Update (an asynchronous module only enqueues; the module
+    // that fetches a result pays for the GPU work it waits on)
+    const char* pf = getenv("DPE_FLOW_PROFILE");
+    const bool profile = pf && pf[0] == '1';
+    std::vector<double> mod_us(Mods.size() + 1, 0.0);
     while (KeepRunning && (maxEpochs < 0 || (long)stats.runCount < maxEpochs)) {
         bool failed = false;
         for (size_t i = 0; i < Mods.size(); ++i) {
-            if (Mods[i]->Update((void*)&cuStream)) {
+            const clk::time_point t_mod = profile ? clk::now() : clk::time_point();
+            const int rc_mod = Mods[i]->Update((void*)&cuStream);
+            if (profile) mod_us[i] += std::chrono::duration<double, std::micro>(clk::now() - t_mod).count();
+            if (rc_mod) {
                 std::cerr << "[Flow] " << Mods[i]->GetModuleName() << "->Update() Failed. \nStopping Flow." << std::endl;
                 failed = true;
                 break;
@@ -138,6 +148,9 @@ void Flow::FlowThread(long maxEpochs) {
               << "[Flow] Max block duration = " << stats.max_us << " us, run count = " << stats.maxCount << std::endl
               << "[Flow] Min block duration = " << stats.min_us << " us, run count = " << stats.minCount << std::endl
               << "[Flow] Total time = " << stats.total_s << " seconds." << std::endl;
+    if (profile && stats.runCount)
+        for (size_t i = 0; i < Mods.size(); ++i)
+            std::clog << "[Flow] profile: " << Mods[i]->GetModuleName() << " " << mod_us[i] / stats.runCount << " us per epoch" << std::endl;
     FlowDone = true;
 }
 
