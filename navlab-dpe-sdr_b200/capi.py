@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdpe_b200.so")
+LIB_PATH = os.environ.get("DPE_B200_LIB") or os.path.join(_HERE, "lib", "libdpe_b200.so")   # DPE_B200_LIB: another build of the library (A/B of kernel variants)
 
 DPE_MAX_CHAN = 37
 DPE_ABI_VERSION = 2

@@ -26,7 +26,8 @@ namespace dpe {
 // launcher picks the one whose CTA count fills whole waves best: at the demo size (390 625 candidates) 4 per thread is
 // 763 CTAs on 592 slots -- 1.29 waves, the second one 29 % full -- while 6 per thread is 509 CTAs: one wave.
 // (Tried: 64-thread CTAs, 8 per SM, so that the 0.86 wave spreads 6-7 CTAs instead of 3-4 over every SM: 41.6 us against
-// 37.5 -- the finer spread does not pay for twice the prologues and block partials.)
+// 37.5 -- the finer spread does not pay for twice the prologues and block partials.  Tried: 6 candidates per thread at 96 /
+// 80 registers, 5 / 6 CTAs per SM: 37.3 / 39.4 us against 33.5 -- the spills cost more than the extra warps hide.)
 template <int SAT_MODE, int WITH_SUMS, int kLkCand, bool LP1>
 __global__ void __launch_bounds__(kReduceBlock, (kLkCand == 3) ? 8 : 4)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
