@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, call W (1 GPU): the evidence run of the final tree -- full GPU tests, smoke, default bench, reference arm, launch lists,
+# round 2, call Y (1 GPU): the evidence run of the final tree -- full GPU tests, smoke, default bench, reference arm, launch lists,
 # ncu --set full of k_brute, the side kernels, the lookup-path kernels and the velocity kernels
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-O=gpurun_out/r2w; mkdir -p $O
+O=gpurun_out/r2y; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; tail -5 $O/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -5 $O/smoke.log
 timeout 600 python bench.py > $O/bench_demo_n1.json 2> $O/bench_demo_n1.err; tail -2 $O/bench_demo_n1.err
@@ -22,7 +22,7 @@ for f in k_brute_demo side_kernels lookup_kernels; do python scripts/ncu_summary
 head -30 $O/k_brute_demo_ncu_summary.txt
 python - <<'PY'
 import json
-for l in open('gpurun_out/r2w/bench_demo_n1.json'):
+for l in open('gpurun_out/r2y/bench_demo_n1.json'):
     if l.startswith('{'):
         d=json.loads(l)
         print('ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['ms_per_step'], 'frac', d['roofline']['frac'], 'launches/epoch', d['gpu_launches_per_epoch'])
