@@ -205,6 +205,49 @@ def test_maximum_channel_count_37(capi):
     ctx.close()
 
 
+@pytest.mark.parametrize("case", range(8))
+def test_randomised_epochs_against_the_oracle(capi, case):
+    """Eight seeded draws of everything an epoch is made of -- receiver seed and C/N0, the PRN subset (3..12 channels, in a
+    shuffled order), the block, an IRREGULAR grid (not a lattice: every candidate drawn on its own, so buckets are ragged
+    and lags / fractions arbitrary), the offset of the grid centre, the lag window, the estimator, LPower -- through
+    lookup and brute force, weighted or arg-max, against the oracle: scores <= 1e-5, identical arg-max, the fix."""
+    rng = np.random.RandomState(1000 + case)
+    prns = list(synth.PRNS_12)
+    rng.shuffle(prns)
+    prns = tuple(prns[:int(rng.randint(3, 13))])
+    sc = H.scenario(2.5e6, prns, seed=20180704 + 17 * case, cn0=float(rng.uniform(38.0, 50.0)))
+    block = int(rng.randint(0, 4))
+    G = int(rng.randint(200, 3000))
+    spread = rng.uniform(5.0, 120.0)
+    grid = np.ascontiguousarray(rng.uniform(-spread, spread, size=(G, 4)))
+    grid[int(rng.randint(0, G))] = 0.0                             # the centre itself is a candidate
+    T = int(rng.choice([1, 5, 9]))
+    tg = np.sort(rng.uniform(-spread, spread, size=T))
+    rx_time = sc.cfg.rx_time0 + (block + 1) * sc.cfg.T
+    center = sc.rx_state(rx_time).copy()
+    center[:4] += rng.uniform(-30.0, 30.0, size=4)
+    ep = sc.epoch_inputs(block, center=center, time_grid=tg)
+    iq = sc.block(block)
+    lpower = int(rng.choice([1, 1, 2, 3]))
+    weighted = bool(rng.randint(0, 2))
+    W_ = int(rng.choice([8, 16, 32]))
+    bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"])
+    ref = H.oracle_pos(bcs, grid, ep, lpower=lpower, weighted=weighted, per_time=weighted)
+    ctx = capi.Context(fs=ep["fs"], S=ep["S"], max_chan=len(prns), G=G, time_dim=T, lpower=lpower, lag_halfwidth=W_,
+                       flags=capi.FLAG_BRUTE_TILES)
+    ctx.grid_set(grid)
+    est = capi.EST_WEIGHTED if weighted else capi.EST_ARGMAX
+    for mode in (capi.SCORE_LOOKUP, capi.SCORE_BRUTE):
+        r, s_ = _scores(capi, ctx, iq, ep, mode, G, est)
+        assert r.out_of_window == 0
+        assert np.max(np.abs(s_ - ref["scores"]) / ref["scores"]) < RTOL, (case, mode)
+        assert r.argmax == int(np.argmax(ref["scores"]))
+        dz = np.abs(np.array(r.z[:4]) - ref["z"])
+        assert dz[:3].max() < (1e-3 if weighted else 1e-9) and dz[3] < (1e-3 if weighted else 1e-9), (case, mode, dz)
+    ctx.close()
+
+
 def test_ten_megahertz_block_length_beyond_16_bits(capi):
     """S = 200000 overflows the reference's unsigned short block length (sampleblock.h:81)."""
     sc, iq, grid, ep = H.epoch_case(fs=10.0e6, prns=synth.PRNS_12, n=5, spacing=(2.0, 2.0, 2.0, 2.0))
