@@ -272,6 +272,11 @@ int dpe_fold_estimate(dpe_ctx* ctx, int est_mode);
  * BCM_VelMeasML + BCM_MakeVelMeas (batchcorrscores.cu:1158-1180,
  * batchcorrmanifold.cu:1861-1963,2030-2068).  Fills zVal[4:8].                   */
 int dpe_score_vel(dpe_ctx* ctx, void* stream);
+/* dpe_score_vel_est: the same manifold with the estimator chosen -- DPE_EST_ARGMAX (what dpe_score_vel does) or
+ * DPE_EST_WEIGHTED, the reference's dormant BCM_VelMeasReduction + BCM_ReduceAndVelMeas (batchcorrmanifold.cu:1090-1347,
+ * 1525-1667): zVal[4:8] = sum_i score_i v_i / sum_i score_i over the ECEF velocity candidates.  In dpe_epoch_run /
+ * dpe_epoch_submit: with_vel = 3.                                                                                */
+int dpe_score_vel_est(dpe_ctx* ctx, int est_mode, void* stream);
 /* dpe_score_vel_brute: the same fix with every (velocity candidate, PRN) pair correlating the whole block against its
  * own BLENDED carrier (1 - a) exp(-j 2 pi n m / N_c) + a exp(-j 2 pi n (m+1) / N_c) -- SURVEY.md section 8 a', last
  * sentence; by linearity equal to the lerp of two CarrScores bins (batchcorrmanifold.cu:1950-1958) to rounding.

@@ -43,7 +43,7 @@ EXPORTS = (
     "dpe_microbench_hbm", "dpe_epoch_submit", "dpe_epoch_collect", "dpe_epoch_pending", "dpe_epoch_run_dist",
     "dpe_comm_get_unique_id", "dpe_comm_init", "dpe_comm_destroy", "dpe_comm_info", "dpe_ctx_stream",
     "dpe_kernel_attr", "dpe_epoch_set_device", "dpe_stream_create_on", "dpe_device_alloc",
-    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute", "dpe_fold_estimate", "dpe_microbench_fp64")
+    "dpe_device_free", "dpe_copy_h2d", "dpe_score_vel_brute", "dpe_fold_estimate", "dpe_microbench_fp64", "dpe_score_vel_est")
 
 
 class DpeCfg(C.Structure):
@@ -107,6 +107,7 @@ def load_library(path: str | None = None):
     lib.dpe_fold_estimate.argtypes = [vp, i32]
     lib.dpe_score_vel.argtypes = [vp, vp]
     lib.dpe_score_vel_brute.argtypes = [vp, vp]
+    lib.dpe_score_vel_est.argtypes = [vp, i32, vp]
     lib.dpe_result_fetch.argtypes = [vp, C.POINTER(DpeResult), vp]
     lib.dpe_epoch_run.argtypes = [vp, vp, C.POINTER(DpeEpoch), vp, i32, i32, i32, C.POINTER(DpeResult), vp]
     lib.dpe_dev_ptr.argtypes = [vp, i32]
@@ -223,6 +224,9 @@ class Context:
 
     def score_vel(self, stream=0):
         _check(self.lib, self.lib.dpe_score_vel(self.h, C.c_void_p(stream)))
+
+    def score_vel_est(self, est_mode, stream=0):
+        _check(self.lib, self.lib.dpe_score_vel_est(self.h, est_mode, C.c_void_p(stream)))
 
     def score_vel_brute(self, stream=0):
         _check(self.lib, self.lib.dpe_score_vel_brute(self.h, C.c_void_p(stream)))

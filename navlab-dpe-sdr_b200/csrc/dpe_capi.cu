@@ -599,9 +599,13 @@ int dpe_fold_estimate(dpe_ctx* c, int est_mode) {
     return DPE_OK;
 }
 
-int dpe_score_vel(dpe_ctx* c, void* stream) {
+int dpe_score_vel(dpe_ctx* c, void* stream) { return dpe_score_vel_est(c, DPE_EST_ARGMAX, stream); }
+
+int dpe_score_vel_est(dpe_ctx* c, int est_mode, void* stream) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
+    DPE_REQUIRE(est_mode == DPE_EST_ARGMAX || est_mode == DPE_EST_WEIGHTED, DPE_EINVAL, "bad est_mode");
     DevGuard guard(c->cfg.device);
+    c->vel_weighted = (est_mode == DPE_EST_WEIGHTED);
     DPE_REQUIRE(c->Gv > 0 && c->have_vgrid, DPE_ESTATE, "score_vel without a velocity grid");
     DPE_REQUIRE(c->have_prepare && c->have_corr, DPE_ESTATE, "score_vel before replica_prepare / correlogram");
     DPE_REQUIRE(c->have_epoch & DPE_PART_GEOMETRY, DPE_ESTATE, "score_vel before the geometry part of epoch_set");
@@ -659,7 +663,8 @@ static int upload_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, cons
     DPE_REQUIRE(score_mode != DPE_SCORE_BRUTE || (c->cfg.flags & DPE_FLAG_BRUTE_TILES), DPE_ESTATE,
                 "context created without DPE_FLAG_BRUTE_TILES");
     DPE_REQUIRE(!with_vel || (c->Gv > 0 && c->have_vgrid), DPE_ESTATE, "velocity manifold requested without a velocity grid");
-    DPE_REQUIRE(with_vel >= 0 && with_vel <= 2, DPE_EINVAL, "with_vel: 0 none, 1 lookup, 2 brute force");
+    DPE_REQUIRE(with_vel >= 0 && with_vel <= 3, DPE_EINVAL,
+                "with_vel: 0 none, 1 lookup (arg-max), 2 brute force (arg-max), 3 lookup (score-weighted mean)");
     const bool root = !c->comm || c->rank == 0;
     const int C = ep->C;
     const size_t sat_bytes = sizeof(double) * 8 * (size_t)C * c->T;
@@ -746,7 +751,7 @@ static int compute_epoch(dpe_ctx* c, int score_mode, int est_mode, int with_vel,
         if ((rc = launch_estimate(c, est_mode, c->gathered, c->nranks, s))) return rc;
     }
     if (with_vel == 2) { if ((rc = dpe_score_vel_brute(c, s))) return rc; }
-    else if (with_vel && (rc = dpe_score_vel(c, s))) return rc;
+    else if (with_vel && (rc = dpe_score_vel_est(c, with_vel == 3 ? DPE_EST_WEIGHTED : DPE_EST_ARGMAX, s))) return rc;
     return DPE_OK;
 }
 

@@ -132,6 +132,7 @@ struct dpe_ctx {
     int64_t vmax_groups; int vel_attr_set;
     int stage_fold_est, folded_est;    // dpe_fold_estimate's mode (-1 = off); est_mode + 1 of the estimate the last dpe_score_pos wrote, 0 = none
     int fold_est_mode;                 // >= 0: the scoring kernel's last CTA also writes the single-rank estimate (dpe_epoch_*)
+    int vel_weighted;                  // the next launch_score_vel forms the score-weighted estimate (dpe_score_vel_est)
     int carr_direct;                   // debug switch: evaluate the carrier spectrum directly (k_carr_partial_direct)
     int32_t Wd, NBd, n_fft; int have_vgrid;
     // state

@@ -193,17 +193,20 @@ k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ 
 }
 
 // arg-max over all block partials + BCM_MakeVelMeas (all threads of the last CTA)
+// (weighted: BCM_ReduceAndVelMeas, batchcorrmanifold.cu:1658-1661 -- z = sum s v / sum s)
 __device__ __forceinline__ void finish_velocity(const double* __restrict__ blk_partial, int n_blk, const EpochDev& e,
                                                 const double* __restrict__ vgrid_all, double* __restrict__ zval,
-                                                double* __restrict__ rval, double* __restrict__ res) {
+                                                double* __restrict__ rval, double* __restrict__ res, bool weighted = false) {
     double r[8];
     reduce_all_partials(blk_partial, n_blk, r);
     if (threadIdx.x == 0) {
         const int64_t jm = (int64_t)r[6];
         const double* g = vgrid_all + 4 * jm;
-        const double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
-                             e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
-                             e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
+        double z[4] = {e.R[0] * g[0] + e.R[1] * g[1] + e.R[2] * g[2] + e.center[4],
+                       e.R[3] * g[0] + e.R[4] * g[1] + e.R[5] * g[2] + e.center[5],
+                       e.R[6] * g[0] + e.R[7] * g[1] + e.R[8] * g[2] + e.center[6], g[3] + e.center[7]};
+        if (weighted)
+            for (int k = 0; k < 4; ++k) z[k] = r[k] / r[4];
         for (int k = 0; k < 4; ++k) { zval[4 + k] = z[k]; res[4 + k] = z[k]; }
         for (int rr = 4; rr < 8; ++rr)
             for (int k = 0; k < 8; ++k) rval[rr * 8 + k] = (rr == k) ? 1.0 : 0.0;
@@ -271,8 +274,10 @@ __device__ __forceinline__ VelCand vel_cand(const EpochDev& e, const double* __r
 // (sum of scores, max, argmax, out-of-window).  kVelCand candidates per thread (j = base + tid + 128 k), branch-free over
 // them so that their FP64 chains interleave -- one candidate per thread left the kernel at 45 us for 25^4 candidates,
 // latency bound, with the per-CTA prologue (EpochDev copy, lines of sight) paid once per 128 candidates.
+// WSUM: also the score-weighted sums of the ECEF velocity candidates (BCM_VelMeasReduction, batchcorrmanifold.cu:1090-1347:
+// the same score, :1193-1197 the accumulation), for the weighted estimate.
 constexpr int kVelCand = 6;
-template <bool LP1>
+template <bool LP1, bool WSUM>
 __global__ void __launch_bounds__(kReduceBlock, 4)
 k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
             const double2* __restrict__ carr, double fs, int n_fft, int Wd, int NBd, int T, int lpower, int64_t Gv,
@@ -319,12 +324,18 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
         if (!act[k]) continue;
         const int64_t j = base + (int64_t)k * kReduceBlock;
         vscores[j] = score[k];
+        if (WSUM) {                                              // the ECEF velocity of the candidate (:1138-1141)
+            v[0] += score[k] * (vc[k].ex + K_OEDOT * e.center[1]);
+            v[1] += score[k] * (vc[k].ey - K_OEDOT * e.center[0]);
+            v[2] += score[k] * vc[k].ez;
+            v[3] += score[k] * vc[k].pt;
+        }
         v[4] += score[k];
         if (score[k] > mx) { mx = score[k]; mi = (double)j; }    // increasing index order: the lowest index wins ties
     }
-    block_reduce_store_vals<1>(v, mx, mi, (double)oow, blk_partial);
+    block_reduce_store_vals<WSUM ? 5 : 1>(v, mx, mi, (double)oow, blk_partial);
     // last CTA: arg-max over all candidates + BCM_MakeVelMeas (zVal[4:8], RVal rows 4-7, batchcorrmanifold.cu:2030-2068)
-    if (take_last_ticket(ticket)) finish_velocity(blk_partial, gridDim.x, e, vgrid_all, zval, rval, res);
+    if (take_last_ticket(ticket)) finish_velocity(blk_partial, gridDim.x, e, vgrid_all, zval, rval, res, WSUM);
 }
 
 // =============================================================================================
@@ -582,8 +593,13 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     const int nblk = (int)((c->Gv + kReduceBlock * kVelCand - 1) / (kReduceBlock * kVelCand));
 #define DPE_VEL_ARGS c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd, c->T, c->cfg.lpower, c->Gv, c->vscores, \
                      c->vblk_partial, c->ticket + 3, c->vgrid, c->zval, c->rval, c->result
-    if (c->cfg.lpower == 1) k_score_vel<true><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
-    else k_score_vel<false><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+    if (c->vel_weighted) {
+        if (c->cfg.lpower == 1) k_score_vel<true, true><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+        else k_score_vel<false, true><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+    } else {
+        if (c->cfg.lpower == 1) k_score_vel<true, false><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+        else k_score_vel<false, false><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+    }
 #undef DPE_VEL_ARGS
     c->launches += 3;
     prof_end(c, s);
@@ -595,7 +611,7 @@ int kernel_attr_vel(const char* name, cudaFuncAttributes* a) {
     DPE_KATTR("k_carr_partial", k_carr_partial);
     DPE_KATTR("k_carr_partial_direct", k_carr_partial_direct);
     DPE_KATTR("k_carr_finalize", k_carr_finalize);
-    DPE_KATTR("k_score_vel", k_score_vel<true>);
+    DPE_KATTR("k_score_vel", (k_score_vel<true, false>));
     DPE_KATTR("k_brute_vel", k_brute_vel);
     DPE_KATTR("k_vel_pair_bins", k_vel_pair_bins);
     DPE_KATTR("k_vel_plane", k_vel_plane);

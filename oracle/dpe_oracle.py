@@ -462,6 +462,33 @@ def vel_meas_ml(carr_scores, grid, center, enu2ecef, sat_states, time_dim, carr_
                 f_idx=f_idx, c_idx=c_idx, valid=valid)
 
 
+def vel_meas_reduction(carr_scores, grid, center, enu2ecef, sat_states, time_dim, carr_freq,
+                       doppler_sign, fs, n_fft, lpower=1, n_blocks=8, n_threads=64):
+    """The reference's DORMANT score-weighted velocity estimate exactly as written: BCM_VelMeasReduction
+    (batchcorrmanifold.cu:1090-1347) + BCM_ReduceAndVelMeas (:1525-1667), launch shape <<<8, 64>>> then <<<1, 8>>>
+    (:2555-2566, commented out there; oracle/ref_driver.cu -DREF_WEIGHTED launches them).  The per-candidate score is
+    BCM_VelMeasML's (middle time-grid satellite state, :1149; line of sight to the grid centre, :1161-1168); the
+    estimate is  z[4:8] = sum_i score_i (v_i, drift_i) / sum_i score_i  over the ECEF velocity candidates (:1193-1197,
+    :1658-1661).  Returns dict(z[4], parts[n_blocks][5], sum_score, scores[Gv])."""
+    idx_base, idxo, f_idx, c_idx, valid = vel_bins(
+        grid, center, enu2ecef, sat_states, time_dim, carr_freq, doppler_sign, fs, n_fft)
+    scores, _ = pos_scores_from_bins(carr_scores, idxo, f_idx, c_idx, valid, lpower)
+    g = np.asarray(grid, np.float64)
+    R = np.asarray(enu2ecef, np.float64)
+    vx = R[0] * g[:, 0] + R[1] * g[:, 1] + R[2] * g[:, 2] + center[4]      # :1138-1141
+    vy = R[3] * g[:, 0] + R[4] * g[:, 1] + R[5] * g[:, 2] + center[5]
+    vz = R[6] * g[:, 0] + R[7] * g[:, 1] + R[8] * g[:, 2] + center[6]
+    vd = g[:, 3] + center[7]
+    w = np.stack([scores * vx, scores * vy, scores * vz, scores * vd, scores], axis=1)
+    stride = n_blocks * n_threads
+    tid = np.arange(g.shape[0]) % stride
+    parts = np.zeros((n_blocks, 5))
+    for b in range(n_blocks):
+        parts[b] = w[(tid // n_threads) == b].sum(axis=0)
+    tot = parts.sum(axis=0)
+    return dict(z=tot[:4] / tot[4], parts=parts, sum_score=tot[4], scores=scores)
+
+
 # --------------------------------------------------------------------------
 # Brute-force identity (SURVEY section 8 a'): direct time-domain correlation
 # against the blended replica; used to validate the north-star kernel's

@@ -132,12 +132,17 @@ def main():
         name = "ref_grid_t%d_n%d.npz" % (a.gen_grid, a.n)
     if a.weighted:                                         # BatchCorrManifold in and out + the dormant estimator's results
         import re
-        drop = ("iq", "carr_scores_win", "sat_raw", "ri_end", "pos_scores")
+        drop = ("iq", "sat_raw", "ri_end", "pos_scores")
         pack = {k: v for k, v in pack.items() if not re.match(r"^e\d+_", k) or re.sub(r"^e\d+_", "", k) not in drop}
         for e in range(a.epochs):
             pack["e%d_zval_weighted" % e] = np.fromfile(os.path.join(dump, "e%03d_zval_weighted.bin" % e), dtype=np.float64)
             pack["e%d_weighted_parts" % e] = np.fromfile(os.path.join(dump, "e%03d_weighted_parts.bin" % e),
                                                          dtype=np.float64).reshape(8, 5)
+            # the velocity twins (BCM_VelMeasReduction + BCM_ReduceAndVelMeas) on the module's CarrScores
+            pack["e%d_zval_weighted_vel" % e] = np.fromfile(os.path.join(dump, "e%03d_zval_weighted_vel.bin" % e),
+                                                            dtype=np.float64)
+            pack["e%d_weighted_vel_parts" % e] = np.fromfile(os.path.join(dump, "e%03d_weighted_vel_parts.bin" % e),
+                                                             dtype=np.float64).reshape(8, 5)
         name = "ref_weighted_n%d.npz" % a.n
     if a.lpower != 1:                                      # BatchCorrManifold in and out: enough to pin sum |v|^L
         import re

@@ -23,8 +23,9 @@
 // lies, so that its DORMANT score-weighted estimator -- BCM_PosMeasReduction (:816-1056) +
 // BCM_ReduceAndPosMeas (:1365-1510), launches commented out at :2547-2567 -- can be launched on the
 // module's own device buffers after every BatchCorrManifold::Update, with exactly the arguments of the
-// commented launch.  Dumps e<epoch>_zval_weighted.bin (4 doubles) and e<epoch>_weighted_parts.bin
-// (8 x weightState_t {a,b,c,d,score}).
+// commented launch.  Dumps e<epoch>_zval_weighted.bin (8 doubles: position-clock, velocity-drift) and
+// e<epoch>_weighted_parts.bin / e<epoch>_weighted_vel_parts.bin (8 x weightState_t {a,b,c,d,score} each); the velocity
+// twins BCM_VelMeasReduction (:1090-1347) + BCM_ReduceAndVelMeas (:1525-) are launched the same way.
 #ifdef REF_WEIGHTED
 #include "batchcorrmanifold.cu"
 #endif
@@ -55,7 +56,7 @@ static void dump_host(const std::string& dir, int epoch, const char* name, const
 // adds no data: only a door to the protected members of the module the reference flow created
 class BcmProbe : public dsp::BatchCorrManifold {
   public:
-    int RunWeighted(double z[4], double parts[40]) {
+    int RunWeighted(double z[8], double parts[40], double vparts[40]) {
         double *z_d = NULL, *R_d = NULL;
         if (cudaMalloc((void**)&z_d, 16 * sizeof(double)) != cudaSuccess) return -1;
         if (cudaMalloc((void**)&R_d, 64 * sizeof(double)) != cudaSuccess) return -1;
@@ -69,8 +70,18 @@ class BcmProbe : public dsp::BatchCorrManifold {
                                sizeof(dsp::utils::weightState_t<double>) * threadsPerMeasRedBlock, posStream>>>(
             weightedPosStates_d, threadsPerMeasRedBlock, z_d, R_d);
         if (cudaStreamSynchronize(posStream) != cudaSuccess) return -2;
-        cudaMemcpy(z, z_d, 4 * sizeof(double), cudaMemcpyDeviceToHost);
+        // batchcorrmanifold.cu:2555-2560 and :2565-2566, verbatim arguments
+        BCM_VelMeasReduction<<<threadsPerMeasRedBlock, threadsPerVelManiBlock,
+                               sizeof(dsp::utils::weightState_t<double>) * threadsPerVelManiBlock, velStream>>>(
+            satStates_d, carrScores_d, xCurr_d, gridVelLocs_d, enu2ecefMat_d, carrFrequency_d, txTimePtr_d, *rxTimePtr,
+            numChan, currSamplingFreq, *numfftPointsPtr, dopplerSign_d, weightedVelStates_d);
+        BCM_ReduceAndVelMeas<<<1, threadsPerMeasRedBlock,
+                               sizeof(dsp::utils::weightState_t<double>) * threadsPerMeasRedBlock, velStream>>>(
+            weightedVelStates_d, threadsPerMeasRedBlock, z_d, R_d);
+        if (cudaStreamSynchronize(velStream) != cudaSuccess) return -4;
+        cudaMemcpy(z, z_d, 8 * sizeof(double), cudaMemcpyDeviceToHost);
         cudaMemcpy(parts, weightedPosStates_d, 40 * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(vparts, weightedVelStates_d, 40 * sizeof(double), cudaMemcpyDeviceToHost);
         cudaFree(z_d);
         cudaFree(R_d);
         return cudaGetLastError() == cudaSuccess ? 0 : -3;
@@ -101,11 +112,13 @@ class RefHarness : public dsp::DPEFlow {
                     cudaStreamSynchronize(cuStream);
                     DumpOutputs(out, e, W, dump == 2);
 #ifdef REF_WEIGHTED
-                    double zw[4], parts[40];
-                    int wr = static_cast<BcmProbe*>(static_cast<dsp::BatchCorrManifold*>(Mods[i]))->RunWeighted(zw, parts);
+                    double zw[8], parts[40], vparts[40];
+                    int wr = static_cast<BcmProbe*>(static_cast<dsp::BatchCorrManifold*>(Mods[i]))->RunWeighted(zw, parts, vparts);
                     if (wr) { fprintf(stderr, "weighted kernels failed (%d)\n", wr); exit(6); }
-                    dump_host(out, e, "zval_weighted", zw, sizeof(zw));
+                    dump_host(out, e, "zval_weighted", zw, 4 * sizeof(double));
+                    dump_host(out, e, "zval_weighted_vel", zw + 4, 4 * sizeof(double));
                     dump_host(out, e, "weighted_parts", parts, sizeof(parts));
+                    dump_host(out, e, "weighted_vel_parts", vparts, sizeof(vparts));
 #endif
                 }
             }

@@ -280,9 +280,15 @@ def _weighted_gold():
                   cp_start=k("cp_start"), cp_ref=k("cp_ref"), rc_end=k("rc_end"), cp_end=k("cp_end"),
                   cp_ref_tow=k("cp_ref_tow"), rx_time=float(k("rx_time")[0]), center=k("x_kk1"), enu2ecef=k("enu2ecef"),
                   sat_states=k("sat_states").reshape(-1, 8), doppler_sign=1, S=S, fs=fs, time_dim=T)
-        out.append(dict(ep=ep, win=w[..., 0] + 1j * w[..., 1], tx_time=k("tx_time"), z=k("zval_weighted"),
-                        parts=k("weighted_parts"), z_ml=k("zval")))
-    return dict(C=C, T=T, S=S, W=W, fs=fs, grid=g["grid"], epochs=out)
+        rec = dict(ep=ep, win=w[..., 0] + 1j * w[..., 1], tx_time=k("tx_time"), z=k("zval_weighted"),
+                   parts=k("weighted_parts"), z_ml=k("zval"))
+        if "e%d_zval_weighted_vel" % e in g.files:          # the velocity twins (golden regenerated in round 2)
+            Wd = int(g["Wd"])
+            cw = k("carr_scores_win").reshape(C, 2 * Wd + 2, 2)
+            rec.update(carr_win=cw[..., 0] + 1j * cw[..., 1], z_vel=k("zval_weighted_vel"), vel_parts=k("weighted_vel_parts"))
+        out.append(rec)
+    return dict(C=C, T=T, S=S, W=W, fs=fs, grid=g["grid"], epochs=out, Wd=int(g["Wd"]), n_fft=int(g["n_fft"]),
+                vel_dim=int(g["vel_dim"]))
 
 
 def test_oracle_weighted_estimator_matches_the_reference_kernels():
@@ -307,6 +313,25 @@ def test_oracle_weighted_estimator_matches_the_reference_kernels():
         assert abs(r2["sum_score"] / e["parts"][:, 4].sum() - 1.0) < 1e-5
         # and it is a different estimate from the arg-max the reference actually publishes
         assert np.max(np.abs(e["z"] - e["z_ml"][:4])) > 1e-3
+
+
+def test_oracle_weighted_velocity_estimator_matches_the_reference_kernels():
+    """BCM_VelMeasReduction <<<8,64>>> + BCM_ReduceAndVelMeas <<<1,8>>> (batchcorrmanifold.cu:1090-1347, 1525-1667; dormant,
+    launches commented out at :2555-2566), executed by oracle/_ref/ref_dpe_weighted on the module's own CarrScores."""
+    wg = _weighted_gold()
+    C, Wd, n_fft = wg["C"], wg["Wd"], wg["n_fft"]
+    vgrid, _ = H.synth.uniform_grid(wg["vel_dim"], 1.0)
+    assert all("z_vel" in e for e in wg["epochs"])
+    for e in wg["epochs"]:
+        ep = e["ep"]
+        full = np.zeros((C, n_fft), complex)
+        full[:, n_fft // 2 - Wd: n_fft // 2 - Wd + 2 * Wd + 2] = e["carr_win"]
+        r = orc.vel_meas_reduction(full, vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"], wg["T"], ep["fi"],
+                                   ep["doppler_sign"], wg["fs"], n_fft)
+        assert np.max(np.abs(r["z"] - e["z_vel"])) < 1e-9                        # m/s
+        assert np.max(np.abs(r["parts"] - e["vel_parts"]) / np.abs(e["vel_parts"][:, 4:5])) < 1e-11
+        # and it is a different estimate from the arg-max the reference actually publishes
+        assert np.max(np.abs(e["z_vel"] - e["z_ml"][4:8])) > 1e-3
 
 
 @pytest.mark.gpu

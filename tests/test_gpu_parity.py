@@ -462,6 +462,41 @@ def test_brute_force_velocity_needs_its_flag(capi):
     ctx.close()
 
 
+@pytest.mark.parametrize("fs,prns", [(2.5e6, synth.PRNS_8), (10.0e6, synth.PRNS_12)])
+def test_weighted_velocity_estimate_matches_oracle(capi, fs, prns):
+    """DPE_EST_WEIGHTED on the velocity manifold (the reference's dormant BCM_VelMeasReduction + BCM_ReduceAndVelMeas;
+    the oracle's restatement is pinned to those kernels in test_golden_ref.py): zVal[4:8] = sum s v / sum s."""
+    sc = H.scenario(fs, prns)
+    grid, tg = synth.uniform_grid(3, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(9, (0.5, 0.5, 0.5, 0.25))
+    center = sc.rx_state(sc.cfg.rx_time0 + sc.cfg.T).copy()
+    center[4:] += (1.0, -0.5, 0.5, 0.3)
+    ep = sc.epoch_inputs(0, center=center, time_grid=tg)
+    iq = sc.block(0)
+    bcs = orc.batch_corr_scores(iq, ep["prn"], ep["rc_start"], ep["ri_start"], ep["fc"], ep["fi"], ep["cp_start"],
+                                ep["cp_ref"], ep["fs"], want_carrier=True)
+    ref = orc.vel_meas_reduction(bcs["carr_scores"], vgrid, ep["center"], ep["enu2ecef"], ep["sat_states"],
+                                 ep["time_dim"], ep["fi"], ep["doppler_sign"], ep["fs"], bcs["n_fft"])
+    ctx = capi.Context(fs=fs, S=ep["S"], max_chan=len(prns), G=grid.shape[0], time_dim=len(tg), lag_halfwidth=16,
+                       Gv=vgrid.shape[0], dopp_halfwidth=64)
+    ctx.grid_set(grid)
+    ctx.vel_grid_set(vgrid)
+    r_ml = ctx.epoch_run(iq, ep, with_vel=1)
+    r_w = ctx.epoch_run(iq, ep, with_vel=3)
+    vs = ctx.copy_out(capi.PTR_VEL_SCORES, np.float64, vgrid.shape[0])
+    assert np.max(np.abs(vs - ref["scores"]) / ref["scores"]) < SCORE_RTOL
+    assert np.max(np.abs(np.array(r_w.z[4:8]) - ref["z"])) < 1e-6           # m/s: FP32 carrier spectrum under an FP64 mean
+    assert r_w.vel_argmax == r_ml.vel_argmax and r_w.vel_max_score == r_ml.vel_max_score
+    assert np.array_equal(np.array(r_w.z[:4]), np.array(r_ml.z[:4]))
+    assert np.max(np.abs(np.array(r_w.z[4:8]) - np.array(r_ml.z[4:8]))) > 1e-3     # a different estimate from the arg-max
+    # stage by stage: the same through dpe_score_vel_est
+    ctx.score_vel_est(capi.EST_WEIGHTED)
+    assert list(ctx.result_fetch().z[4:8]) == list(r_w.z[4:8])
+    ctx.score_vel_est(capi.EST_ARGMAX)
+    assert list(ctx.result_fetch().z[4:8]) == list(r_ml.z[4:8])
+    ctx.close()
+
+
 def test_velocity_needs_its_grid(capi):
     ctx = _ctx(capi, 5000, 2, 16, 1, 2.5e6)
     with pytest.raises(capi.DpeError) as e:
