@@ -299,10 +299,11 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec);
     if (c->prof_ev) {
-        for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(c->prof_ev[i]);
+        for (int i = 0; i < 2 * kProfMax; ++i)
+            if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
-        delete[] c->prof_stage;
     }
+    delete[] c->prof_stage;
     delete c;
     return DPE_OK;
 }
@@ -766,7 +767,8 @@ static int enqueue_epoch(dpe_ctx* c, const int16_t* iq, const dpe_epoch* ep, con
 // (scoring path, estimator, velocity, channel count, communicator) and replayed; every kernel argument of the chain is a
 // context-owned buffer (the block is always copied into the packet in this mode), so a replay needs no update.
 static int launch_epoch_graph(dpe_ctx* c, int score_mode, int est_mode, int with_vel, cudaStream_t s) {
-    const uint64_t key = 1u | (uint64_t)score_mode << 1 | (uint64_t)est_mode << 2 | (uint64_t)(with_vel & 3) << 40 |
+    // (pkt_used < 2^29 for S <= 2^26: bits 13..41; the velocity mode sits above it)
+    const uint64_t key = 1u | (uint64_t)score_mode << 1 | (uint64_t)est_mode << 2 | (uint64_t)(with_vel & 3) << 60 |
                          (uint64_t)c->epoch_C << 4 | (uint64_t)(c->comm != nullptr) << 12 | (uint64_t)c->pkt_used << 13;
     if (!c->graph_exec || c->graph_key != key) {
         if (c->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec); c->graph_exec = nullptr; }
@@ -1011,11 +1013,12 @@ int dpe_device_count(void) {
 int dpe_profile_enable(dpe_ctx* c, int on) {
     DPE_REQUIRE(c, DPE_EINVAL, "null context");
     DevGuard guard(c->cfg.device);
-    if (on && !c->prof_ev) {
-        c->prof_ev = new (std::nothrow) cudaEvent_t[2 * kProfMax];
-        c->prof_stage = new (std::nothrow) int[kProfMax];
+    if (on) {
+        if (!c->prof_ev) c->prof_ev = new (std::nothrow) cudaEvent_t[2 * kProfMax]();      // null handles: destroy skips them
+        if (!c->prof_stage) c->prof_stage = new (std::nothrow) int[kProfMax]();
         DPE_REQUIRE(c->prof_ev && c->prof_stage, DPE_ENOMEM, "out of host memory");
-        for (int i = 0; i < 2 * kProfMax; ++i) DPE_CUDA(cudaEventCreate(&c->prof_ev[i]));
+        for (int i = 0; i < 2 * kProfMax; ++i)
+            if (!c->prof_ev[i]) DPE_CUDA(cudaEventCreate(&c->prof_ev[i]));
     }
     c->prof_on = on ? 1 : 0;
     c->prof_n = 0;
