@@ -454,7 +454,7 @@ k_score_pairs(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         __stcs(&scores[j], score);
     }
     block_reduce_store(score, j + grid_offset, p, active, oow, blk_partial);
-    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial, fold);
+    if (take_last_ticket(ticket)) finish_position_partial<2>(blk_partial, gridDim.x, grid, e, grid_offset, partial, fold);
 }
 
 size_t brute_smem_bytes(int) {

@@ -177,7 +177,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     if (cfg->flags & DPE_FLAG_KEEP_CHIP_IDX) DPE_ALLOC(c->chip_idx, C * S);
     DPE_ALLOC(c->idx_next, C);
     DPE_ALLOC(c->no_flip, C);
-    DPE_ALLOC(c->cpart, C * c->nchunk * 2 * c->NLp);
+    DPE_ALLOC(c->cacc, C * c->NLp * 4);
     DPE_ALLOC(c->cs, C * c->NL);
     DPE_ALLOC(c->grid, G * 4);
     DPE_ALLOC(c->scores, G);
@@ -217,7 +217,8 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
         DPE_ALLOC(c->carr, C * c->NBd);
         DPE_ALLOC(c->dc_part, 2 * c->nchunk);
         DPE_ALLOC(c->bb, C * S);
-        DPE_ALLOC(c->vpart, C * c->vnchunk * c->NBd);
+        DPE_ALLOC(c->vacc, C * c->NBd * 2);
+        DPE_ALLOC(c->vticket, DPE_MAX_CHAN);
         DPE_ALLOC(c->vblk_partial, ((cfg->Gv + kReduceBlock - 1) / kReduceBlock) * 8);
         if (cfg->flags & DPE_FLAG_BRUTE_VEL) {
             const size_t NBv = 2 * c->Wd + 1, Gv = (size_t)cfg->Gv;
@@ -259,6 +260,7 @@ int dpe_ctx_create(dpe_ctx** out, const dpe_cfg* cfg) {
     { const char* sp = getenv("DPE_BRUTE_SKIP_PAD"); c->brute_skip_pad = !(sp && sp[0] == '0'); }
     { const char* cd = getenv("DPE_CARR_DIRECT"); c->carr_direct = (cd && cd[0] == '1'); }
     { const char* lk = getenv("DPE_LK_CAND"); const int v = lk ? atoi(lk) : 0; c->lk_cand_forced = (v == 3 || v == 4 || v == 6) ? v : 0; }
+    { const char* pd = getenv("DPE_PDL"); c->use_pdl = !(pd && pd[0] == '0'); }
     c->iq = c->iq_own;
     int rc = launch_gen_ca(c, 0);
     if (!rc) rc = launch_gen_time(c, 0);
@@ -274,10 +276,10 @@ int dpe_ctx_destroy(dpe_ctx* c) {
     cudaDeviceSynchronize();
     if (c->comm) dpe_comm_destroy(c);
     void* ptrs[] = {c->pkt, c->ca, c->sat_geo, c->tidx, c->chan_ticket, c->xw, c->rs, c->chip_idx, c->idx_next, c->no_flip,
-                    c->cpart, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
+                    c->cacc, c->cs, c->bx, c->brd, c->grid, c->scores, c->blk_partial, c->partial,
                     c->zval, c->rval, c->result, c->ticket, c->pair_k, c->pair_a, c->pair_v, c->hist, c->blk_hist,
                     c->bucket_base, c->group_base, c->hdr, c->ent_j, c->ent_a, c->n_groups, c->tail_part, c->tail_ticket, c->dbg_f, c->dbg_alpha,
-                    c->vgrid, c->vscores, c->carr, c->dc_part, c->bb, c->vpart, c->vblk_partial, c->gathered,
+                    c->vgrid, c->vscores, c->carr, c->dc_part, c->bb, c->vacc, c->vticket, c->vblk_partial, c->gathered,
                     c->vbb, c->vpair_k, c->vpair_a, c->vpair_v, c->vhist, c->vblk_hist, c->vbucket_base, c->vgroup_base,
                     c->vhdr, c->vent_j, c->vent_a, c->vn_groups};
     for (void* p : ptrs)

@@ -259,19 +259,33 @@ __device__ __forceinline__ bool take_last_ticket(unsigned int* counter) {
 
 // all threads of one CTA (a power of two, <= kReduceBlock): r[0..4] sums, r[5]/r[6] max / arg-max (lowest index on ties), r[7] sum;
 // valid in thread 0 on return
+template <int kRound = 4>
 __device__ __forceinline__ void reduce_all_partials(const double* __restrict__ blk, int n_blk, double (&r)[8]) {
     __shared__ double shr[kReduceBlock][8];
     r[0] = r[1] = r[2] = r[3] = r[4] = 0.0; r[5] = -1.0; r[6] = 9.0e18; r[7] = 0.0;
-#pragma unroll 4
-    for (int b = threadIdx.x; b < n_blk; b += blockDim.x) {
-        const double* q = blk + (size_t)b * 8;
-        double v[8];
+    // rounds of kRound blocks per thread (4; 2 in the 64-register pair kernels), all loads of a round issued before the first sum: the partials come from other SMs
+    // (L2, ~0.7 us a round trip), and a loop that the compiler could not unroll (the trip count is dynamic) paid that once per
+    // block -- 3 of the 5 us the last CTA of k_score_lookup spent here (profiles/r02ae_phase_stamps.txt).  Same order of
+    // summation as before: block b0 + k * blockDim + tid for k = 0, 1, 2, ...
+    for (int b0 = 0; b0 < n_blk; b0 += kRound * (int)blockDim.x) {
+        double2 v[kRound][4];
+        bool ok[kRound];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcg(q + k);          // written by other CTAs: bypass L1
+        for (int k = 0; k < kRound; ++k) {
+            const int b = b0 + k * (int)blockDim.x + (int)threadIdx.x;
+            ok[k] = b < n_blk;
+            const double2* q = reinterpret_cast<const double2*>(blk + (size_t)(ok[k] ? b : 0) * 8);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) r[k] += v[k];
-        r[7] += v[7];
-        if (v[5] > r[5] || (v[5] == r[5] && v[6] < r[6])) { r[5] = v[5]; r[6] = v[6]; }
+            for (int j = 0; j < 4; ++j) v[k][j] = __ldcg(q + j);       // written by other CTAs: bypass L1
+        }
+#pragma unroll
+        for (int k = 0; k < kRound; ++k) {
+            if (!ok[k]) continue;
+            r[0] += v[k][0].x; r[1] += v[k][0].y; r[2] += v[k][1].x; r[3] += v[k][1].y; r[4] += v[k][2].x;
+            r[7] += v[k][3].y;
+            const double m5 = v[k][2].y, m6 = v[k][3].x;
+            if (m5 > r[5] || (m5 == r[5] && m6 < r[6])) { r[5] = m5; r[6] = m6; }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) shr[threadIdx.x][k] = r[k];
@@ -324,21 +338,24 @@ struct FoldEst { int est_mode; double* zval; double* rval; double* res; };
 
 // per-rank partial of the position manifold: sums, max / arg-max, and the arg-max candidate's state
 // (BCM_MakePosMeas, batchcorrmanifold.cu:1990-2000)
+template <int kRound = 4>
 __device__ __forceinline__ void finish_position_partial(const double* __restrict__ blk, int n_blk,
                                                         const double* __restrict__ grid, const EpochDev& e,
                                                         int64_t grid_offset, double* __restrict__ partial,
                                                         const FoldEst& fold) {
     double r[8];
-    reduce_all_partials(blk, n_blk, r);
+    __shared__ double sp[kPartialLen];                    // the partial, also handed to the folded estimate from here (not read back from global)
+    reduce_all_partials<kRound>(blk, n_blk, r);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) partial[k] = r[k];
-        for (int k = 8; k < kPartialLen; ++k) partial[k] = 0.0;
+        for (int k = 0; k < 8; ++k) sp[k] = r[k];
+        for (int k = 8; k < kPartialLen; ++k) sp[k] = 0.0;
         if (r[5] >= 0.0) {
             const Cand p = cand_ecef(e, grid + 4 * ((int64_t)r[6] - grid_offset));
-            partial[8] = p.px; partial[9] = p.py; partial[10] = p.pz; partial[11] = p.pt;
+            sp[8] = p.px; sp[9] = p.py; sp[10] = p.pz; sp[11] = p.pt;
         }
-        if (fold.est_mode >= 0) finalize_estimate(partial, 1, fold.est_mode, fold.zval, fold.rval, fold.res);
+        for (int k = 0; k < kPartialLen; ++k) partial[k] = sp[k];
+        if (fold.est_mode >= 0) finalize_estimate(sp, 1, fold.est_mode, fold.zval, fold.rval, fold.res);
     }
 }
 

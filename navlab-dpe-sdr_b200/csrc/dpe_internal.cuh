@@ -13,7 +13,8 @@
 //   brd       float  [C][skewX(S_pad)]  chosen replica (flip applied) by position pair:
 //                                       (d[p], d[p+1], r[p], r[p+1]), d[p] = r[p-1] - r[p] (circular),
 //                                       zero beyond S; same float4 skew
-//   cpart     double2[C][NCHUNK][2][NLp] per-chunk partial correlograms (A: n<idxNext, B: rest)
+//   cacc      int64  [C][NLp][4]        correlogram totals in 2^-19 fixed point: (A.re, A.im, B.re, B.im) per lag, A: n<idxNext, B: rest
+//                                       (integer atomics from every chunk's CTA: order-independent; cleared by the reader)
 //   cs        double2[C][NL]            fft-shifted "CodeScores" window, lag k = l - W
 //   grid      double [G][4]             candidates (ENU metres + clock metres)
 //   scores    double [G]                "PosScores"
@@ -36,7 +37,10 @@
 
 namespace dpe {
 
-constexpr int kCorrChunk = 1024;       // samples per partial-correlogram block (k_prep_corr; 512 was tried: 31 us instead of 26)
+#ifndef DPE_CORR_CHUNK
+#define DPE_CORR_CHUNK 1024
+#endif
+constexpr int kCorrChunk = DPE_CORR_CHUNK;   // samples per partial-correlogram block (k_prep_corr)
 constexpr int kCarrChunk = 1024;       // samples per partial carrier-spectrum block (k_carr_partial)
 constexpr int kLagTile = 8;            // lags per thread in the correlogram kernel
 constexpr int kPartialLen = DPE_PARTIAL_LEN;
@@ -44,6 +48,7 @@ constexpr int kReduceBlock = 128;
 constexpr int kSortBlock = 128;        // candidates per CTA of the pair sort (k_pair_bins / k_scatter)
 constexpr int kProfMax = 8192;
 constexpr int kPinSlots = 8;
+constexpr double kFixScale = 524288.0;  // 2^19: fixed-point scale of the chunk-partial accumulators (k_prep_corr, k_carr_partial)
 
 // brute-force kernel geometry
 constexpr int kBfNC = 32;              // candidates per warp (one group)
@@ -60,6 +65,40 @@ constexpr int kBfLag = 1;               // a stage is refilled this many tiles a
 // sort and the reductions of one epoch then run UNDER the k_brute of the other.
 #define DPE_SIDE128 __launch_bounds__(128, 6)
 #define DPE_SIDE256 __launch_bounds__(256, 6)
+
+// Phase stamps of the single-wave kernels (probe builds only: make VARIANT=phase adds -DDPE_PHASE_TIMING; the product
+// build compiles these to nothing).  Thread 0 of a CTA keeps %globaltimer (ns) at every mark and prints the differences.
+#ifdef DPE_PHASE_TIMING
+#define DPE_PT_DECL unsigned long long pt_[10]; int pt_n_ = 0
+#define DPE_PT_MARK() do { if (threadIdx.x == 0 && pt_n_ < 10) { unsigned long long t_; \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); pt_[pt_n_++] = t_; } } while (0)
+#define DPE_PT_PRINT(tag, sel) do { if (threadIdx.x == 0 && (sel)) { unsigned int sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); \
+        printf("PT %s cta %d,%d sm %u t0 %llu :", tag, (int)blockIdx.x, (int)blockIdx.y, sm_, pt_[0]); \
+        for (int q_ = 1; q_ < pt_n_; ++q_) printf(" %llu", pt_[q_] - pt_[0]); printf("\n"); } } while (0)
+#else
+#define DPE_PT_DECL do { } while (0)
+#define DPE_PT_MARK() do { } while (0)
+#define DPE_PT_PRINT(tag, sel) do { } while (0)
+#endif
+
+// Programmatic dependent launch (sm_90+): a scoring kernel launched with launch_dep(..., pdl = true) may start while the
+// kernel before it on the stream is still running -- its prologue (per-channel constants, candidate states) overlaps the
+// producer's tail -- and calls grid_dep_wait() before its first read of what the producer writes.  The producer calls
+// grid_dep_trigger() at its start (all of its CTAs are resident by then: nothing it needs is taken away).  Without the
+// launch attribute both calls are no-ops.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // Device copy of the per-epoch parameters (+ values derived on the device).
 struct EpochDev {
@@ -102,7 +141,7 @@ struct dpe_ctx {
     double* sat_geo;                   // dpe::SatGeo [C][T]: centre-relative geometry per satellite state (DPE_SAT_PER_TIME)
     float2* xw; int8_t* rs; int16_t* chip_idx;
     int32_t* idx_next; int32_t* no_flip;
-    double2* cpart; double2* cs;
+    long long* cacc; double2* cs;      // cacc [maxC][NLp][4]
     float *bx, *brd;
     int64_t bx_stride, brd_stride;     // floats per sample-plane copy (8 copies per channel) / per replica plane
     double* grid; double* scores;
@@ -124,7 +163,7 @@ struct dpe_ctx {
     int64_t* dbg_f; double* dbg_alpha;
     // velocity (section 8 f-1)
     double* vgrid; double* vscores; double2* carr;       // [Gv][4], [Gv], [C][NBd]
-    long long* dc_part; float2* bb; double2* vpart; double* vblk_partial;   // [nchunk][2] DC sums per chunk; bb = conj(carrier) plane [C][S]
+    long long* dc_part; float2* bb; long long* vacc; unsigned int* vticket; double* vblk_partial;   // vacc [maxC][NBd][2]: carrier-spectrum totals, 2^-19 fixed point; vticket [maxC];   // [nchunk][2] DC sums per chunk; bb = conj(carrier) plane [C][S]
     // brute-force velocity manifold (DPE_FLAG_BRUTE_VEL): baseband plane with the chosen replica applied + pair lists
     float2* vbb; int64_t vS_pad;
     int16_t* vpair_k; float* vpair_a; float2* vpair_v;
@@ -150,6 +189,7 @@ struct dpe_ctx {
     cudaStream_t vel_stream; cudaEvent_t ev_fork, ev_vel; int fork_valid, vel_fork;
     int64_t launches;
     int lk_cand_forced;                // DPE_LK_CAND = 3 | 4 | 6: candidates per thread of k_score_lookup (0 = chosen per launch)
+    int use_pdl;                       // DPE_PDL (default 1): the scoring kernels of the lookup path are launched as programmatic dependents
     int want_sums;                     // k_score_pairs accumulates sum s*x (0 only inside an arg-max dpe_epoch_submit)
     // asynchronous epochs (dpe_epoch_submit / dpe_epoch_collect)
     cudaStream_t own_stream;

@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(256) k_gen_time(double fs, int S, double* __re
 //      the phase is reduced to [0, 1) cycles in FP64 and only then handed to the FP32 sincospif -- the
 //      range-reduced FP32 NCO the north star asks for (phase error <= 6e-8 cycle per sample, incoherent).
 //   2. each thread owns an 8-sample x 8-lag register tile (64 complex MACs per 23 shared loads), FP32 inside
-//      the chunk, FP64 across chunks; part A = samples before the nav-bit edge, part B = from the edge on, so
-//      no-flip = A + B and flipped = A - B without a second pass.
-//   3. the CTA that takes the last ticket of its channel adds the chunk partials in chunk order (FP64,
-//      fixed order), decides flip / no-flip on lag 0 (BCS_ChooseCodeCorr, batchcorrscores.cu:499-543) and
-//      writes the window (BCS_cufftBatchShift, :554-584: cs[l] <-> shifted bin l - W + S/2).
+//      the chunk, exact 64-bit fixed point across chunks (integer atomics: order-independent); part A = samples
+//      before the nav-bit edge, part B = from the edge on, so no-flip = A + B and flipped = A - B without a second pass.
+//   3. the CTA that takes the last ticket of its channel reads the channel's totals, decides flip / no-flip on
+//      lag 0 (BCS_ChooseCodeCorr, batchcorrscores.cu:499-543) and writes the window (BCS_cufftBatchShift,
+//      :554-584: cs[l] <-> shifted bin l - W + S/2).
 // xw / rs (and the conjugate carrier cc for the carrier branch) still go to HBM once: the brute-force planes and the
 // velocity manifold read them.
 // ---------------------------------------------------------------------------
@@ -90,7 +90,7 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
             const EpochDev* __restrict__ ep, double fs, int S, int W, int NL, int NLp, int nchunk,
             float2* __restrict__ xw, int8_t* __restrict__ rs, int16_t* __restrict__ chip_idx,
             int32_t* __restrict__ idx_next, long long* __restrict__ dc_part, float2* __restrict__ cc,
-            double2* __restrict__ cpart, double2* __restrict__ cs, int32_t* __restrict__ no_flip,
+            long long* __restrict__ cacc, double2* __restrict__ cs, int32_t* __restrict__ no_flip,
             unsigned int* __restrict__ chan_ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_edge;
@@ -99,6 +99,9 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     const int c = blockIdx.y;
     const EpochDev& e = *ep;
     if (c >= e.C) return;
+    DPE_PT_DECL;
+    DPE_PT_MARK();                                    // [0] start
+    grid_dep_trigger();                               // a dependent scoring kernel may set itself up beside this one
     const int chunk = blockIdx.x;
     const int n0 = chunk * kCorrChunk;
     const int nx = kCorrChunk + NLp + 8;             // halo: lags -W .. -W+NLp-1 (+7 slack)
@@ -115,6 +118,7 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
         if (chunk == 0) idx_next[c] = en;
     }
     __syncthreads();
+    DPE_PT_MARK();                                    // [1] code table + edge in shared memory
 
     const double fc = e.fc[c], rc = e.rc_start[c], fi = e.fi[c], ri = e.ri_start[c];
     // carrier branch (velocity manifold): the CTAs of channel 0 also sum the raw samples of their chunk -- the DC sum of
@@ -125,7 +129,7 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
     // the kernel sat in "long scoreboard": 3.3 stalled warps per issue at 16 % occupancy); 2 x 5 x 128 covers the 1024
     // samples of the chunk and the halo of the usual lag windows in two rounds of loads
     constexpr int kPrepBatch = 5;
-    for (int i0 = threadIdx.x; i0 < nx; i0 += kPrepBatch * blockDim.x) {
+    for (int i0 = threadIdx.x; i0 < nx; i0 += kPrepBatch * (int)blockDim.x) {
         double tq[kPrepBatch];
         short2 vq[kPrepBatch];
         int nq[kPrepBatch];
@@ -172,6 +176,7 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
         }
     }
     __syncthreads();
+    DPE_PT_MARK();                                    // [2] samples wiped into the shared tile
 
     int edge = s_edge;
     if (!(edge > 0 && edge < S)) edge = S;           // no edge in block: everything is part A
@@ -187,13 +192,25 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
             dc_part[2 * chunk] = si; dc_part[2 * chunk + 1] = sq;
         }
     }
+    // One tile = (run of 8 lags, range of 8-sample runs): 64 complex MACs per lane and step in registers, then the 32 sums
+    // of the tile -- 8 lags x (A, B) x (re, im) -- go through a halving butterfly (31 shuffles; lane L ends up with the
+    // whole-warp sum of value L) and every lane adds its value to the channel's FIXED-POINT accumulator with one 64-bit
+    // integer atomic: integer addition is associative, so the total does not depend on the order the CTAs arrive in
+    // (bit-identical from run to run), and no per-chunk partials travel through HBM to a serial reduction at the end.
+    // (Before: cpart[C][nchunk][2][NLp] in FP64 and a last CTA per channel that walked the 49 chunks of its 34 lags --
+    // 10 of the kernel's 28 us, profiles/r02ae_phase_stamps.txt.)  Scale 2^19: an FP32 partial of magnitude >= 16 is
+    // represented exactly, |partial| < 2^27 and nchunk <= 2^16 keep the total below 2^62.
+    // Lag runs are dealt to the warps whole while a full round of them is left; the remaining ones (5 runs on 4 warps at
+    // W = 16) are cut into one quarter of the samples per warp, so that no warp works while the others wait.
     const int n_lag_runs = NLp / kLagTile;
-    for (int lr = warp; lr < n_lag_runs; lr += (int)(blockDim.x >> 5)) {
+    const int nw = (int)(blockDim.x >> 5);
+    long long* const acc_c = cacc + (size_t)c * NLp * 4;
+    auto run_tile = [&](const int lr, const int sr_begin, const int sr_end) {
         float2 accA[kLagTile], accB[kLagTile];
 #pragma unroll
         for (int l = 0; l < kLagTile; ++l) { accA[l] = make_float2(0.f, 0.f); accB[l] = accA[l]; }
 #pragma unroll 1
-        for (int sr = lane; sr < kCorrChunk / 8; sr += 32) {
+        for (int sr = sr_begin + lane; sr < sr_end; sr += 32) {
             const int m = sr * 8;                     // local sample of the run
             float r[8];
 #pragma unroll
@@ -225,56 +242,58 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
                 }
             }
         }
+        float v[4 * kLagTile];                        // value 4 l + {0, 1, 2, 3} = A.re, A.im, B.re, B.im of lag lr*8 + l
 #pragma unroll
-        for (int l = 0; l < kLagTile; ++l) {
+        for (int l = 0; l < kLagTile; ++l) { v[4 * l] = accA[l].x; v[4 * l + 1] = accA[l].y; v[4 * l + 2] = accB[l].x; v[4 * l + 3] = accB[l].y; }
+        static_assert(4 * kLagTile == 32, "one value per lane after the butterfly");
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                accA[l].x += __shfl_xor_sync(0xffffffffu, accA[l].x, o);
-                accA[l].y += __shfl_xor_sync(0xffffffffu, accA[l].y, o);
-                accB[l].x += __shfl_xor_sync(0xffffffffu, accB[l].x, o);
-                accB[l].y += __shfl_xor_sync(0xffffffffu, accB[l].y, o);
+        for (int o = 16, n = 16; o > 0; o >>= 1, n >>= 1) {
+            const bool up = (lane & o) != 0;          // lanes with bit o set keep the upper half of the values
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const float keep = up ? v[j + n] : v[j];
+                const float send = up ? v[j] : v[j + n];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
         }
-        if (lane == 0) {
-            double2* out = cpart + (((size_t)c * nchunk + chunk) * 2) * NLp + lr * kLagTile;
-#pragma unroll
-            for (int l = 0; l < kLagTile; ++l) {
-                out[l] = make_double2((double)accA[l].x, (double)accA[l].y);
-                out[NLp + l] = make_double2((double)accB[l].x, (double)accB[l].y);
-            }
-        }
-    }
+        const long long q = __double2ll_rn((double)v[0] * kFixScale);
+        if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc_c + lr * 32 + lane), (unsigned long long)q);
+    };
+    const int n_whole = (n_lag_runs / nw) * nw;
+    for (int lr = warp; lr < n_whole; lr += nw) run_tile(lr, 0, kCorrChunk / 8);
+    constexpr int kSteps = kCorrChunk / 8 / 32;       // 32-lane steps per lag run
+    static_assert(kSteps >= 1 && kCorrChunk % 256 == 0, "whole warps of 8-sample runs");
+    for (int it = warp; it < (n_lag_runs - n_whole) * kSteps; it += nw)
+        run_tile(n_whole + it / kSteps, (it % kSteps) * 32, (it % kSteps) * 32 + 32);
 
     // ---- last CTA of this channel: chunk partials -> CodeScores window ----
+    DPE_PT_MARK();                                    // [3] thread 0's (warp 0's) lag runs done
     __threadfence();
     __syncthreads();
+    DPE_PT_MARK();                                    // [4] every warp done
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(&chan_ticket[c], 1u);
         s_last = (t == (unsigned int)nchunk - 1);
         if (s_last) chan_ticket[c] = 0;               // self-resetting for the next launch
     }
     __syncthreads();
+    DPE_PT_MARK();                                    // [5] ticket taken
+    DPE_PT_PRINT("prep", !s_last && (blockIdx.x % 12) == 0 && (blockIdx.y % 7) == 0);
     if (!s_last) return;
     __threadfence();
     const bool has_edge = (s_edge > 0) && (s_edge < S);
-    // Sums over the chunks, part A and part B of every lag: one warp per lag, lanes stride the chunks, xor-tree in FP64 (a
-    // fixed order).  (The first version walked the 49 chunks serially per lag, twice -- once in thread 0 for the decision
-    // on lag 0, once per lag -- about 100 dependent L2 round trips at the end of a latency-bound kernel.)
+    // the channel's accumulators are complete: back to FP64 (exact: a power-of-two scale), and cleared for the next launch
     double2* sumA = reinterpret_cast<double2*>(smem_raw);      // the shared tiles are dead by now: [NL] + [NL]
     double2* sumB = sumA + NL;
-    for (int l = warp; l < NL; l += (int)(blockDim.x >> 5)) {
-        double ax = 0, ay = 0, bx_ = 0, by = 0;
-        for (int ch = lane; ch < nchunk; ch += 32) {
-            const double2* p = cpart + (((size_t)c * nchunk + ch) * 2) * NLp + l;
-            const double2 a = __ldcg(p), b2 = __ldcg(p + NLp);
-            ax += a.x; ay += a.y; bx_ += b2.x; by += b2.y;
+    for (int l = threadIdx.x; l < NLp; l += blockDim.x) {
+        longlong2* p = reinterpret_cast<longlong2*>(acc_c + 4 * l);
+        if (l < NL) {
+            const longlong2 a = __ldcg(p), b2 = __ldcg(p + 1);
+            sumA[l] = make_double2((double)a.x * (1.0 / kFixScale), (double)a.y * (1.0 / kFixScale));
+            sumB[l] = make_double2((double)b2.x * (1.0 / kFixScale), (double)b2.y * (1.0 / kFixScale));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o);
-            bx_ += __shfl_xor_sync(0xffffffffu, bx_, o); by += __shfl_xor_sync(0xffffffffu, by, o);
-        }
-        if (lane == 0) { sumA[l] = make_double2(ax, ay); sumB[l] = make_double2(bx_, by); }
+        p[0] = make_longlong2(0, 0);
+        p[1] = make_longlong2(0, 0);
     }
     __syncthreads();
     // lag 0 decides (:512); every thread evaluates the same expression on the same sums
@@ -286,6 +305,8 @@ k_prep_corr(const int16_t* __restrict__ iq, const int8_t* __restrict__ ca, const
         cs[(size_t)c * NL + l] = keep ? make_double2(a.x + b2.x, a.y + b2.y)     // no-flip = A + B
                                       : make_double2(a.x - b2.x, a.y - b2.y);    // flipped = A - B (only chosen when an edge exists)
     }
+    DPE_PT_MARK();                                    // [6] window written (last CTA of the channel)
+    DPE_PT_PRINT("prep-last", true);
 }
 
 // ---------------------------------------------------------------------------
@@ -357,13 +378,14 @@ int launch_gen_time(dpe_ctx* c, cudaStream_t s) {
 int launch_prepare(dpe_ctx* c, cudaStream_t s) {
     const int S = (int)c->S;
     const int nx = kCorrChunk + c->NLp + 8;
-    const size_t smem = (size_t)(nx + (nx >> 3) + 1) * sizeof(float2) +
-                        (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float) + 1024;
+    size_t smem = (size_t)(nx + (nx >> 3) + 1) * sizeof(float2) +
+                  (size_t)(kCorrChunk + (kCorrChunk >> 3) + 1) * sizeof(float) + 1024;
+    if (smem < 2 * sizeof(double2) * (size_t)c->NL) smem = 2 * sizeof(double2) * (size_t)c->NL;     // the last CTA's sums reuse the tiles
     dim3 grid(c->nchunk, c->epoch_C);
     prof_begin(c, DPE_STAGE_PREPARE, s);
     k_prep_corr<<<grid, 128, smem, s>>>(c->iq, c->ca, c->tidx, c->ep, c->cfg.fs, S, c->W, c->NL, c->NLp, c->nchunk,
                                         c->xw, c->rs, c->chip_idx, c->idx_next, c->Gv > 0 ? c->dc_part : nullptr,
-                                        c->Gv > 0 ? c->bb : nullptr, c->cpart, c->cs, c->no_flip, c->chan_ticket);
+                                        c->Gv > 0 ? c->bb : nullptr, c->cacc, c->cs, c->no_flip, c->chan_ticket);
     c->launches++;
     DPE_CUDA(cudaGetLastError());
     prof_end(c, s);

@@ -27,7 +27,11 @@ namespace dpe {
 // 763 CTAs on 592 slots -- 1.29 waves, the second one 29 % full -- while 6 per thread is 509 CTAs: one wave.
 // (Tried: 64-thread CTAs, 8 per SM, so that the 0.86 wave spreads 6-7 CTAs instead of 3-4 over every SM: 41.6 us against
 // 37.5 -- the finer spread does not pay for twice the prologues and block partials.  Tried: 6 candidates per thread at 96 /
-// 80 registers, 5 / 6 CTAs per SM: 37.3 / 39.4 us against 33.5 -- the spills cost more than the extra warps hide.)
+// 80 registers, 5 / 6 CTAs per SM: 37.3 / 39.4 us against 33.5 -- the spills cost more than the extra warps hide.  Tried:
+// 7 per thread at 168 registers, 3 CTAs per SM -- 437 CTAs on 444 slots, every SM holds 3, where 6 per thread leaves 65 SMs
+// with 4 CTAs and 83 with 3 and the kernel ends with those that hold 4 (phase stamps, profiles/r02ae_phase_stamps.txt):
+// 34.7 us against 33.8, and 58.9 against 54.3 us for the velocity branch with the same change in k_score_vel -- 12 warps per SM
+// hide less of the FP64 / conversion latency than the even load gives back.)
 template <int SAT_MODE, int WITH_SUMS, int kLkCand, bool LP1>
 __global__ void __launch_bounds__(kReduceBlock, (kLkCand == 3) ? 8 : 4)
 k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep, const double* __restrict__ sat,
@@ -38,6 +42,8 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     __shared__ EpochDev e;
     __shared__ ChanConst cc[DPE_MAX_CHAN];
     __shared__ SatGeo geo_mid[DPE_MAX_CHAN];
+    DPE_PT_DECL;
+    DPE_PT_MARK();                                    // [0] start
     for (int i = threadIdx.x; i < (int)(sizeof(EpochDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&e)[i] = reinterpret_cast<const uint32_t*>(ep)[i];
     __syncthreads();
@@ -45,6 +51,7 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     if (SAT_MODE == DPE_SAT_MIDDLE)
         for (int c = threadIdx.x; c < e.C; c += blockDim.x) geo_mid[c] = make_sat_geo(e, sat + ((size_t)c * T + T / 2) * 8);
     __syncthreads();
+    DPE_PT_MARK();                                    // [1] per-channel constants in shared memory
     const int64_t base = (int64_t)blockIdx.x * (kReduceBlock * kLkCand) + threadIdx.x;
     CandRel rel[kLkCand];
     double pt[kLkCand], score[kLkCand];
@@ -66,6 +73,8 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
     }
     int oow = 0;
     const double rx_time = e.rx_time, Sd = (double)S;
+    DPE_PT_MARK();                                    // [2] candidates read and turned
+    grid_dep_wait();                                  // the correlogram (cs) and, per time index, the geometry table come from the kernels before
     for (int c = 0; c < e.C; ++c) {
         const ChanConst kc = cc[c];
         const double rc_end = e.rc_end[c];
@@ -102,6 +111,7 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
             oow += (act[k] && !b.ok) ? 1 : 0;
         }
     }
+    DPE_PT_MARK();                                    // [3] all channels scored (warp 0)
     // this thread's candidates in increasing index order: strict > keeps the lowest index on ties
     double v[5] = {0, 0, 0, 0, 0}, mx = -1.0, mi = 9.0e18;
 #pragma unroll
@@ -119,7 +129,12 @@ k_score_lookup(const double* __restrict__ grid, const EpochDev* __restrict__ ep,
         if (score[k] > mx) { mx = score[k]; mi = (double)(j + grid_offset); }
     }
     block_reduce_store_vals<WITH_SUMS ? 5 : 1>(v, mx, mi, (double)oow, blk_partial);
-    if (take_last_ticket(ticket)) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial, fold);
+    DPE_PT_MARK();                                    // [4] block partial stored
+    const bool last = take_last_ticket(ticket);
+    DPE_PT_MARK();                                    // [5] ticket taken
+    if (last) finish_position_partial(blk_partial, gridDim.x, grid, e, grid_offset, partial, fold);
+    DPE_PT_MARK();                                    // [6] (last CTA) partials reduced, estimate written
+    DPE_PT_PRINT(last ? "look-last" : "look", last || (blockIdx.x % 60) == 0);
 }
 
 __global__ void __launch_bounds__(128) k_sat_geo(const EpochDev* __restrict__ ep, const double* __restrict__ sat, int T,
@@ -179,8 +194,9 @@ template <int SAT_MODE, int WITH_SUMS, int NC>
 static void launch_lk(dpe_ctx* c, int nblk, const SatGeo* tab, const FoldEst& fold, cudaStream_t s) {
 #define DPE_LK_ARGS c->grid, c->ep, c->sat, c->cs, c->cfg.fs, (int)c->S, c->W, c->NL, c->T, c->cfg.lpower, c->G, \
                     c->cfg.grid_offset, c->scores, c->blk_partial, c->ticket, c->partial, tab, fold
-    if (c->cfg.lpower == 1) k_score_lookup<SAT_MODE, WITH_SUMS, NC, true><<<nblk, kReduceBlock, 0, s>>>(DPE_LK_ARGS);
-    else k_score_lookup<SAT_MODE, WITH_SUMS, NC, false><<<nblk, kReduceBlock, 0, s>>>(DPE_LK_ARGS);
+    const bool pdl = c->use_pdl != 0;
+    if (c->cfg.lpower == 1) launch_dep(k_score_lookup<SAT_MODE, WITH_SUMS, NC, true>, nblk, kReduceBlock, 0, s, pdl, DPE_LK_ARGS);
+    else launch_dep(k_score_lookup<SAT_MODE, WITH_SUMS, NC, false>, nblk, kReduceBlock, 0, s, pdl, DPE_LK_ARGS);
 #undef DPE_LK_ARGS
 }
 

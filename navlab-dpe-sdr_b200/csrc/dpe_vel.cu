@@ -43,6 +43,37 @@ __device__ __forceinline__ float2 baseband(const float2* __restrict__ xw, const 
     return make_float2((x.x - (mean.x * k.x - mean.y * k.y)) * r, (x.y - (mean.x * k.y + mean.y * k.x)) * r);
 }
 
+// Chunk partials of the carrier spectrum meet in a per-channel FIXED-POINT accumulator (64-bit integer atomics, scale 2^19:
+// integer addition is associative, so the spectrum is bit-identical whatever order the CTAs arrive in -- the same scheme as
+// the correlogram's, dpe_prepare.cu); the CTA that takes the channel's last ticket converts the totals to CarrScores and
+// clears the accumulator for the next launch.  (Before: vpart[C][nchunk][NBd] in FP64 and a k_carr_finalize launch, 6 us.)
+__device__ __forceinline__ void carr_add(long long* __restrict__ acc_c, int l, double re, double im) {
+    const long long qr = __double2ll_rn(re * kFixScale), qi = __double2ll_rn(im * kFixScale);
+    if (qr != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc_c + 2 * l), (unsigned long long)qr);
+    if (qi != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc_c + 2 * l + 1), (unsigned long long)qi);
+}
+// all threads of the CTA, after their carr_add calls
+__device__ __forceinline__ void carr_tail(long long* __restrict__ acc_c, unsigned int* __restrict__ ticket, int nchunk, int NBd,
+                                          double2* __restrict__ carr_c) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == (unsigned int)nchunk - 1);
+        if (s_last) *ticket = 0;                       // self-resetting for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int l = threadIdx.x; l < NBd; l += blockDim.x) {
+        longlong2* p = reinterpret_cast<longlong2*>(acc_c + 2 * l);
+        const longlong2 a = __ldcg(p);
+        carr_c[l] = make_double2((double)a.x * (1.0 / kFixScale), (double)a.y * (1.0 / kFixScale));
+        *p = make_longlong2(0, 0);
+    }
+}
+
 // One CTA per (1024-sample chunk, channel); warp w owns bins w, w+8, ...; lanes stride the samples.
 // bb[n] = zw[n] * chosen replica[n]  with zw = (x - mean) * conj(carrier) from k_prepare
 // (BCS_SubtractDCOffset :470-485, BCS_ChoosyBatchMultiplyAndPad :422-452).
@@ -53,10 +84,12 @@ __global__ void DPE_SIDE256
 k_carr_partial_direct(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part,
                       const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
                       const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
-                      int n_fft, int nchunk, int n_dc, double2* __restrict__ vpart) {
+                      int n_fft, int nchunk, int n_dc, long long* __restrict__ vacc, unsigned int* __restrict__ vticket,
+                      double2* __restrict__ carr) {
     __shared__ float2 xs[kCarrChunk];
     const int c = blockIdx.y;
     if (c >= ep->C) return;
+    grid_dep_trigger();
     const int chunk = blockIdx.x, n0 = chunk * kCarrChunk;
     const bool flip = !no_flip[c];
     const int edge = idx_next[c];
@@ -92,8 +125,9 @@ k_carr_partial_direct(const float2* __restrict__ xw, const float2* __restrict__ 
             ar += __shfl_xor_sync(0xffffffffu, ar, o);
             ai += __shfl_xor_sync(0xffffffffu, ai, o);
         }
-        if (lane == 0) vpart[((size_t)c * nchunk + chunk) * NBd + l] = make_double2((double)ar, (double)ai);
+        if (lane == 0) carr_add(vacc + (size_t)c * NBd * 2, l, (double)ar, (double)ai);
     }
+    carr_tail(vacc + (size_t)c * NBd * 2, vticket + c, nchunk, NBd, carr + (size_t)c * NBd);
 }
 
 // The same partial spectrum through block moments.  One CTA per (1024-sample chunk, channel):
@@ -109,11 +143,13 @@ __global__ void DPE_SIDE256
 k_carr_partial(const float2* __restrict__ xw, const float2* __restrict__ cc, const long long* __restrict__ dc_part,
                const int8_t* __restrict__ rs, const int32_t* __restrict__ idx_next,
                const int32_t* __restrict__ no_flip, const EpochDev* __restrict__ ep, int S, int Wd, int NBd,
-               int n_fft, int nchunk, int n_dc, double2* __restrict__ vpart) {
+               int n_fft, int nchunk, int n_dc, long long* __restrict__ vacc, unsigned int* __restrict__ vticket,
+               double2* __restrict__ carr) {
     extern __shared__ float2 qpart[];                           // [4][NBd] quarter partials
     __shared__ float2 mom[kCarrChunk / 32][4];
     const int c = blockIdx.y;
     if (c >= ep->C) return;
+    grid_dep_trigger();
     const int chunk = blockIdx.x, n0 = chunk * kCarrChunk;
     const bool flip = !no_flip[c];
     const int edge = idx_next[c];
@@ -166,39 +202,19 @@ k_carr_partial(const float2* __restrict__ xw, const float2* __restrict__ cc, con
         double re = 0, im = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { re += (double)qpart[q * NBd + l].x; im += (double)qpart[q * NBd + l].y; }
-        vpart[((size_t)c * nchunk + chunk) * NBd + l] = make_double2(re, im);
+        carr_add(vacc + (size_t)c * NBd * 2, l, re, im);
     }
-}
-
-// one warp per bin, lanes stride the chunks, xor-tree (fixed order)
-__global__ void DPE_SIDE256
-k_carr_finalize(const double2* __restrict__ vpart, const EpochDev* __restrict__ ep, int NBd,
-                int nchunk, double2* __restrict__ carr) {
-    const int c = blockIdx.x;
-    if (c >= ep->C) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l = blockIdx.y * 8 + warp;
-    if (l >= NBd) return;
-    double re = 0, im = 0;
-    for (int ch = lane; ch < nchunk; ch += 32) {
-        const double2 p = vpart[((size_t)c * nchunk + ch) * NBd + l];
-        re += p.x; im += p.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
-    }
-    if (lane == 0) carr[(size_t)c * NBd + l] = make_double2(re, im);
+    carr_tail(vacc + (size_t)c * NBd * 2, vticket + c, nchunk, NBd, carr + (size_t)c * NBd);
 }
 
 // arg-max over all block partials + BCM_MakeVelMeas (all threads of the last CTA)
 // (weighted: BCM_ReduceAndVelMeas, batchcorrmanifold.cu:1658-1661 -- z = sum s v / sum s)
+template <int kRound = 4>
 __device__ __forceinline__ void finish_velocity(const double* __restrict__ blk_partial, int n_blk, const EpochDev& e,
                                                 const double* __restrict__ vgrid_all, double* __restrict__ zval,
                                                 double* __restrict__ rval, double* __restrict__ res, bool weighted = false) {
     double r[8];
-    reduce_all_partials(blk_partial, n_blk, r);
+    reduce_all_partials<kRound>(blk_partial, n_blk, r);
     if (threadIdx.x == 0) {
         const int64_t jm = (int64_t)r[6];
         const double* g = vgrid_all + 4 * jm;
@@ -276,6 +292,7 @@ __device__ __forceinline__ VelCand vel_cand(const EpochDev& e, const double* __r
 // latency bound, with the per-CTA prologue (EpochDev copy, lines of sight) paid once per 128 candidates.
 // WSUM: also the score-weighted sums of the ECEF velocity candidates (BCM_VelMeasReduction, batchcorrmanifold.cu:1090-1347:
 // the same score, :1193-1197 the accumulation), for the weighted estimate.
+// (7 per thread at 3 CTAs per SM, for an even 3 CTAs on every SM at 25^4 candidates, was slower: see k_score_lookup.)
 constexpr int kVelCand = 6;
 template <bool LP1, bool WSUM>
 __global__ void __launch_bounds__(kReduceBlock, 4)
@@ -304,6 +321,7 @@ k_score_vel(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep, c
     }
     const double nf = (double)n_fft;
     int oow = 0;
+    grid_dep_wait();                                  // the carrier spectrum comes from the kernel before
     for (int c = 0; c < e.C; ++c) {
         const VelChan u = vch[c];
         const double2* __restrict__ cc = carr + (size_t)c * NBd;
@@ -534,7 +552,7 @@ k_score_vpairs(const double* __restrict__ vgrid, const EpochDev* __restrict__ ep
     }
     double v5[5] = {0, 0, 0, 0, active ? score : 0.0};
     block_reduce_store_vals<1>(v5, active ? score : -1.0, active ? (double)j : 9.0e18, (double)oow, blk_partial);
-    if (take_last_ticket(ticket)) finish_velocity(blk_partial, gridDim.x, e, vgrid, zval, rval, res);
+    if (take_last_ticket(ticket)) finish_velocity<2>(blk_partial, gridDim.x, e, vgrid, zval, rval, res);
 }
 
 int vel_brute_set_attributes(dpe_ctx* c) {   // per context (device); not while a stream capture is open
@@ -584,24 +602,23 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
     const double x = 2.0 * 3.141592653589793 * (c->Wd + 1) * 15.5 / (double)c->n_fft;
     if (x * x * x * x / 24.0 < 2.0e-8 && c->n_fft <= (1 << 23) && !c->carr_direct)
         k_carr_partial<<<g2, 256, sizeof(float2) * 4 * c->NBd, s>>>(c->xw, c->bb, c->dc_part, c->rs, c->idx_next, c->no_flip,
-                                                                   c->ep, S, c->Wd, c->NBd, c->n_fft, c->vnchunk, c->nchunk, c->vpart);
+                                                                   c->ep, S, c->Wd, c->NBd, c->n_fft, c->vnchunk, c->nchunk, c->vacc,
+                                                                   c->vticket, c->carr);
     else
         k_carr_partial_direct<<<g2, 256, 0, s>>>(c->xw, c->bb, c->dc_part, c->rs, c->idx_next, c->no_flip, c->ep, S, c->Wd,
-                                                 c->NBd, c->n_fft, c->vnchunk, c->nchunk, c->vpart);
-    dim3 g3(C, (c->NBd + 7) / 8);
-    k_carr_finalize<<<g3, 256, 0, s>>>(c->vpart, c->ep, c->NBd, c->vnchunk, c->carr);
+                                                 c->NBd, c->n_fft, c->vnchunk, c->nchunk, c->vacc, c->vticket, c->carr);
     const int nblk = (int)((c->Gv + kReduceBlock * kVelCand - 1) / (kReduceBlock * kVelCand));
 #define DPE_VEL_ARGS c->vgrid, c->ep, c->sat, c->carr, c->cfg.fs, c->n_fft, c->Wd, c->NBd, c->T, c->cfg.lpower, c->Gv, c->vscores, \
                      c->vblk_partial, c->ticket + 3, c->vgrid, c->zval, c->rval, c->result
+#define DPE_VEL_LAUNCH(LP, WS) launch_dep(k_score_vel<LP, WS>, nblk, kReduceBlock, 0, s, c->use_pdl != 0, DPE_VEL_ARGS)
     if (c->vel_weighted) {
-        if (c->cfg.lpower == 1) k_score_vel<true, true><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
-        else k_score_vel<false, true><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+        if (c->cfg.lpower == 1) DPE_VEL_LAUNCH(true, true); else DPE_VEL_LAUNCH(false, true);
     } else {
-        if (c->cfg.lpower == 1) k_score_vel<true, false><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
-        else k_score_vel<false, false><<<nblk, kReduceBlock, 0, s>>>(DPE_VEL_ARGS);
+        if (c->cfg.lpower == 1) DPE_VEL_LAUNCH(true, false); else DPE_VEL_LAUNCH(false, false);
     }
+#undef DPE_VEL_LAUNCH
 #undef DPE_VEL_ARGS
-    c->launches += 3;
+    c->launches += 2;
     prof_end(c, s);
     DPE_CUDA(cudaGetLastError());
     return DPE_OK;
@@ -610,7 +627,6 @@ int launch_score_vel(dpe_ctx* c, cudaStream_t s) {
 int kernel_attr_vel(const char* name, cudaFuncAttributes* a) {
     DPE_KATTR("k_carr_partial", k_carr_partial);
     DPE_KATTR("k_carr_partial_direct", k_carr_partial_direct);
-    DPE_KATTR("k_carr_finalize", k_carr_finalize);
     DPE_KATTR("k_score_vel", (k_score_vel<true, false>));
     DPE_KATTR("k_brute_vel", k_brute_vel);
     DPE_KATTR("k_vel_pair_bins", k_vel_pair_bins);

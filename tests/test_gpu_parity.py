@@ -330,6 +330,39 @@ def test_epoch_run_host_buffers_and_determinism(capi):
     assert ctx.launch_count() > 0
 
 
+def test_chunk_totals_are_bit_reproducible_and_two_contexts_agree(capi):
+    """The chunk partials of the correlogram and of the carrier spectrum meet in fixed-point integer accumulators
+    (order-independent atomics, cleared by the CTA that reads them): CodeScores, CarrScores and both fixes are
+    bit-identical from epoch to epoch, between the kernel-by-kernel and the CUDA-graph call, and between two contexts."""
+    fs, prns = 2.5e6, synth.PRNS_8
+    sc = H.scenario(fs, prns)
+    grid, tg = synth.uniform_grid(5, (5.0, 5.0, 5.0, 6.0))
+    vgrid, _ = synth.uniform_grid(7, (0.5, 0.5, 0.5, 0.25))
+    eps = [sc.epoch_inputs(b, time_grid=tg) for b in (0, 1)]
+    blks = [sc.block(b) for b in (0, 1)]
+    C, S, W_, Wd = len(prns), eps[0]["S"], 16, 64
+    seen = []
+    for _ in range(2):
+        ctx = capi.Context(fs=fs, S=S, max_chan=C, G=grid.shape[0], time_dim=len(tg), lag_halfwidth=W_,
+                           Gv=vgrid.shape[0], dopp_halfwidth=Wd)
+        ctx.grid_set(grid)
+        ctx.vel_grid_set(vgrid)
+        for k in range(6):
+            blk, ep = blks[k % 2], eps[k % 2]                      # alternate two blocks: a stale accumulator would show
+            r = ctx.epoch_run(blk, ep, with_vel=1) if k % 3 else ctx.epoch_run_dist(blk, ep, with_vel=1)
+            cs = ctx.copy_out(capi.PTR_CODE_SCORES, np.float64, C * (2 * W_ + 2) * 2)
+            carr = ctx.copy_out(capi.PTR_CARR_SCORES, np.float64, C * (2 * Wd + 2) * 2)
+            seen.append((k % 2, cs.copy(), carr.copy(), tuple(r.z), r.max_score, r.vel_max_score))
+        ctx.close()
+    for b in (0, 1):
+        same = [x for x in seen if x[0] == b]
+        assert len(same) == 6
+        for x in same[1:]:
+            assert np.array_equal(x[1], same[0][1]) and np.array_equal(x[2], same[0][2])
+            assert x[3:] == same[0][3:]
+    assert not np.array_equal(seen[0][1], seen[1][1])              # the two blocks do differ
+
+
 # ---- velocity / clock-drift manifold (SURVEY.md 8 f-1) ------------------------------------------
 @pytest.mark.parametrize("fs,prns", [(2.5e6, synth.PRNS_8), (10.0e6, synth.PRNS_12)])
 def test_velocity_manifold_matches_oracle(capi, fs, prns):
