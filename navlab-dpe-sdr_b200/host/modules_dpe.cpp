@@ -305,6 +305,10 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
     if (sh->ctx) { dpe_ctx_destroy(sh->ctx); sh->ctx = nullptr; }
     const int64_t G_total = cfg.G_total;
     const int64_t per = (G_total + numGPUs - 1) / numGPUs;          // contiguous index ranges (sharding.py::shard_range)
+    if ((int64_t)(numGPUs - 1) * per >= G_total && numGPUs > 1) {   // checked before any rank thread exists: a rank that
+        std::cerr << "[" << ModuleName << "] more GPUs than grid points" << std::endl;   // never joins would leave the others in the communicator's rendezvous
+        return -1;
+    }
     cfg.G = std::min(per, G_total);
     cfg.grid_offset = 0;
     DPE_CALL(dpe_ctx_create(&sh->ctx, &cfg));
@@ -325,7 +329,6 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
             rc.grid_offset = std::min((int64_t)r * per, G_total);
             rc.G = std::min(per, G_total - rc.grid_offset);
             rc.Gv = 0;                                              // the velocity manifold runs on rank 0 only
-            if (rc.G < 1) { std::cerr << "[" << ModuleName << "] more GPUs than grid points" << std::endl; return -1; }
             std::vector<double> shard(grid.begin() + 4 * rc.grid_offset, grid.begin() + 4 * (rc.grid_offset + rc.G));
             pool->workers.emplace_back(&RankPool::Worker, pool, r, rc, std::move(shard), numGPUs,
                                        std::vector<unsigned char>(id, id + DPE_COMM_ID_BYTES));
