@@ -69,7 +69,7 @@ int Flow::StartModules() {
     for (size_t i = 0; i < Mods.size(); ++i)
         if (Mods[i]->Start((void*)&cuStream)) {
             std::cerr << "[Flow] Unable to start module " << Mods[i]->GetModuleName() << std::endl;
-            for (size_t j = 0; j < i; ++j) Mods[j]->Stop();
+            for (size_t j = 0; j <= i; ++j) Mods[j]->Stop();     // the one that failed too: it may hold what it got half way
             return -1;
         }
     started = true;

@@ -301,6 +301,7 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
         cfg.dopp_halfwidth = Wd;
     }
     SharedCtx* sh = SharedFor(cuFlowStream);
+    flowStream = cuFlowStream;                                      // from here on Stop() has something to release
     if (sh->pool) { sh->pool->Shutdown(); delete sh->pool; sh->pool = nullptr; }
     if (sh->ctx) { dpe_ctx_destroy(sh->ctx); sh->ctx = nullptr; }
     const int64_t G_total = cfg.G_total;
@@ -349,7 +350,6 @@ int BatchCorrManifold::Start(void* cuFlowStream) {
     DPE_CALL(dpe_stream_sync(stream));
     UpdateOutput(2, (int64_t)timeGrid.size(), timeGrid.data(), 0);
     UpdateOutput(3, cfg.G, const_cast<void*>(dpe_dev_ptr(sh->ctx, DPE_PTR_POS_SCORES)), 0);   // rank 0's shard
-    flowStream = cuFlowStream;
     Started = true;
     return 0;
 }
@@ -399,7 +399,8 @@ int BatchCorrManifold::Update(void* cuFlowStream) {
 }
 
 int BatchCorrManifold::Stop() {
-    if (Started && flowStream) SharedRelease(flowStream);
+    if (flowStream) SharedRelease(flowStream);                      // also after a Start() that failed half way
+    flowStream = nullptr;
     Started = false;
     return 0;
 }

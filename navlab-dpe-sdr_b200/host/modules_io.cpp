@@ -244,7 +244,8 @@ int SampleBlock::Update(void*) {
 }
 
 int SampleBlock::Stop() {
-    if (!Started) return 0;
+    // (also after a Start() that failed half way: the source, the buffers and the stream it got that far are released here)
+    if (!Started && fd < 0 && Blocks.empty() && !readerStream) return 0;
     KeepRunning = false;
     { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
     // a reader blocked in read() on an idle TCP sender must come back: shut the socket down first

@@ -448,3 +448,22 @@ def test_dpe_flow_sharded_over_gpus_equals_the_single_gpu_flow(flowapi, tmp_path
         assert sh.exec(c) == 0
     assert sh.run_blocking("rx", 1) != 0
     sh.close()
+
+
+def test_flow_start_failure_is_clean_and_repeatable(flowapi, tmp_path):
+    """A flow whose modules cannot all start (here: the grid file does not exist; on a box without a GPU the sample
+    ring fails first) returns an error from startflow, stops every module it had started -- the failing one included:
+    reader thread, buffers, stream, context -- and can be started again or destroyed without hanging."""
+    sc, grid, files = _write_scenario(tmp_path, 3, 1, first_block=0)
+    sh = flowapi.Shell()
+    for c in ["newflow dpe rx", "loadflow rx", 'setparam rx SampleBlock Filename "%s"' % files["dat"],
+              'setparam rx DPInit HandoffFilename "%s"' % files["handoff"],
+              'setparam rx DPInit RINEXFilename "%s"' % files["rinex"],
+              'setparam rx BatchCorrManifold LoadPosGridFilename "%s"' % str(tmp_path / "no_such_grid.csv"),
+              "setparam rx BatchCorrManifold LoadPosGrid true", "setparam rx BatchCorrManifold PosGridDimSize 3",
+              'setparam rx XECEFLogger Filename "%s"' % str(tmp_path / "X.csv")]:
+        assert sh.exec(c) == 0, c
+    assert sh.run_blocking("rx", 1) != 0
+    assert sh.run_blocking("rx", 1) != 0                 # nothing was left half started
+    assert sh.stats("rx")["run_count"] == 0
+    sh.close()
