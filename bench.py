@@ -613,6 +613,24 @@ def run_ours(args):
 _FLOW_FILES = {}
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _c_stdout_to_stderr():
+    """The console mirror answers commands on the process's stdout like the reference's console does ("Flow 0 (DPE)
+    created."); bench.py's stdout carries exactly one JSON line, so file descriptor 1 points at stderr while a flow runs."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def _flow_files(n_epochs):
     sc, grid, tg = build_workload("demo")
     d = "/tmp/dpe_bench_flow"
@@ -633,6 +651,11 @@ def flow_realtime(args, path):
     flowapi = dpe_pkg.submodule("flowapi")
     n_epochs = args.flow_epochs
     sc, d, files = _flow_files(n_epochs)
+    with _c_stdout_to_stderr():
+        return _flow_realtime(flowapi, sc, d, files, n_epochs, path)
+
+
+def _flow_realtime(flowapi, sc, d, files, n_epochs, path):
     sh = flowapi.Shell()
     cmds = ["newflow dpe rx", "loadflow rx",
             'setparam rx SampleBlock Filename "%s"' % files["dat"],
