@@ -353,7 +353,7 @@ int64_t dpe_launch_count(dpe_ctx* ctx);
 /* the context's own stream (cudaStream_t as void*): what dpe_epoch_submit launches on          */
 void* dpe_ctx_stream(dpe_ctx* ctx);
 /* registers per thread / dynamic+static shared bytes of a kernel of this library, by name
- * ("k_brute", "k_prepare", ...): lets a bench report whether the side kernels fit beside k_brute */
+ * ("k_brute", "k_prep_corr", ...): lets a bench report whether the side kernels fit beside k_brute */
 int dpe_kernel_attr(const char* kernel, int* regs, int* smem_bytes, int* max_threads);
 
 /* ---- runtime helpers for host code that does not link the CUDA runtime ------------
@@ -379,14 +379,14 @@ int dpe_device_count(void);
  * every bracket recorded since the last read to ms[stage] (DPE_N_STAGES entries),
  * the number of brackets to count[stage], and clears the record.                 */
 enum {
-    DPE_STAGE_PREPARE = 0,       /* k_prepare                                        */
-    DPE_STAGE_CORRELOGRAM = 1,   /* k_corr_partial + k_corr_finalize (+ replica plane)*/
+    DPE_STAGE_PREPARE = 0,       /* k_prep_corr: unpack, wipe-off, replica, correlogram window, flip choice */
+    DPE_STAGE_CORRELOGRAM = 1,   /* (nothing since round 2: the correlogram is finished inside k_prep_corr) */
     DPE_STAGE_LOOKUP = 2,        /* k_score_lookup (grid reduction fused, last CTA)  */
-    DPE_STAGE_BRUTE_BINS = 3,    /* k_pair_bins + k_bucket_scan + k_scatter          */
+    DPE_STAGE_BRUTE_BINS = 3,    /* k_pair_bins + k_block_scan + k_scatter           */
     DPE_STAGE_BRUTE_CORR = 4,    /* k_brute (the north-star kernel) alone            */
     DPE_STAGE_BRUTE_SCORE = 5,   /* k_score_pairs (grid reduction fused, last CTA)   */
     DPE_STAGE_ESTIMATE = 6,      /* k_finalize                                       */
-    DPE_STAGE_VELOCITY = 7,      /* velocity manifold: DC, baseband, windowed DFT, scoring */
+    DPE_STAGE_VELOCITY = 7,      /* velocity manifold: k_carr_partial + k_score_vel, or the brute-force chain */
     DPE_N_STAGES = 8
 };
 int dpe_profile_enable(dpe_ctx* ctx, int on);
