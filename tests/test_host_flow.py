@@ -5,6 +5,7 @@ startflow` end to end on synthetic files against the oracle closed loop and the 
 epochs (tests/golden/ref_epochs_n9.npz)."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -467,3 +468,44 @@ def test_flow_start_failure_is_clean_and_repeatable(flowapi, tmp_path):
     assert sh.run_blocking("rx", 1) != 0                 # nothing was left half started
     assert sh.stats("rx")["run_count"] == 0
     sh.close()
+
+
+def test_host_readers_survive_malformed_files(flowapi, tmp_path):
+    """Truncated, bit-flipped, shuffled and random handoff / RINEX / grid files: the readers return an error or a
+    result, never crash or hang (run in a child process so that a crash would fail this test, not the session)."""
+    import random
+    rnd = random.Random(20180704)
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    bases = {"handoff": open(os.path.join(here, "golden", "handoff_params_usrp6.csv"), "rb").read(),
+             "rinex": open(os.path.join(root, "navlab-dpe-sdr_b200", "data", "brdc_toe417600.18n"), "rb").read(),
+             "grid": b"\n".join(b"%f,%f,%f,%f" % (i, i + 1, i + 2, i + 3) for i in range(81))}
+    jobs = []
+    for kind, base in bases.items():
+        for t in range(25):
+            b = bytearray(base)
+            mode = t % 5
+            if mode == 0:
+                b = b[:rnd.randrange(0, len(b))]
+            elif mode == 1:
+                for _ in range(20):
+                    b[rnd.randrange(len(b))] = rnd.randrange(256)
+            elif mode == 2:
+                b = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 2000)))
+            elif mode == 3:
+                i = rnd.randrange(len(b))
+                b[i:i] = b"9" * rnd.randrange(1, 400)
+            else:
+                lines = bytes(b).split(b"\n")
+                rnd.shuffle(lines)
+                b = b"\n".join(lines[:rnd.randrange(1, len(lines) + 1)])
+            p = tmp_path / ("%s_%d" % (kind, t))
+            p.write_bytes(bytes(b))
+            jobs.append("%s %s" % (kind, p))
+    (tmp_path / "jobs.txt").write_text("\n".join(jobs))
+    child = ("import sys\nsys.path.insert(0, %r)\nimport dpe_pkg\nf = dpe_pkg.submodule('flowapi')\nn = 0\n"
+             "for line in open(sys.argv[1]):\n    kind, path = line.split()\n    try:\n"
+             "        {'handoff': f.read_handoff, 'grid': f.read_grid, 'rinex': lambda p: f.sat_position(p, 5, 417600.0)}[kind](path)\n"
+             "    except Exception:\n        pass\n    n += 1\nprint('done', n)\n" % root)
+    r = subprocess.run([sys.executable, "-c", child, str(tmp_path / "jobs.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and ("done %d" % len(jobs)) in r.stdout, r.stderr[-1000:]
